@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the FetalSynthGen per-sample generation path (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels)
+    python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
+
+One *step* = one batch of `--batch` (default 8) synthetic 256^3 volumes per GPU through the whole
+base pipeline (GMM -> warp+gamma+bias -> blur -> down-sample+noise -> up-sample /max), all
+stage probabilities forced to 1 (fixed work), Philox noise.  `value` = volumes/s with inputs
+resident in HBM; `e2e` = the same through the host-buffer API (H2D of segmentation + 4 seed
+volumes and D2H of image + segmentation inside the timed region).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "256^3 synth volumes/sec"
+UNIT = "volumes/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- synthetic inputs
+def draw_oracle_params(rs, shape, res=0.5):
+    """Drawn parameters for one sample in np_oracle.generate_base form (all gates on)."""
+    from fetalsyngen_b200.tables import make_affine_matrix, resample_size, resample_stds
+
+    q = {"mus": (25 + 200 * rs.rand(50)).astype(np.float32), "sigmas": (5 + 20 * rs.rand(50)).astype(np.float32), "gmm_noise": rs.randn(*shape).astype(np.float32), "flip": bool(rs.rand() < 0.5), "resolution": np.array([res] * 3)}
+    rot = (2 * 20 * rs.rand(3) - 20) / 180 * np.pi
+    q["A"] = make_affine_matrix(rot, 0.04 * rs.rand(3) - 0.02, 1 + 0.2 * rs.rand(3) - 0.1).astype(np.float32)
+    q["c2"] = (np.array(shape) - 1) / 2
+    s = [int(round((0.03 + 0.03 * rs.rand()) * v)) for v in shape]
+    q["Fsmall"] = (4 * rs.rand() * rs.randn(*s, 3)).astype(np.float32)
+    q["gamma"] = float(np.exp(0.1 * rs.randn()))
+    b = [max(int(round((0.004 + 0.016 * rs.rand()) * v)), 1) for v in shape]
+    q["bf_low"] = ((0.01 + 0.29 * rs.rand()) * rs.randn(*b)).astype(np.float32)
+    sp = res + 2 * res * rs.rand()
+    q["spacing"] = np.array([sp] * 3)
+    q["stds"] = resample_stds(q["spacing"], [res] * 3, rs.rand())
+    q["noise_std"] = float(5 + 10 * rs.rand())
+    q["noise"] = rs.randn(*[resample_size(v, res, sp) for v in shape]).astype(np.float32)
+    return q
+
+
+def _cpu_worker(args):
+    shape, seed, nvol = args
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import np_oracle as O
+    from fetalsyngen_b200.utils.phantom import label_phantom
+
+    seg, seeds = label_phantom(shape)
+    lab = sum(s.astype(np.int64) for s in seeds)
+    rs = np.random.RandomState(seed)
+    t = 0.0
+    for _ in range(nvol):
+        q = draw_oracle_params(rs, shape)
+        t0 = time.perf_counter()
+        out, sg, _ = O.generate_base(lab, seg, q)
+        O.scale_intensity(out)
+        t += time.perf_counter() - t0
+    return t
+
+
+def cpu_port_throughput(shape, workers: int, vols_per_worker: int, pool=None):
+    """volumes/s of the numpy port of the reference path on `workers` host processes."""
+    t0 = time.perf_counter()
+    if workers == 1 or pool is None:
+        _cpu_worker((shape, 0, vols_per_worker))
+        workers = 1
+    else:
+        pool.map(_cpu_worker, [(shape, i, vols_per_worker) for i in range(workers)])
+    dt = time.perf_counter() - t0
+    return workers * vols_per_worker / dt, dt
+
+
+def host_workers():
+    cores = os.cpu_count() or 1
+    try:
+        mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2**30
+    except Exception:
+        mem_gb = 16
+    return max(1, min(cores, 32, int(mem_gb // 6)))
+
+
+# ---------------------------------------------------------------------------------- reference arm
+def run_reference(args, shape):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    workers = host_workers()
+    pool = mp.get_context("spawn").Pool(workers) if workers > 1 else None
+    cpu_port_throughput((32, 32, 32), workers, 1, pool)  # worker start-up, imports, page-in (untimed)
+    vals = []
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_port_throughput(shape, workers, 1, pool)
+        vals.append(v)
+        t_all += dt
+    if pool is not None:
+        pool.close()
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"base pipeline, all stage probs=1, {shape[0]}^3 @0.5mm phantom; one step = {workers} volumes (1 per host process)", "shape": list(shape)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": f"{args.steps} x {workers} volumes, numpy port of the reference path (oracle/np_oracle.py), one process per volume"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------- our arm
+def build_generator(shape, device):
+    from fetalsyngen_b200.generator.augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
+    from fetalsyngen_b200.generator.deformation.affine_nonrigid import SpatialDeformation
+    from fetalsyngen_b200.generator.intensity.rand_gmm import ImageFromSeeds
+    from fetalsyngen_b200.generator.model import FetalSynthGen
+
+    labels = [0] + list(range(10, 50))
+    classes = [0] + [10] * 10 + [20] * 10 + [30] * 10 + list(range(40, 50))
+    return FetalSynthGen(
+        shape=list(shape), resolution=[0.5, 0.5, 0.5], device=device,
+        intensity_generator=ImageFromSeeds(1, 6, labels, classes),
+        spatial_deform=SpatialDeformation(20, 0.02, 0.1, list(shape), 1.0, True, 0.03, 0.06, 4, 0.5, device),
+        resampler=RandResample(1.0, 0.5, 1.5), bias_field=RandBiasField(1.0, 0.004, 0.02, 0.01, 0.3),
+        noise=RandNoise(1.0, 5, 15), gamma=RandGamma(1.0, 0.1),
+    )
+
+
+ALGO_BYTES_PER_VOXEL = {  # SURVEY.md section 8(d); n = coarse-grid voxels / N
+    "fsg_gmm": lambda r: 4 + 4,            # 4 seed bytes read + 4 B written (seed sum fused)
+    "fsg_warp": lambda r: 10,              # img 4 + seg 1 read, img 4 + seg 1 written
+    "fsg_blur3d": lambda r: 8,             # fused single pass (this round runs 3 passes = 24 B of real traffic)
+    "fsg_resample": lambda r: 4 + 4 * r,
+    "fsg_zoom": lambda r: 4 + 4 * r,
+    "fsg_zoom_minmax": lambda r: 4 * r,
+    "fsg_warp_shift": lambda r: 0,
+}
+
+
+def run_ours(args, shape):
+    import torch
+    import torch.distributed as dist
+
+    from fetalsyngen_b200 import _lib
+    from fetalsyngen_b200.utils.phantom import label_phantom
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    B = args.batch
+    nvox = int(np.prod(shape))
+    np.random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+
+    seg_h, seeds_h = label_phantom(shape)
+    gen = build_generator(shape, dev)
+    eng = gen.engine(shape)
+    seg_d = torch.from_numpy(seg_h).to(dev)
+    seeds_d = [torch.from_numpy(s).to(dev) for s in seeds_h]
+    out_img = torch.empty((B, *shape), dtype=torch.float32, device=dev)
+    out_seg = torch.empty((B, *shape), dtype=torch.uint8, device=dev)
+
+    def step():
+        gen.sample_batch([seg_d] * B, [seeds_d] * B, scale=True, out_img=out_img, out_seg=out_seg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.stats.reset()
+    _lib.stats.timing = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    _lib.stats.timing = False
+    per_call = _lib.stats.elapsed_ms()
+    launches = _lib.stats.total_calls()
+    clocks = sampler.stop() if rank == 0 else {}
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1000)
+
+    # ---- e2e through the host-buffer API
+    from fetalsyngen_b200.host_pipeline import HostPipeline
+
+    hp = HostPipeline(gen, B)
+    hp.set_inputs([seg_h] * B, [seeds_h] * B)
+    for _ in range(2):
+        hp.step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hp.step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA-event time inside the timed region)
+    peak, peak_src = peaks()
+    top = max(per_call.items(), key=lambda kv: kv[1][1])
+    name, (ncalls, tms) = top
+    r = 0.2  # mean coarse-grid fraction for spacing ~ U(0.5,1.5): E[(0.5/s)^3] ~ 0.2
+    algo = ALGO_BYTES_PER_VOXEL.get(name, lambda r: 0)(r) * nvox * B
+    achieved = algo / (tms / ncalls / 1000) / 1e9 if tms > 0 else 0.0
+    traffic = None
+    prof = ROOT / "profiles" / "dominant_kernel_traffic.json"
+    if prof.exists():
+        traffic = json.loads(prof.read_text()).get(name)
+
+    # ---- CPU baseline: bounded sample of the same workload on the host cores
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_port_throughput(shape, 1, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"1 volume of the same workload, numpy port of the reference path (oracle/np_oracle.py), {dt:.1f} s, single process"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[1]: batch of {B} volumes/GPU/step, {shape[0]}^3 @0.5mm phantom, deformation+GMM+gamma+bias+blur+resample+noise, all stage probs=1, Philox noise, ScaleIntensity fused", "shape": list(shape), "batch_per_gpu": B, "l2": f"inputs larger than L2 ({B * nvox * 4 / 2**20:.0f} MiB per buffer per step)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "per_call_ms": {k: round(v[1] / v[0], 4) for k, v in per_call.items()}},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--shape", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    shape = (args.shape,) * 3
+    if args.impl == "reference":
+        args.steps = min(args.steps, 3)
+        run_reference(args, shape)
+    else:
+        run_ours(args, shape)
+
+
+if __name__ == "__main__":
+    main()

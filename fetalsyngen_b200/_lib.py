@@ -1,0 +1,156 @@
+"""ctypes binding of libfsg.so (the C-ABI declared in include/fsg.h).
+
+The product path has no CPU fallback: if the library is missing or a launch fails, a
+``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libfsg.so"
+MAX_JOBS = 16
+MAX_TAPS = 127
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class Tab(C.Structure):
+    _fields_ = [("f", C.c_int16), ("c", C.c_int16), ("wc", _f32)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("sample", C.c_uint64), ("stage", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class GmmJob(C.Structure):
+    _fields_ = [("seed", _vp * 4), ("mus", _vp), ("sigmas", _vp), ("noise", _vp), ("out", _vp), ("labels_out", _vp),
+                ("rng", Rng), ("nlabels", _i32), ("_pad", _i32)]
+
+
+class WarpJob(C.Structure):
+    _fields_ = [("src_img", _vp), ("src_seg", _vp), ("src_img2", _vp), ("dst_img", _vp), ("dst_seg", _vp), ("dst_img2", _vp),
+                ("fsmall", _vp), ("ftab", _vp * 3), ("bf_low", _vp), ("btab", _vp * 3), ("shift", _vp),
+                ("A", _f32 * 9), ("c2", _f32 * 3), ("center", _f32 * 3), ("gamma", _f32),
+                ("fs", _i32 * 3), ("bs", _i32 * 3), ("mode", _i32), ("flip", _i32), ("has_gamma", _i32), ("_pad", _i32)]
+
+
+class BlurJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("tmp", _vp), ("taps", _vp * 3), ("ntaps", _i32 * 3), ("_pad", _i32)]
+
+
+class ResampleJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("tab", _vp * 3), ("noise", _vp), ("rng", Rng), ("noise_std", _f32), ("has_noise", _i32),
+                ("n", _i32 * 3), ("_pad", _i32)]
+
+
+class NoiseJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("noise", _vp), ("rng", Rng), ("noise_std", _f32), ("_pad", _i32)]
+
+
+class ZoomJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("tab", _vp * 3), ("minmax", _vp), ("n", _i32 * 3), ("post", _i32)]
+
+
+_STRUCTS = {"fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
+            "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
+
+# name -> (restype, argtypes); every symbol include/fsg.h declares
+SIGNATURES = {
+    "fsg_version": (C.c_int, []),
+    "fsg_last_error": (C.c_char_p, []),
+    "fsg_sizeof": (C.c_int, [C.c_char_p]),
+    "fsg_gmm": (C.c_int, [C.POINTER(GmmJob), C.c_int, _i64, _vp]),
+    "fsg_warp_shift": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_warp": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_warp_coords": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "fsg_blur3d": (C.c_int, [C.POINTER(BlurJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_resample": (C.c_int, [C.POINTER(ResampleJob), C.c_int] + [C.c_int] * 3 + [_vp]),
+    "fsg_add_noise": (C.c_int, [C.POINTER(NoiseJob), C.c_int, _i64, _vp]),
+    "fsg_zoom_minmax": (C.c_int, [C.POINTER(ZoomJob), C.c_int] + [C.c_int] * 3 + [_vp]),
+    "fsg_zoom": (C.c_int, [C.POINTER(ZoomJob), C.c_int] + [C.c_int] * 3 + [_vp]),
+    "fsg_minmax": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "fsg_scale_intensity": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "fsg_f32_to_u8": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fsg_u8_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fsg_u8_to_i64": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
+}
+
+_lib = None
+
+
+class FsgError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Load libfsg.so (building it with nvcc when absent and a compiler is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise FsgError(f"{LIB_PATH} is missing: run `python -m fetalsyngen_b200.build` (there is no CPU fallback)")
+        from . import build as _b
+
+        _b.build()
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    for cname, st in _STRUCTS.items():
+        got = lib.fsg_sizeof(cname.encode())
+        if got != C.sizeof(st):
+            raise FsgError(f"ABI mismatch for {cname}: library {got} bytes, binding {C.sizeof(st)} bytes")
+    _lib = lib
+    return lib
+
+
+class LaunchStats:
+    """Counts C-ABI calls and, when ``timing`` is on, brackets each call with CUDA events on the
+    launching stream (bench.py uses this for the per-kernel roofline)."""
+
+    def __init__(self):
+        self.calls: dict = {}
+        self.timing = False
+        self._events: list = []
+
+    def reset(self):
+        self.calls.clear()
+        self._events.clear()
+
+    def total_calls(self) -> int:
+        return sum(self.calls.values())
+
+    def elapsed_ms(self) -> dict:
+        """Per entry point: (number of calls, total device milliseconds). Synchronises."""
+        import torch
+
+        torch.cuda.synchronize()
+        out: dict = {}
+        for name, a, b in self._events:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + a.elapsed_time(b))
+        return out
+
+
+stats = LaunchStats()
+
+
+def call(name: str, *args):
+    lib = load()
+    stats.calls[name] = stats.calls.get(name, 0) + 1
+    if stats.timing:
+        import torch
+
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        stats._events.append((name, a, b))
+    else:
+        rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FsgError(f"{name} failed ({rc}): {lib.fsg_last_error().decode()}")

@@ -1,0 +1,354 @@
+"""Device engine: turns drawn per-sample parameters (``SamplePlan``) into batched launches of
+the libfsg kernels.  torch is used for device memory and streams only.
+
+Stage order and semantics follow ``FetalSynthGen.generate/augment``
+(reference ``fetalsyngen/generator/model.py:94-229``):
+  GMM -> warp(+flip, +gamma, +bias) -> blur -> down-sample(+noise) -> up-sample(/max)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tables import DeviceTables, resample_size, zoom_size
+
+STAGE_GMM, STAGE_NOISE = 1, 2
+
+
+@dataclass
+class SamplePlan:
+    """Everything the reference would draw for one sample (None = that gate is off)."""
+
+    mus: np.ndarray = None                # float32 [nlabels]
+    sigmas: np.ndarray = None             # float32 [nlabels]
+    gmm_noise: torch.Tensor | None = None  # injected N(0,1) draws [S], device (parity mode)
+    rng_seed: int = 0                     # Philox key (production mode)
+    sample_id: int = 0                    # Philox subsequence
+    deform: bool = False
+    flip: bool = False
+    A: np.ndarray | None = None           # float32 3x3
+    c2: np.ndarray | None = None          # float64 [3]
+    center: np.ndarray | None = None      # float32 [3] = (size-1)/2
+    fsmall: np.ndarray | None = None      # float32 [s0,s1,s2,3] (already scaled by nonlin_std)
+    gamma: float | None = None
+    bf_low: np.ndarray | None = None      # float32 [b0,b1,b2] (already scaled by bf_std)
+    spacing: np.ndarray | None = None     # float64 [3]
+    stds: np.ndarray | None = None        # float64 [3]
+    noise_std: float | None = None
+    noise: torch.Tensor | None = None     # injected draws [n0*n1*n2] or [S] (parity mode)
+    meta: dict = field(default_factory=dict)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t: torch.Tensor, dtype, device, name):
+    if t.device != device:
+        raise ValueError(f"{name}: expected a tensor on {device}, got {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+class SynthEngine:
+    """Owns the per-device tables and scratch volumes for volumes of one shape."""
+
+    def __init__(self, shape, resolution, device):
+        self.shape = tuple(int(s) for s in shape)
+        self.resolution = np.asarray(resolution, dtype=np.float64)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.FsgError(f"fetalsyngen_b200 runs on CUDA devices only (got device={device!r}); there is no CPU fallback")
+        if not torch.cuda.is_available():
+            raise _lib.FsgError("no CUDA device is available; fetalsyngen_b200 has no CPU fallback")
+        _lib.load()
+        self.nvox = int(np.prod(self.shape))
+        self.tables = DeviceTables(self.device)
+        self._scratch: dict = {}
+
+    # ------------------------------------------------------------------ memory
+    def scratch(self, name: str, batch: int, dtype=torch.float32, numel=None) -> torch.Tensor:
+        numel = self.nvox if numel is None else numel
+        key = (name, dtype)
+        t = self._scratch.get(key)
+        if t is None or t.shape[0] < batch or t.shape[1] < numel:
+            t = torch.empty((batch, numel), dtype=dtype, device=self.device)
+            self._scratch[key] = t
+        return t
+
+    def upload(self, arrays: list[np.ndarray]) -> list[torch.Tensor]:
+        """One H2D copy for a list of small float32 host arrays; returns device views."""
+        sizes = [int(a.size) for a in arrays]
+        offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(int)
+        host = torch.empty(int(offs[-1]) or 4, dtype=torch.float32, pin_memory=True)
+        hv = host.numpy()
+        for a, o, s in zip(arrays, offs[:-1], sizes):
+            hv[o : o + s] = np.asarray(a, dtype=np.float32).reshape(-1)
+        dev = host.to(self.device, non_blocking=True)
+        # keep the pinned staging buffer alive until the copy has run
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending = [(h, e) for h, e in getattr(self, "_pending", []) if not e.query()] + [(host, ev)]
+        return [dev[o : o + s] for o, s in zip(offs[:-1], sizes)]
+
+    # ------------------------------------------------------------------ K1
+    def gmm(self, plans, seeds, out: torch.Tensor, labels_out=None):
+        """seeds[b]: list of 1..4 int8/uint8 device volumes summed into the label map."""
+        B = len(plans)
+        small = self.upload([p.mus for p in plans] + [p.sigmas for p in plans])
+        jobs = (_lib.GmmJob * B)()
+        for b, p in enumerate(plans):
+            j = jobs[b]
+            vols = list(seeds[b])
+            if not 1 <= len(vols) <= 4:
+                raise ValueError("each sample needs 1..4 seed volumes")
+            for m, v in enumerate(vols):
+                if v.dtype not in (torch.int8, torch.uint8) or v.numel() != out.shape[-1]:
+                    raise TypeError("seed volumes must be int8/uint8 tensors with one label per output voxel")
+                _check(v, v.dtype, self.device, "seed volume")
+                j.seed[m] = v.data_ptr()
+            j.mus, j.sigmas = small[b].data_ptr(), small[B + b].data_ptr()
+            j.nlabels = int(p.mus.size)
+            j.noise = _ptr(None if p.gmm_noise is None else _check(p.gmm_noise, torch.float32, self.device, "gmm_noise"))
+            j.out = out[b].data_ptr()
+            j.labels_out = None if labels_out is None else labels_out[b].data_ptr()
+            j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_GMM, 0)
+        _lib.call("fsg_gmm", jobs, B, int(out.shape[-1]), _stream())
+        self._keep = (small,)
+
+    # ------------------------------------------------------------------ K2
+    def _warp_jobs(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True):
+        B = len(plans)
+        sx, sy, sz = self.shape
+        arrays, slots = [], []
+        for p in plans:
+            slot = {}
+            if p.deform and p.fsmall is not None:
+                slot["f"] = len(arrays)
+                arrays.append(p.fsmall)
+            if epilogue and p.bf_low is not None:
+                slot["b"] = len(arrays)
+                arrays.append(p.bf_low)
+            slots.append(slot)
+        small = self.upload(arrays) if arrays else []
+        shift = self.scratch("shift", B, torch.float32, 4)
+        jobs = (_lib.WarpJob * B)()
+        keep = [small, shift]
+        for b, p in enumerate(plans):
+            j = jobs[b]
+            j.src_img, j.dst_img = _ptr(None if src_img is None else src_img[b]), _ptr(None if dst_img is None else dst_img[b])
+            j.src_seg, j.dst_seg = _ptr(None if src_seg is None else src_seg[b]), _ptr(None if dst_seg is None else dst_seg[b])
+            j.src_img2, j.dst_img2 = _ptr(None if src_img2 is None else src_img2[b]), _ptr(None if dst_img2 is None else dst_img2[b])
+            j.mode, j.flip = int(bool(p.deform)), int(bool(p.flip))
+            j.shift = shift[b].data_ptr()
+            if p.deform:
+                j.A = (C.c_float * 9)(*np.asarray(p.A, dtype=np.float32).reshape(-1))
+                j.c2 = (C.c_float * 3)(*np.asarray(p.c2, dtype=np.float64).astype(np.float32))
+                j.center = (C.c_float * 3)(*np.asarray(p.center, dtype=np.float32))
+                if "f" in slots[b]:
+                    fs = p.fsmall.shape[:3]
+                    j.fsmall = small[slots[b]["f"]].data_ptr()
+                    j.fs = (C.c_int32 * 3)(*fs)
+                    for a in range(3):
+                        t = self.tables.zoom(fs[a], self.shape[a] / fs[a])
+                        if t.numel() // 8 != self.shape[a]:
+                            raise ValueError("control-grid zoom does not reproduce the volume shape")
+                        j.ftab[a] = t.data_ptr()
+            if epilogue and p.gamma is not None:
+                j.has_gamma, j.gamma = 1, float(np.float32(p.gamma))
+            if "b" in slots[b]:
+                bs = p.bf_low.shape
+                j.bf_low = small[slots[b]["b"]].data_ptr()
+                j.bs = (C.c_int32 * 3)(*bs)
+                for a in range(3):
+                    t = self.tables.zoom(bs[a], self.shape[a] / bs[a])
+                    if t.numel() // 8 != self.shape[a]:
+                        raise ValueError("bias-grid zoom does not reproduce the volume shape")
+                    j.btab[a] = t.data_ptr()
+        return jobs, keep
+
+    def warp(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True):
+        B = len(plans)
+        sx, sy, sz = self.shape
+        jobs, keep = self._warp_jobs(plans, src_img, src_seg, dst_img, dst_seg, src_img2, dst_img2, epilogue)
+        didx = [b for b, p in enumerate(plans) if p.deform]
+        if didx:
+            dj = (_lib.WarpJob * len(didx))(*[jobs[b] for b in didx])
+            _lib.call("fsg_warp_shift", dj, len(didx), sx, sy, sz, _stream())
+        _lib.call("fsg_warp", jobs, B, sx, sy, sz, _stream())
+        self._keep_warp = keep
+
+    def warp_coords(self, plan):
+        sx, sy, sz = self.shape
+        jobs, keep = self._warp_jobs([plan], None, None, None, None, epilogue=False)
+        _lib.call("fsg_warp_shift", jobs, 1, sx, sy, sz, _stream())
+        out = torch.empty((3, sx, sy, sz), dtype=torch.float32, device=self.device)
+        _lib.call("fsg_warp_coords", jobs, sx, sy, sz, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
+        return out
+
+    # ------------------------------------------------------------------ K4a
+    def blur(self, stds_list, src, dst, tmp):
+        """Separable Gaussian blur of src[b] into dst[b] (tmp[b] = scratch); stds per sample."""
+        B = len(stds_list)
+        sx, sy, sz = self.shape
+        jobs = (_lib.BlurJob * B)()
+        keep = []
+        for b, stds in enumerate(stds_list):
+            j = jobs[b]
+            j.src, j.dst, j.tmp = src[b].data_ptr(), dst[b].data_ptr(), tmp[b].data_ptr()
+            for a in range(3):
+                if stds[a] > 0:
+                    t = self.tables.taps(float(stds[a]))
+                    keep.append(t)
+                    j.taps[a], j.ntaps[a] = t.data_ptr(), t.numel() // 4
+        _lib.call("fsg_blur3d", jobs, B, sx, sy, sz, _stream())
+
+    # ------------------------------------------------------------------ K4b
+    def lowres_shape(self, spacing):
+        return tuple(resample_size(self.shape[a], self.resolution[a], spacing[a]) for a in range(3))
+
+    def resample(self, plans, src, dst):
+        """Trilinear down-sampling (+noise when plan.noise_std is set). Returns per-sample (shape, factors)."""
+        B = len(plans)
+        sx, sy, sz = self.shape
+        jobs = (_lib.ResampleJob * B)()
+        info = []
+        for b, p in enumerate(plans):
+            j = jobs[b]
+            n = self.lowres_shape(p.spacing)
+            factors = []
+            for a in range(3):
+                t, fac = self.tables.resample(self.shape[a], self.resolution[a], p.spacing[a])
+                j.tab[a] = t.data_ptr()
+                factors.append(fac)
+            j.n = (C.c_int32 * 3)(*n)
+            j.src, j.dst = src[b].data_ptr(), dst[b].data_ptr()
+            if p.noise_std is not None:
+                j.has_noise, j.noise_std = 1, float(np.float32(p.noise_std))
+                j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
+                j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_NOISE, 0)
+            info.append((n, np.asarray(factors, dtype=np.float64)))
+        _lib.call("fsg_resample", jobs, B, sx, sy, sz, _stream())
+        return info
+
+    def add_noise(self, plans, src, dst, numel=None):
+        B = len(plans)
+        jobs = (_lib.NoiseJob * B)()
+        for b, p in enumerate(plans):
+            j = jobs[b]
+            j.src, j.dst = src[b].data_ptr(), dst[b].data_ptr()
+            j.noise_std = float(np.float32(p.noise_std))
+            j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
+            j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_NOISE, 0)
+        _lib.call("fsg_add_noise", jobs, B, self.nvox if numel is None else numel, _stream())
+
+    # ------------------------------------------------------------------ K4c
+    def zoom(self, src_list, src_shapes, factors_list, dst, post=0, minmax=None):
+        """myzoom_torch(src, factors) into dst[b] of the engine shape; post 1 = /max, 2 = /max + ScaleIntensity."""
+        B = len(src_list)
+        sx, sy, sz = self.shape
+        jobs = (_lib.ZoomJob * B)()
+        mm = self.scratch("minmax", B, torch.float32, 2) if minmax is None else minmax
+        for b in range(B):
+            j = jobs[b]
+            n = src_shapes[b]
+            for a in range(3):
+                if zoom_size(n[a], factors_list[b][a]) != self.shape[a]:
+                    raise ValueError(f"zoom of extent {n[a]} by {factors_list[b][a]} does not give {self.shape[a]}")
+                j.tab[a] = self.tables.zoom(n[a], factors_list[b][a]).data_ptr()
+            j.n = (C.c_int32 * 3)(*n)
+            j.src, j.dst = src_list[b].data_ptr(), dst[b].data_ptr()
+            j.minmax, j.post = mm[b].data_ptr(), post
+        if post > 0:
+            _lib.call("fsg_zoom_minmax", jobs, B, sx, sy, sz, _stream())
+        _lib.call("fsg_zoom", jobs, B, sx, sy, sz, _stream())
+        return mm
+
+    # ------------------------------------------------------------------ misc
+    def scale_intensity(self, x: torch.Tensor, out: torch.Tensor | None = None):
+        out = torch.empty_like(x) if out is None else out
+        mm = torch.empty(2, dtype=torch.float32, device=self.device)
+        _lib.call("fsg_minmax", x.data_ptr(), x.numel(), mm.data_ptr(), _stream())
+        _lib.call("fsg_scale_intensity", x.data_ptr(), out.data_ptr(), x.numel(), mm.data_ptr(), _stream())
+        return out
+
+    def to_u8(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dtype == torch.uint8:
+            return x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
+        _lib.call("fsg_f32_to_u8", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        return out
+
+    def from_u8(self, x: torch.Tensor, dtype) -> torch.Tensor:
+        if dtype == torch.uint8:
+            return x
+        out = torch.empty(x.shape, dtype=dtype, device=self.device)
+        if dtype == torch.float32:
+            _lib.call("fsg_u8_to_f32", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        elif dtype == torch.int64:
+            _lib.call("fsg_u8_to_i64", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        else:
+            out = self.from_u8(x, torch.float32).to(dtype)
+        return out
+
+    # ------------------------------------------------------------------ fused base pipeline
+    def run_base(self, plans, seeds, segs, out_img=None, out_seg=None, scale=False):
+        """Whole base path for a batch.  seeds[b] = 1..4 label volumes, segs[b] = uint8 volume.
+        Returns (images [B,*shape] float32, segs [B,*shape] uint8)."""
+        B = len(plans)
+        if B < 1 or B > _lib.MAX_JOBS:
+            raise ValueError(f"batch must be 1..{_lib.MAX_JOBS}")
+        shp = (B, *self.shape)
+        out_img = torch.empty(shp, dtype=torch.float32, device=self.device) if out_img is None else out_img
+        out_seg = torch.empty(shp, dtype=torch.uint8, device=self.device) if out_seg is None else out_seg
+        buf0 = self.scratch("buf0", B)
+        buf1 = self.scratch("buf1", B)
+        buf2 = self.scratch("buf2", B)
+        self.gmm(plans, seeds, buf0)
+        rs = [b for b, p in enumerate(plans) if p.spacing is not None]
+        no_rs = [b for b, p in enumerate(plans) if p.spacing is None]
+        # warp straight into the output for samples that skip the resolution simulation
+        warp_dst = [out_img[b].view(-1) if (plans[b].spacing is None and plans[b].noise_std is None) else buf1[b] for b in range(B)]
+        self.warp(plans, buf0, segs, warp_dst, out_seg)
+        if rs:
+            sub = [plans[b] for b in rs]
+            self.blur([p.stds for p in sub], [buf1[b] for b in rs], [buf2[b] for b in rs], [buf0[b] for b in rs])
+            info = self.resample(sub, [buf2[b] for b in rs], [buf0[b] for b in rs])
+            self.zoom([buf0[b] for b in rs], [i[0] for i in info], [1 / i[1] for i in info], [out_img[b].view(-1) for b in rs], post=2 if scale else 1)
+        nz = [b for b in no_rs if plans[b].noise_std is not None]
+        if nz:
+            self.add_noise([plans[b] for b in nz], [buf1[b] for b in nz], [out_img[b].view(-1) for b in nz])
+        if scale and no_rs:
+            for b in no_rs:
+                self.scale_intensity(out_img[b], out_img[b])
+        return out_img, out_seg
+
+
+_ENGINES: dict = {}
+
+
+def engine_for(device, shape, resolution=(1.0, 1.0, 1.0)) -> SynthEngine:
+    """Process-wide engine cache keyed by (device, shape, resolution)."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    key = (str(dev), tuple(int(s) for s in shape), tuple(float(r) for r in resolution))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = SynthEngine(shape, resolution, dev)
+        _ENGINES[key] = eng
+    return eng

@@ -1,0 +1,240 @@
+"""``FetalSynthGen`` — same constructor and ``sample / generate / augment`` contract as the
+reference generator (``fetalsyngen/generator/model.py:27-276``), re-implemented as a short
+sequence of fused sm_100a kernels:
+
+  reference stage (model.py)                      here
+  ----------------------------------------------  -----------------------------------------
+  load_seeds + sample_intensities  (:119-128)     fsg_gmm   (seed sum + lookup + noise)
+  spatial_deform.deform            (:147-152)     fsg_warp_shift + fsg_warp
+  gamma, biasfield                 (:183-190)     epilogue of fsg_warp
+  resampled (blur + down-sample)   (:193-198)     fsg_blur3d + fsg_resample
+  noise                            (:201-203)     epilogue of fsg_resample
+  resampled.resize_back            (:206)         fsg_zoom_minmax + fsg_zoom (/max)
+  SR artifacts                     (:209-220)     generator/augmentation/artifacts.py
+
+All random *parameters* are drawn on the host in the reference's order (so ``np.random.seed``
+reproduces the same scalars as the reference); per-voxel noise comes from counter-based Philox
+streams keyed by a seed drawn from torch's generator.  ``inject`` (not in the reference API)
+lets the parity tests supply the reference's captured random tensors.
+"""
+from __future__ import annotations
+
+from typing import Iterable
+
+import numpy as np
+import torch
+
+from ..engine import SamplePlan, engine_for
+from .augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
+from .deformation.affine_nonrigid import SpatialDeformation
+from .intensity.rand_gmm import ImageFromSeeds
+
+
+class FetalSynthGen:
+    def __init__(
+        self,
+        shape: Iterable[int],
+        resolution: Iterable[float],
+        device: str,
+        intensity_generator: ImageFromSeeds,
+        spatial_deform: SpatialDeformation,
+        resampler: RandResample,
+        bias_field: RandBiasField,
+        noise: RandNoise,
+        gamma: RandGamma,
+        blur_cortex=None,
+        struct_noise=None,
+        simulate_motion=None,
+        boundaries=None,
+    ):
+        self.shape = shape
+        self.resolution = resolution
+        self.intensity_generator = intensity_generator
+        self.spatial_deform = spatial_deform
+        self.resampled = resampler
+        self.biasfield = bias_field
+        self.gamma = gamma
+        self.noise = noise
+        self.artifacts = {
+            "blur_cortex": blur_cortex,
+            "struct_noise": struct_noise,
+            "simulate_motion": simulate_motion,
+            "boundaries": boundaries,
+        }
+        self.device = device
+        self._sample_counter = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _validated_genparams(self, d: dict) -> dict:
+        """Drop None-valued keys recursively: they are not pinned (model.py:85-92)."""
+        if not isinstance(d, dict):
+            return d
+        return {k: self._validated_genparams(v) for k, v in d.items() if v is not None}
+
+    def engine(self, shape=None):
+        return engine_for(self.device, tuple(self.shape if shape is None else shape), self.resolution)
+
+    def _new_plan(self) -> SamplePlan:
+        self._sample_counter += 1
+        return SamplePlan(rng_seed=int(torch.randint(0, 2**62, (1,)).item()), sample_id=self._sample_counter)
+
+    # ------------------------------------------------------------------ draws
+    def _draw_generate(self, plan, seeds, shape, genparams, inject):
+        ig = self.intensity_generator
+        params = {}
+        if seeds is not None:
+            m2s = ig.draw_subclusters(genparams=genparams.get("selected_seeds", {}))
+            plan.meta["seed_vols"] = ig.select_seeds(seeds, m2s, self.engine(shape).device)
+            plan.mus, plan.sigmas = ig.draw_gmm(genparams.get("seed_intensities", {}), inject)
+            params["selected_seeds"] = {"mlabel2subclusters": m2s}
+        else:
+            params["selected_seeds"] = {}
+            params["seed_intensities"] = {}
+        fields, deform_params = self.spatial_deform.draw(shape, genparams.get("deform_params", {}), inject)
+        for k, v in fields.items():
+            setattr(plan, k, v)
+        params["deform_params"] = deform_params
+        return params
+
+    def _draw_augment(self, plan, shape, genparams, inject):
+        plan.gamma = self.gamma.draw(genparams.get("gamma_params", {}))
+        plan.bf_low, bf_params = self.biasfield.draw(shape, genparams.get("bf_params", {}), inject)
+        plan.spacing, plan.stds = self.resampled.draw(np.array(self.resolution), genparams.get("resample_params", {}), inject)
+        plan.noise_std = self.noise.draw(genparams.get("noise_params", {}))
+        return {
+            "gamma_params": {"gamma": plan.gamma},
+            "bf_params": bf_params,
+            "resample_params": {"spacing": None if plan.spacing is None else plan.spacing.tolist()},
+            "noise_params": {"noise_std": plan.noise_std},
+        }
+
+    @staticmethod
+    def _inject_tensors(plan, inject, device):
+        if not inject:
+            return
+        if "gmm_noise" in inject:
+            plan.gmm_noise = torch.as_tensor(inject["gmm_noise"], dtype=torch.float32).to(device).contiguous().view(-1)
+        if "noise" in inject:
+            plan.noise = torch.as_tensor(inject["noise"], dtype=torch.float32).to(device).contiguous().view(-1)
+
+    # ------------------------------------------------------------------ device stages
+    def _run_generate(self, eng, plan, image, segmentation, fuse_augment: bool):
+        """GMM (or image prior) + warp; with fuse_augment the gamma/bias epilogues ride along."""
+        seg_u8 = eng.to_u8(segmentation.to(eng.device))
+        src = torch.empty((1, eng.nvox), dtype=torch.float32, device=eng.device)
+        img_dev = None if image is None else image.to(eng.device, torch.float32).contiguous()
+        if "seed_vols" in plan.meta:
+            eng.gmm([plan], [[v.view(-1) for v in plan.meta["seed_vols"]]], src)
+        else:
+            if img_dev is None:
+                raise ValueError("If no seeds are passed, an image must be loaded to be used as intensity prior!")
+            lo, hi = img_dev.min(), img_dev.max()
+            src = ((img_dev - lo) / (hi - lo) * 255).view(1, -1)  # model.py:138
+        dst = torch.empty((1, eng.nvox), dtype=torch.float32, device=eng.device)
+        dseg = torch.empty((1, eng.nvox), dtype=torch.uint8, device=eng.device)
+        dst2 = None if img_dev is None else torch.empty((1, eng.nvox), dtype=torch.float32, device=eng.device)
+        eng.warp([plan], src, [seg_u8.view(-1)], dst, dseg, None if img_dev is None else [img_dev.view(-1)], dst2, epilogue=fuse_augment)
+        return dst, dseg, dst2
+
+    def _run_augment_tail(self, eng, plan, x):
+        """blur + down-sample (+noise) + up-sample (/max), or full-resolution noise."""
+        if plan.spacing is not None:
+            blurred = torch.empty_like(x)
+            tmp = eng.scratch("buf0", 1)
+            eng.blur([plan.stds], x, blurred, tmp)
+            low = eng.scratch("buf1", 1)
+            info = eng.resample([plan], blurred, low)
+            out = torch.empty_like(x)
+            eng.zoom([low[0]], [info[0][0]], [1 / info[0][1]], out, post=1)
+            return out
+        if plan.noise_std is not None:
+            out = torch.empty_like(x)
+            eng.add_noise([plan], x, out)
+            return out
+        return x
+
+    def _run_artifacts(self, output, segmentation, genparams):
+        artifacts = {}
+        for name, artifact in self.artifacts.items():
+            if artifact is not None:
+                output, metadata = artifact(output, segmentation, self.device, genparams.get("artifact_params", {}), resolution=self.resolution)
+                artifacts[name] = metadata
+        return output, artifacts
+
+    # ------------------------------------------------------------------ reference API
+    def generate(self, image, segmentation, seeds, genparams: dict = {}, inject: dict | None = None):
+        """Synthetic deformed image from seeds (or the image) + deformed segmentation
+        (model.py:94-159).  Returns (output, segmentation, image, synth_params)."""
+        shape = tuple(segmentation.shape)
+        eng = self.engine(shape)
+        plan = self._new_plan()
+        params = self._draw_generate(plan, seeds, shape, genparams, inject)
+        self._inject_tensors(plan, inject, eng.device)
+        dst, dseg, dst2 = self._run_generate(eng, plan, image, segmentation, fuse_augment=False)
+        if seeds is not None:
+            params["seed_intensities"] = {"mus": torch.from_numpy(plan.mus).to(eng.device), "sigmas": torch.from_numpy(plan.sigmas).to(eng.device)}
+        seg_out = eng.from_u8(dseg.view(shape), segmentation.dtype)
+        return dst.view(shape), seg_out, None if dst2 is None else dst2.view(shape), params
+
+    def augment(self, image, segmentation, genparams: dict = {}, inject: dict | None = None):
+        """Intensity / resolution augmentations + SR artifacts (model.py:161-229)."""
+        shape = tuple(image.shape)
+        eng = self.engine(shape)
+        plan = self._new_plan()
+        params = self._draw_augment(plan, shape, genparams, inject)
+        self._inject_tensors(plan, inject, eng.device)
+        x = image.to(eng.device, torch.float32).contiguous().view(1, -1)
+        if plan.gamma is not None or plan.bf_low is not None:
+            y = torch.empty_like(x)
+            eng.warp([plan], x, None, y, None)
+            x = y
+        out = self._run_augment_tail(eng, plan, x).view(shape)
+        out, artifacts = self._run_artifacts(out, segmentation, genparams)
+        params["artifacts"] = artifacts
+        return out, params
+
+    def sample(self, image, segmentation, seeds, genparams: dict = {}, inject: dict | None = None):
+        """generate + augment with the elementwise stages fused into the warp (model.py:231-276)."""
+        if genparams:
+            genparams = self._validated_genparams(genparams)
+        shape = tuple(segmentation.shape)
+        eng = self.engine(shape)
+        plan = self._new_plan()
+        params = self._draw_generate(plan, seeds, shape, genparams, inject)
+        params.update(self._draw_augment(plan, shape, genparams, inject))
+        self._inject_tensors(plan, inject, eng.device)
+        dst, dseg, dst2 = self._run_generate(eng, plan, image, segmentation, fuse_augment=True)
+        if seeds is not None:
+            params["seed_intensities"] = {"mus": torch.from_numpy(plan.mus).to(eng.device), "sigmas": torch.from_numpy(plan.sigmas).to(eng.device)}
+        out = self._run_augment_tail(eng, plan, dst).view(shape)
+        seg_out = eng.from_u8(dseg.view(shape), segmentation.dtype)
+        out, artifacts = self._run_artifacts(out, seg_out, genparams)
+        params["artifacts"] = artifacts
+        return out, seg_out, None if dst2 is None else dst2.view(shape), params
+
+    # ------------------------------------------------------------------ batched fast path
+    def sample_batch(self, segmentations, seeds, scale: bool = False, out_img=None, out_seg=None, genparams: dict = {}):
+        """Generate ``len(segmentations)`` independent samples with batched launches.
+
+        segmentations[b]: uint8 device volume; seeds[b]: the reference's seed-path dictionary
+        ``{n_sub: {mlabel: path}}`` or a list of 1..4 int8 device volumes (already selected).
+        Returns (images [B,*shape] float32, segmentations [B,*shape] uint8, [params]); both
+        tensors stay on the device.  SR artifacts are not applied on this path."""
+        shape = tuple(self.shape)
+        eng = self.engine(shape)
+        plans, params, vols = [], [], []
+        for b in range(len(segmentations)):
+            plan = self._new_plan()
+            sd = seeds[b]
+            if isinstance(sd, dict):
+                pr = self._draw_generate(plan, sd, shape, genparams, None)
+                vols.append([v.view(-1) for v in plan.meta["seed_vols"]])
+            else:
+                pr = self._draw_generate(plan, None, shape, genparams, None)
+                plan.mus, plan.sigmas = self.intensity_generator.draw_gmm(genparams.get("seed_intensities", {}))
+                vols.append([v.view(-1) for v in sd])
+            pr.update(self._draw_augment(plan, shape, genparams, None))
+            plans.append(plan)
+            params.append(pr)
+        img, seg = eng.run_base(plans, vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)
+        return img, seg, params

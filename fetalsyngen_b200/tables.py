@@ -1,0 +1,125 @@
+"""Host-side 1-D tables that parameterise the kernels.
+
+The float32 rounding of the reference's sample positions is implementation-defined
+(``torch.arange(..., dtype=float32)`` in ``myzoom_torch``, utils/generation.py:318-338; numpy
+float64 ``arange`` cast to float32 in ``RandResample``, synthseg.py:84-102), so the positions
+are produced here with the very same library calls and handed to the kernels as
+``fsg_tab {int16 f, int16 c, float wc}`` arrays.  The kernels then only do the blends.
+Tables are tiny (<= a few KB), cached per key on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+TAB_DTYPE = np.dtype([("f", "<i2"), ("c", "<i2"), ("wc", "<f4")])
+
+
+def _pack(v: np.ndarray, n_in: int, mark_outside: bool) -> np.ndarray:
+    v = v.astype(np.float32)
+    fl = np.floor(v)
+    tab = np.zeros(v.shape[0], dtype=TAB_DTYPE)
+    tab["f"] = fl.astype(np.int16)
+    tab["c"] = np.minimum(fl.astype(np.int32) + 1, n_in - 1).astype(np.int16)
+    tab["wc"] = v - fl
+    if mark_outside:  # linear sampling returns 0 unless 0 < v <= n_in-1 (generation.py:229-235)
+        out = ~((v > 0) & (v <= n_in - 1))
+        tab["f"][out] = -1
+        tab["c"][out] = 0
+        tab["wc"][out] = 0
+    return tab
+
+
+def zoom_size(n_in: int, factor: float) -> int:
+    return int(np.round(n_in * float(factor)))
+
+
+def zoom_table(n_in: int, factor: float) -> np.ndarray:
+    """Sampling table of ``myzoom_torch`` along one axis (utils/generation.py:315-361)."""
+    factor = float(factor)
+    delta = (1.0 - factor) / (2.0 * factor)
+    n_out = zoom_size(n_in, factor)
+    v = torch.arange(delta, delta + n_out / factor, 1 / factor, dtype=torch.float)[:n_out].numpy().copy()
+    v[v < 0] = 0
+    v[v > (n_in - 1)] = n_in - 1
+    return _pack(v, n_in, mark_outside=False)
+
+
+def resample_size(n_in: int, res_in: float, spacing: float) -> int:
+    return int(n_in * res_in / spacing)
+
+
+def resample_table(n_in: int, res_in: float, spacing: float):
+    """Coarse-grid positions of ``RandResample`` along one axis (synthseg.py:84-102).
+    Returns (table, factor)."""
+    n_out = resample_size(n_in, res_in, spacing)
+    factor = n_out / n_in
+    delta = (1.0 - factor) / (2.0 * factor)
+    v = np.arange(delta, delta + n_out / factor, 1 / factor)[:n_out]
+    return _pack(v, n_in, mark_outside=True), factor
+
+
+def gaussian_taps(sigma: float) -> np.ndarray:
+    """``make_gaussian_kernel`` (utils/generation.py:74-81), evaluated on the host."""
+    sl = int(np.ceil(3 * sigma))
+    ts = torch.linspace(-sl, sl, 2 * sl + 1, dtype=torch.float)
+    g = torch.exp((-((ts / sigma) ** 2) / 2))
+    return (g / g.sum()).numpy()
+
+
+def resample_stds(spacing, res_in, blur_u: float) -> np.ndarray:
+    """Blur widths of the resolution simulation (synthseg.py:78-80)."""
+    spacing = np.asarray(spacing, dtype=np.float64)
+    res_in = np.asarray(res_in, dtype=np.float64)
+    stds = (0.85 + 0.3 * blur_u) * np.log(5) / np.pi * spacing / res_in
+    stds[spacing <= res_in] = 0.0
+    return stds
+
+
+def make_affine_matrix(rot, sh, s) -> np.ndarray:
+    """3x3 float64 affine of the spatial deformation: shear_x . shear_y . shear_z . Rx . Ry . Rz,
+    rows scaled (utils/generation.py:39-71)."""
+    c, si = np.cos(np.asarray(rot, dtype=np.float64)), np.sin(np.asarray(rot, dtype=np.float64))
+    mats = [
+        np.array([[1, 0, 0], [sh[1], 1, 0], [sh[2], 0, 1]], dtype=np.float64),
+        np.array([[1, sh[0], 0], [0, 1, 0], [0, sh[2], 1]], dtype=np.float64),
+        np.array([[1, 0, sh[0]], [0, 1, sh[1]], [0, 0, 1]], dtype=np.float64),
+        np.array([[1, 0, 0], [0, c[0], -si[0]], [0, si[0], c[0]]], dtype=np.float64),
+        np.array([[c[1], 0, si[1]], [0, 1, 0], [-si[1], 0, c[1]]], dtype=np.float64),
+        np.array([[c[2], -si[2], 0], [si[2], c[2], 0], [0, 0, 1]], dtype=np.float64),
+    ]
+    a = mats[0]
+    for m in mats[1:]:
+        a = a @ m
+    return a * np.asarray(s, dtype=np.float64)[:, None]
+
+
+class DeviceTables:
+    """Per-device cache of uploaded tables / tap arrays."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._cache: dict = {}
+
+    def _put(self, key, arr: np.ndarray) -> torch.Tensor:
+        t = self._cache.get(key)
+        if t is None:
+            t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy()).to(self.device)
+            if len(self._cache) > 4096:
+                self._cache.clear()
+            self._cache[key] = t
+        return t
+
+    def zoom(self, n_in: int, factor: float) -> torch.Tensor:
+        return self._put(("zoom", n_in, float(factor)), zoom_table(n_in, factor))
+
+    def resample(self, n_in: int, res_in: float, spacing: float):
+        key = ("resample", n_in, float(res_in), float(spacing))
+        if key not in self._cache:
+            tab, factor = resample_table(n_in, res_in, spacing)
+            self._put(key, tab)
+            self._cache[key + ("factor",)] = factor
+        return self._cache[key], self._cache[key + ("factor",)]
+
+    def taps(self, sigma: float) -> torch.Tensor:
+        return self._put(("taps", float(sigma)), gaussian_taps(sigma))

@@ -1,0 +1,181 @@
+/* libfsg — C-ABI of the B200-native FetalSynthGen per-sample generation path.
+ *
+ * Boundary: every entry point replaces the torch-eager body of one stage of the reference's
+ * FetalSynthGen.sample() (fetalsyngen/generator/model.py:94-276).  The reference has no FFI
+ * for the base stages (they are torch calls) and a pybind11 one for the motion artifact
+ * (svort/slice_acquisition/slice_acq_cuda.cpp:156-161); a maintainer binds this library with
+ * ctypes.  Signatures carry plain pointers, sizes and an opaque stream
+ * handle only — no torch types.
+ *
+ * Conventions
+ *  - Volumes are C-contiguous [x][y][z] (z fastest), float32 images, uint8 label maps.
+ *  - All data pointers are DEVICE pointers unless the name ends in _host.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - Every call processes a batch of `njobs` independent volumes that share one shape
+ *    (njobs <= FSG_MAX_JOBS); job structs are HOST memory, copied by value into the launch.
+ *  - Return value: 0 = ok, non-zero = error; fsg_last_error() gives the message
+ *    (thread-local).  Nothing allocates device memory inside a stage call.
+ *  - No CPU fallback exists: without a CUDA device every launch returns an error.
+ */
+#ifndef FSG_H
+#define FSG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSG_VERSION 100
+#define FSG_MAX_JOBS 16
+#define FSG_MAX_TAPS 127
+
+/* One entry of a 1-D linear sampling table (output index -> source cell).
+ * Built on the host with the reference's own expressions (torch.arange float32 positions,
+ * utils/generation.py:318-361; numpy float64 positions cast to float32, synthseg.py:84-102)
+ * because their float32 rounding is implementation-defined.  f < 0 marks a position outside
+ * (0, S-1] for which linear sampling yields 0 (utils/generation.py:229-235). */
+typedef struct fsg_tab {
+  int16_t f;  /* floor index */
+  int16_t c;  /* ceil index, clamped to S-1 */
+  float wc;   /* weight of the ceil sample; floor weight is 1 - wc */
+} fsg_tab;
+
+/* Counter-based RNG stream: Philox4x32-10, key = seed, counter = (block, stage, sample). */
+typedef struct fsg_rng {
+  uint64_t seed;
+  uint64_t sample;
+  uint32_t stage;
+  uint32_t _pad;
+} fsg_rng;
+
+/* K1 — GMM intensity synthesis. Replaces ImageFromSeeds.sample_intensities' per-voxel part
+ * (generator/intensity/rand_gmm.py:146-149) fused with the seed sum of load_seeds
+ * (rand_gmm.py:90-97): L = sum(seed[m]); I = max(0, mus[L] + sigmas[L] * N). */
+typedef struct fsg_gmm_job {
+  const int8_t* seed[4]; /* 1..4 label volumes summed per voxel; unused entries NULL */
+  const float* mus;      /* [nlabels] */
+  const float* sigmas;   /* [nlabels] */
+  const float* noise;    /* [nvox] standard normal draws to inject, or NULL -> Philox */
+  float* out;            /* [nvox] */
+  uint8_t* labels_out;   /* optional [nvox] summed labels, or NULL */
+  fsg_rng rng;
+  int32_t nlabels;
+  int32_t _pad;
+} fsg_gmm_job;
+int fsg_gmm(const fsg_gmm_job* jobs_host, int njobs, int64_t nvox, void* stream);
+
+/* K2 — fused spatial deformation. Replaces SpatialDeformation.deform
+ * (generator/deformation/affine_nonrigid.py:86-120, 164-193, 299-366) + myzoom_torch of the
+ * control grid (utils/generation.py:310-397) + fast_3D_interp_torch linear/nearest
+ * (utils/generation.py:204-288), with RandGamma (synthseg.py:262-275) and RandBiasField
+ * (synthseg.py:157-188) as optional epilogues on the image.
+ * mode 0: identity sampling (deformation gate off) — only flip + epilogues are applied.
+ * mode 1: coordinates = A*(grid - center + F) + c2, clamped to [0,S-1], minus shift. */
+typedef struct fsg_warp_job {
+  const float* src_img;   /* [S] or NULL */
+  const uint8_t* src_seg; /* [S] or NULL */
+  const float* src_img2;  /* optional second image (load_image=True), or NULL */
+  float* dst_img;
+  uint8_t* dst_seg;
+  float* dst_img2;
+  const float* fsmall;    /* [fs0][fs1][fs2][3] control-grid displacements, or NULL */
+  const fsg_tab* ftab[3]; /* zoom tables of the control grid, lengths sx, sy, sz */
+  const float* bf_low;    /* [bs0][bs1][bs2] log-bias control grid, or NULL */
+  const fsg_tab* btab[3]; /* zoom tables of the bias grid */
+  const float* shift;     /* [3] floor(min coord) per axis (written by fsg_warp_shift) */
+  float A[9];
+  float c2[3];
+  float center[3];
+  float gamma;            /* applied when has_gamma */
+  int32_t fs[3];
+  int32_t bs[3];
+  int32_t mode;
+  int32_t flip;
+  int32_t has_gamma;
+  int32_t _pad;
+} fsg_warp_job;
+/* Pre-pass: writes floor(min over the volume of the clamped coordinate) per axis into
+ * job.shift (affine_nonrigid.py:350-358).  No volume traffic; coordinates are recomputed. */
+int fsg_warp_shift(const fsg_warp_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+int fsg_warp(const fsg_warp_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+/* Debug/parity aid: writes the three coordinate volumes (after clamp and shift). */
+int fsg_warp_coords(const fsg_warp_job* job_host, int sx, int sy, int sz, float* xx, float* yy, float* zz, void* stream);
+
+/* K4a — separable zero-padded Gaussian blur. Replaces gaussian_blur_3d
+ * (utils/generation.py:84-110); taps come from make_gaussian_kernel on the host. */
+typedef struct fsg_blur_job {
+  const float* src;
+  float* dst;
+  float* tmp;            /* scratch volume (same size) */
+  const float* taps[3];  /* per axis, or NULL / ntaps 0 to skip the axis */
+  int32_t ntaps[3];
+  int32_t _pad;
+} fsg_blur_job;
+int fsg_blur3d(const fsg_blur_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+
+/* K4b — trilinear resampling onto a regular coarse grid + additive noise.
+ * Replaces RandResample.__call__'s interpolation (synthseg.py:84-107 ->
+ * utils/generation.py:227-285) and RandNoise (synthseg.py:217-235). */
+typedef struct fsg_resample_job {
+  const float* src;       /* [sx][sy][sz] */
+  float* dst;             /* [n[0]][n[1]][n[2]] */
+  const fsg_tab* tab[3];  /* lengths n[0], n[1], n[2] */
+  const float* noise;     /* [n0*n1*n2] injected draws or NULL -> Philox (when has_noise) */
+  fsg_rng rng;
+  float noise_std;
+  int32_t has_noise;
+  int32_t n[3];           /* coarse grid of this job (jobs of one launch may differ) */
+  int32_t _pad;
+} fsg_resample_job;
+int fsg_resample(const fsg_resample_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+
+/* Elementwise x + std*N, clamp >= 0 at any resolution (RandNoise when no resampling ran). */
+typedef struct fsg_noise_job {
+  const float* src;
+  float* dst;
+  const float* noise;
+  fsg_rng rng;
+  float noise_std;
+  int32_t _pad;
+} fsg_noise_job;
+int fsg_add_noise(const fsg_noise_job* jobs_host, int njobs, int64_t nvox, void* stream);
+
+/* K4c — separable linear zoom (myzoom_torch, utils/generation.py:310-397) with the global
+ * reductions that follow it on this path.
+ * post 0: raw zoom.  post 1: divide by the global max (RandResample.resize_back,
+ * synthseg.py:109-114).  post 2: post 1 followed by ScaleIntensity(0,1)
+ * (data/datasets.py:311).  For post>0 call fsg_zoom_minmax first; both read src only. */
+typedef struct fsg_zoom_job {
+  const float* src;       /* [n[0]][n[1]][n[2]] */
+  float* dst;             /* [sx][sy][sz] */
+  const fsg_tab* tab[3];  /* lengths sx, sy, sz */
+  float* minmax;          /* [2] device: min, max of the zoomed volume */
+  int32_t n[3];           /* source grid of this job (jobs of one launch may differ) */
+  int32_t post;
+} fsg_zoom_job;
+int fsg_zoom_minmax(const fsg_zoom_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+int fsg_zoom(const fsg_zoom_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+
+/* ScaleIntensity(minv=0,maxv=1) standalone: reduce, then (x-min)/(max-min)
+ * (data/datasets.py:40,311). minmax is a [2] device scratch. */
+int fsg_minmax(const float* x, int64_t n, float* minmax, void* stream);
+int fsg_scale_intensity(const float* x, float* out, int64_t n, const float* minmax, void* stream);
+
+/* Label / dtype plumbing at the API edge (data/datasets.py:315-323). */
+int fsg_f32_to_u8(const float* x, uint8_t* out, int64_t n, void* stream);
+int fsg_u8_to_f32(const uint8_t* x, float* out, int64_t n, void* stream);
+int fsg_u8_to_i64(const uint8_t* x, int64_t* out, int64_t n, void* stream);
+
+/* RNG self-test: fills out[n] with Philox standard normals exactly as the kernels draw them;
+ * raw != 0 writes the raw 32-bit words instead (for the Random123 known-answer test). */
+int fsg_philox_fill(fsg_rng rng, float* out, int64_t n, int raw, void* stream);
+
+int fsg_version(void);
+const char* fsg_last_error(void);
+int fsg_sizeof(const char* struct_name); /* ABI check for bindings */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSG_H */

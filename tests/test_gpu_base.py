@@ -1,0 +1,226 @@
+"""GPU parity tests of the base generation path: CUDA kernels (through the C-ABI) vs the
+golden vectors of the unmodified reference and vs the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+import np_oracle as O
+from golden_util import BASE_CASES, load_case, oracle_params
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from fetalsyngen_b200 import _lib
+    from fetalsyngen_b200.engine import SamplePlan, engine_for
+    from gpu_util import DEV, TOL, engine_from_golden, plan_from_golden, rel_err, seeds_from_golden
+
+
+def test_library_loaded_and_abi():
+    lib = _lib.load(build_if_missing=False)
+    assert lib.fsg_version() == 100
+
+
+def test_philox_raw_matches_published_algorithm():
+    n = 4096
+    out = torch.empty(n, dtype=torch.float32, device=DEV)
+    rng = _lib.Rng(0x299F31D0A4093822, 0x0370734413198A2E, 0x85A308D3, 0)
+    _lib.call("fsg_philox_fill", rng, out.data_ptr(), n, 1, torch.cuda.current_stream().cuda_stream)
+    words = out.cpu().numpy().view(np.uint32)
+    for blk in (0, 1, 7, 1023):
+        want = O.philox4x32_10([blk, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])
+        assert list(words[4 * blk : 4 * blk + 4]) == want
+    # Random123 KAT (counter word 0 = 0x243f6a88 is block index 0x243f6a88: check via the oracle at block 0 instead)
+    assert O.philox4x32_10([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_philox_normals_moments_and_independence():
+    n = 1 << 22
+    out = torch.empty(n, dtype=torch.float32, device=DEV)
+    _lib.call("fsg_philox_fill", _lib.Rng(1234, 5, 1, 0), out.data_ptr(), n, 0, torch.cuda.current_stream().cuda_stream)
+    x = out.double()
+    assert abs(x.mean().item()) < 4 / np.sqrt(n)
+    assert abs(x.std().item() - 1) < 3e-3
+    assert abs((x**3).mean().item()) < 0.02 and abs((x**4).mean().item() - 3) < 0.05
+    # lag-1..4 autocorrelation ~ 0 (covers the 4 outputs of one Philox block)
+    for lag in (1, 2, 3, 4, 256):
+        assert abs((x[:-lag] * x[lag:]).mean().item()) < 5 / np.sqrt(n)
+    # Kolmogorov-Smirnov against the normal CDF
+    xs = np.sort(out.cpu().numpy()[: 1 << 18].astype(np.float64))
+    from math import erf
+
+    cdf = 0.5 * (1 + np.vectorize(erf)(xs / np.sqrt(2)))
+    ks = np.abs(cdf - (np.arange(1, xs.size + 1) / xs.size)).max()
+    assert ks < 1.95 / np.sqrt(xs.size)
+    # a different stream is a different sequence
+    out2 = torch.empty(1024, dtype=torch.float32, device=DEV)
+    _lib.call("fsg_philox_fill", _lib.Rng(1234, 6, 1, 0), out2.data_ptr(), 1024, 0, torch.cuda.current_stream().cuda_stream)
+    assert not torch.equal(out[:1024], out2)
+
+
+@pytest.mark.parametrize("name", BASE_CASES)
+def test_gmm_bit_exact(name):
+    d = load_case(name)
+    eng = engine_from_golden(d)
+    plan = plan_from_golden(d)
+    out = torch.empty((1, eng.nvox), dtype=torch.float32, device=DEV)
+    lab = torch.empty((1, eng.nvox), dtype=torch.uint8, device=DEV)
+    eng.gmm([plan], [seeds_from_golden(d)], out, labels_out=lab)
+    np.testing.assert_array_equal(lab.cpu().numpy().reshape(d["labels"].shape), d["labels"])
+    want = d["intensity"] if "intensity" in d else O.gmm_intensities(d["labels"], d["mus"], d["sigmas"], d["gmm_noise"])
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(want.shape), want)
+
+
+@pytest.mark.parametrize("name", [c for c in BASE_CASES if c != "c32_gates_off"])
+def test_warp_coordinates_bit_exact(name):
+    d = load_case(name)
+    eng = engine_from_golden(d)
+    plan = plan_from_golden(d)
+    got = eng.warp_coords(plan).cpu().numpy()
+    if "coords" in d:
+        want = d["coords"]
+    else:
+        p = oracle_params(d)
+        fs = p.get("Fsmall")
+        F = None if fs is None else O.zoom_linear(fs, np.asarray(d["labels"].shape) / np.asarray(fs.shape[:3]))
+        want = np.stack(O.deformation_coords(d["labels"].shape, d["labels"].shape, d["A"], d["c2"], F))
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", BASE_CASES)
+@pytest.mark.parametrize("scale", [False, True])
+def test_base_pipeline_vs_reference_golden(name, scale):
+    d = load_case(name)
+    eng = engine_from_golden(d)
+    plan = plan_from_golden(d)
+    seg = torch.from_numpy(d["seg_in"]).to(DEV).contiguous().view(-1)
+    img, sg = eng.run_base([plan], [seeds_from_golden(d)], [seg], scale=scale)
+    np.testing.assert_array_equal(sg[0].cpu().numpy(), d["seg_out"])  # bit exact
+    want = d["scaled"] if scale else d["final"]
+    assert rel_err(img[0], want) <= TOL
+
+
+@pytest.mark.parametrize("name", [c for c in BASE_CASES if "intensity" in load_case(c)])
+def test_stage_outputs_vs_reference_golden(name):
+    d = load_case(name)
+    eng = engine_from_golden(d)
+    plan = plan_from_golden(d)
+    shape = d["labels"].shape
+    seg = torch.from_numpy(d["seg_in"]).to(DEV).contiguous().view(1, -1)
+    inten = torch.from_numpy(d["intensity"]).to(DEV).contiguous().view(1, -1)
+    # warp + gamma + bias (fused epilogue) vs the reference's bias_out
+    dst = torch.empty_like(inten)
+    dseg = torch.empty_like(seg)
+    eng.warp([plan], inten, seg, dst, dseg)
+    assert rel_err(dst.view(shape), d["bias_out"]) <= TOL
+    # gamma alone and bias alone (identity-mode launches)
+    _, _, st = O.generate_base(d["labels"], d["seg_in"], oracle_params(d))
+    warped = torch.from_numpy(st["warped"]).to(DEV).contiguous().view(1, -1)
+    g = torch.empty_like(warped)
+    eng.warp([SamplePlan(gamma=plan.gamma)], warped, None, g, None)
+    assert rel_err(g.view(shape), d["gamma_out"]) <= TOL
+    # blur
+    if "blurred" in d:
+        src = torch.from_numpy(d["bias_out"]).to(DEV).contiguous().view(1, -1)
+        bl, tmp = torch.empty_like(src), torch.empty_like(src)
+        eng.blur([plan.stds], src, bl, tmp)
+        assert rel_err(bl.view(shape), d["blurred"]) <= TOL
+        low = torch.empty((1, d["lowres"].size), dtype=torch.float32, device=DEV)
+        blurred = torch.from_numpy(d["blurred"]).to(DEV).contiguous().view(1, -1)
+        info = eng.resample([plan], blurred, low)
+        assert info[0][0] == d["lowres"].shape
+        np.testing.assert_allclose(info[0][1], d["factors"], rtol=0, atol=0)
+        assert rel_err(low.view(d["lowres"].shape), d["noisy"]) <= TOL
+        up = torch.empty((1, eng.nvox), dtype=torch.float32, device=DEV)
+        noisy = torch.from_numpy(d["noisy"]).to(DEV).contiguous().view(-1)
+        eng.zoom([noisy], [d["noisy"].shape], [1 / d["factors"]], up, post=1)
+        assert rel_err(up.view(shape), d["final"]) <= 1e-6
+        assert up.max().item() == 1.0
+
+
+def _random_plan(rs, shape, dev, deform=True, resample=True):
+    p = SamplePlan()
+    p.mus = (25 + 200 * rs.rand(50)).astype(np.float32)
+    p.sigmas = (5 + 20 * rs.rand(50)).astype(np.float32)
+    n = int(np.prod(shape))
+    p.gmm_noise = torch.from_numpy(rs.randn(n).astype(np.float32)).to(dev)
+    p.flip = bool(rs.rand() < 0.5)
+    if deform:
+        from fetalsyngen_b200.tables import make_affine_matrix
+
+        rot = (2 * 20 * rs.rand(3) - 20) / 180 * np.pi
+        p.deform = True
+        p.A = make_affine_matrix(rot, 0.04 * rs.rand(3) - 0.02, 1 + 0.2 * rs.rand(3) - 0.1).astype(np.float32)
+        p.c2 = (np.array(shape) - 1) / 2
+        p.center = ((np.array(shape) - 1) / 2).astype(np.float32)
+        s = [max(int(round(0.045 * v * (1 + 0.3 * rs.rand()))), 1) for v in shape]
+        p.fsmall = (3.0 * rs.randn(*s, 3)).astype(np.float32)
+    p.gamma = float(np.exp(0.1 * rs.randn()))
+    b = [max(int(round(0.012 * v)), 1) for v in shape]
+    p.bf_low = (0.2 * rs.randn(*b)).astype(np.float32)
+    if resample:
+        sp = 0.5 + rs.rand()
+        p.spacing = np.array([sp] * 3)
+        from fetalsyngen_b200.tables import resample_stds
+
+        p.stds = resample_stds(p.spacing, [0.5] * 3, rs.rand())
+        p.noise_std = float(5 + 10 * rs.rand())
+        from fetalsyngen_b200.tables import resample_size
+
+        m = int(np.prod([resample_size(v, 0.5, sp) for v in shape]))
+        p.noise = torch.from_numpy(rs.randn(m).astype(np.float32)).to(dev)
+    return p
+
+
+def _plan_to_oracle(p):
+    q = {"mus": p.mus, "sigmas": p.sigmas, "gmm_noise": p.gmm_noise.cpu().numpy(), "flip": p.flip, "resolution": np.array([0.5] * 3)}
+    if p.deform:
+        q.update(A=p.A, c2=p.c2, Fsmall=p.fsmall)
+    q.update(gamma=p.gamma, bf_low=p.bf_low)
+    if p.spacing is not None:
+        q.update(spacing=p.spacing, stds=p.stds, noise_std=p.noise_std, noise=None)
+    return q
+
+
+def _phantom(rs, shape):
+    """Nested-ellipsoid label phantom: seg labels 0..7 and seed labels 0,10..49."""
+    g = np.meshgrid(*[np.linspace(-1, 1, s) for s in shape], indexing="ij")
+    r = np.sqrt(sum((gi / (0.55 + 0.1 * a)) ** 2 for a, gi in enumerate(g)))
+    seg = np.digitize(r, [0.25, 0.45, 0.6, 0.75, 0.85, 0.93, 1.0][::1])
+    seg = (7 - seg).clip(0, 7).astype(np.uint8)
+    sub = rs.randint(0, 4, size=shape)
+    meta = np.array([0, 1, 1, 2, 3, 3, 4, 4])[seg]
+    lab = np.where(meta > 0, meta * 10 + sub, 0).astype(np.int8)
+    seeds = [np.where(meta == m, lab, 0).astype(np.int8) for m in range(1, 5)]
+    return seg, seeds
+
+
+@pytest.mark.parametrize("shape,seed", [((64, 64, 64), 0), ((72, 56, 80), 1), ((96, 96, 96), 2), ((33, 47, 29), 3)])
+def test_base_pipeline_vs_oracle_random(shape, seed):
+    rs = np.random.RandomState(seed)
+    seg, seeds = _phantom(rs, shape)
+    p = _random_plan(rs, shape, DEV)
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    q = _plan_to_oracle(p)
+    q["noise"] = p.noise.cpu().numpy().reshape(eng.lowres_shape(p.spacing))
+    q["gmm_noise"] = q["gmm_noise"].reshape(shape)
+    want_img, want_seg, _ = O.generate_base(sum(s.astype(np.int64) for s in seeds), seg, q)
+    dseeds = [torch.from_numpy(s).to(DEV).view(-1) for s in seeds]
+    img, sg = eng.run_base([p], [dseeds], [torch.from_numpy(seg).to(DEV).view(-1)])
+    np.testing.assert_array_equal(sg[0].cpu().numpy(), want_seg)
+    assert rel_err(img[0], want_img) <= TOL
+
+
+def test_batched_launch_equals_single_launches():
+    shape = (48, 40, 56)
+    rs = np.random.RandomState(5)
+    seg, seeds = _phantom(rs, shape)
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    plans = [_random_plan(rs, shape, DEV, deform=(i != 2), resample=(i != 1)) for i in range(4)]
+    plans[3].noise_std, plans[3].noise = None, None
+    dseeds = [torch.from_numpy(s).to(DEV).view(-1) for s in seeds]
+    dseg = torch.from_numpy(seg).to(DEV).view(-1)
+    img_b, seg_b = eng.run_base(plans, [dseeds] * 4, [dseg] * 4)
+    img_b, seg_b = img_b.clone(), seg_b.clone()
+    for i, p in enumerate(plans):
+        im, sg = eng.run_base([p], [dseeds], [dseg])
+        assert torch.equal(im[0], img_b[i]) and torch.equal(sg[0], seg_b[i])
