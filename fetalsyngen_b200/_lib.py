@@ -53,7 +53,20 @@ class ZoomJob(C.Structure):
     _fields_ = [("src", _vp), ("dst", _vp), ("tab", _vp * 3), ("minmax", _vp), ("n", _i32 * 3), ("post", _i32)]
 
 
-_STRUCTS = {"fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
+class SepAxis(C.Structure):
+    _fields_ = [("q0", _vp), ("w", _vp), ("n_out", _i32), ("width", _i32)]
+
+
+class SepconvJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("tmp1", _vp), ("tmp2", _vp), ("ax", SepAxis * 3), ("noise", _vp), ("rng", Rng),
+                ("noise_std", _f32), ("has_noise", _i32)]
+
+
+class SepComposeJob(C.Structure):
+    _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32)]
+
+
+_STRUCTS = {"fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
@@ -66,6 +79,8 @@ SIGNATURES = {
     "fsg_warp": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "fsg_warp_coords": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "fsg_blur3d": (C.c_int, [C.POINTER(BlurJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_sep_compose": (C.c_int, [C.POINTER(SepComposeJob), C.c_int, _vp]),
+    "fsg_sepconv": (C.c_int, [C.POINTER(SepconvJob), C.c_int] + [C.c_int] * 3 + [_vp]),
     "fsg_resample": (C.c_int, [C.POINTER(ResampleJob), C.c_int] + [C.c_int] * 3 + [_vp]),
     "fsg_add_noise": (C.c_int, [C.POINTER(NoiseJob), C.c_int, _i64, _vp]),
     "fsg_zoom_minmax": (C.c_int, [C.POINTER(ZoomJob), C.c_int] + [C.c_int] * 3 + [_vp]),

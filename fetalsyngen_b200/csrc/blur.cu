@@ -1,7 +1,8 @@
-// K4a — separable zero-padded Gaussian blur (utils/generation.py:84-110).
-// v1: one pass per axis, x then y then z like the reference's three conv3d calls; every pass
-// reads and writes the volume once (8 B/voxel/pass).  Taps are built on the host with the
-// reference's expressions (make_gaussian_kernel, utils/generation.py:74-81).
+// K4a (stand-alone stage API) — separable zero-padded Gaussian blur in the reference's exact
+// arithmetic order (utils/generation.py:84-110): one pass per axis, x then y then z like the
+// three conv3d calls, taps accumulated in index order without FMA.  Taps are built on the host
+// with the reference's expressions (make_gaussian_kernel, utils/generation.py:74-81).
+// The fused production path (blur composed with the down-sampling) is sepconv.cu.
 #include "common.cuh"
 
 namespace fsg {
@@ -26,21 +27,22 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_axis_kernel(const __grid_co
   const float* __restrict__ src = p.src[jb];
   float* __restrict__ dst = p.dst[jb];
   const int r = nt / 2;
-  const int64_t n = (int64_t)sx * sy * sz;
-  const int64_t stride = (int64_t)gridDim.x * BLUR_THREADS;
-  const int64_t astride = AXIS == 0 ? (int64_t)sy * sz : (AXIS == 1 ? sz : 1);
+  const unsigned n = (unsigned)sx * sy * sz;  // < 2^31 (checked by the caller)
+  const unsigned stride = gridDim.x * BLUR_THREADS;
+  const int astride = AXIS == 0 ? sy * sz : (AXIS == 1 ? sz : 1);
   const int alen = AXIS == 0 ? sx : (AXIS == 1 ? sy : sz);
-  for (int64_t v = (int64_t)blockIdx.x * BLUR_THREADS + threadIdx.x; v < n; v += stride) {
+  for (unsigned v = blockIdx.x * BLUR_THREADS + threadIdx.x; v < n; v += stride) {
     int pos;
     if (AXIS == 2)
-      pos = (int)(v % sz);
+      pos = (int)(v % (unsigned)sz);
     else if (AXIS == 1)
-      pos = (int)((v / sz) % sy);
+      pos = (int)((v / (unsigned)sz) % (unsigned)sy);
     else
-      pos = (int)(v / ((int64_t)sy * sz));
+      pos = (int)(v / ((unsigned)sy * sz));
     float acc = 0.f;
     const int t0 = max(0, r - pos), t1 = min(nt, alen + r - pos);
-    for (int t = t0; t < t1; ++t) acc = add_rn(acc, mul_rn(s_w[t], __ldg(src + v + (int64_t)(t - r) * astride)));
+    const float* __restrict__ q = src + (int)v - r * astride;
+    for (int t = t0; t < t1; ++t) acc = add_rn(acc, mul_rn(s_w[t], __ldg(q + t * astride)));
     dst[v] = acc;
   }
 }
@@ -57,7 +59,7 @@ using namespace fsg;
 extern "C" int fsg_blur3d(const fsg_blur_job* jobs, int njobs, int sx, int sy, int sz, void* stream) {
   FSG_REQUIRE(jobs != nullptr, "fsg_blur3d: jobs pointer is NULL");
   FSG_REQUIRE(njobs >= 1 && njobs <= FSG_MAX_JOBS, "fsg_blur3d: njobs=%d outside [1,%d]", njobs, FSG_MAX_JOBS);
-  FSG_REQUIRE(sx >= 1 && sy >= 1 && sz >= 1, "fsg_blur3d: bad shape");
+  FSG_REQUIRE(sx >= 1 && sy >= 1 && sz >= 1 && (int64_t)sx * sy * sz < ((int64_t)1 << 31), "fsg_blur3d: bad shape");
   cudaStream_t s = as_stream(stream);
   const int64_t n = (int64_t)sx * sy * sz;
   const int64_t want = (n + BLUR_THREADS - 1) / BLUR_THREADS;

@@ -110,6 +110,9 @@ int fsg_sizeof(const char* name) {
   FSG_SZ(fsg_resample_job)
   FSG_SZ(fsg_noise_job)
   FSG_SZ(fsg_zoom_job)
+  FSG_SZ(fsg_sepaxis)
+  FSG_SZ(fsg_sepconv_job)
+  FSG_SZ(fsg_sepcompose_job)
 #undef FSG_SZ
   return -1;
 }

@@ -1,9 +1,8 @@
-// K4b/K4c — regular-grid resampling kernels.
-//  fsg_resample : trilinear down-sampling onto the coarse grid + additive noise
+// K4b — regular-grid resampling kernels (stand-alone stage API; the fused production path is
+// sepconv.cu).
+//  fsg_resample : trilinear down-sampling onto the coarse grid + additive noise, bit-exact
+//                 arithmetic order of the reference
 //                 (augmentation/synthseg.py:84-107 -> utils/generation.py:227-285; :217-235)
-//  fsg_zoom     : separable linear zoom with myzoom_torch's rounding order
-//                 (utils/generation.py:363-386), optional /max and ScaleIntensity epilogues
-//                 (synthseg.py:109-114, data/datasets.py:311), and its min/max pre-pass.
 //  fsg_add_noise: elementwise noise at any resolution.
 #include "common.cuh"
 
@@ -34,9 +33,9 @@ __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_const
     for (int e = 0; e < 4; ++e) {
       const int64_t v = g * 4 + e;
       if (v >= n) break;
-      const int k = (int)(v % n2);
-      const int64_t q = v / n2;
-      const int j = (int)(q % n1), i = (int)(q / n1);
+      const unsigned vv = (unsigned)v, q = vv / (unsigned)n2;
+      const int k = (int)(vv - q * (unsigned)n2);
+      const int i = (int)(q / (unsigned)n1), j = (int)(q - (unsigned)i * (unsigned)n1);
       const fsg_tab ex = job.tab[0][i], ey = job.tab[1][j], ez = job.tab[2][k];
       float val = 0.f;
       if (ex.f >= 0 && ey.f >= 0 && ez.f >= 0) {
@@ -83,107 +82,9 @@ __global__ void __launch_bounds__(RS_THREADS) noise_kernel(const __grid_constant
   }
 }
 
-// myzoom_torch value at output voxel (i,j,k): x-blend, then y-blend, then z-blend.
-__device__ __forceinline__ float zoom_value(const float* __restrict__ src, int n1, int n2, const Tab& tx, const Tab& ty, const Tab& tz) {
-  const float* pff = src + ((size_t)tx.f * n1 + ty.f) * n2;
-  const float* pcf = src + ((size_t)tx.c * n1 + ty.f) * n2;
-  const float* pfc = src + ((size_t)tx.f * n1 + ty.c) * n2;
-  const float* pcc = src + ((size_t)tx.c * n1 + ty.c) * n2;
-  const float a_ff = blend(tx.wf, __ldg(pff + tz.f), tx.wc, __ldg(pcf + tz.f));  // tmp1[y=f, z=f]
-  const float a_fc = blend(tx.wf, __ldg(pff + tz.c), tx.wc, __ldg(pcf + tz.c));  // tmp1[y=f, z=c]
-  const float a_cf = blend(tx.wf, __ldg(pfc + tz.f), tx.wc, __ldg(pcc + tz.f));  // tmp1[y=c, z=f]
-  const float a_cc = blend(tx.wf, __ldg(pfc + tz.c), tx.wc, __ldg(pcc + tz.c));  // tmp1[y=c, z=c]
-  const float b_f = blend(ty.wf, a_ff, ty.wc, a_cf);                             // tmp2[z=f]
-  const float b_c = blend(ty.wf, a_fc, ty.wc, a_cc);                             // tmp2[z=c]
-  return blend(tz.wf, b_f, tz.wc, b_c);
-}
-
-template <bool REDUCE>
-__global__ void __launch_bounds__(RS_THREADS) zoom_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int sx, int sy, int sz) {
-  const fsg_zoom_job& job = batch.j[blockIdx.y];
-  const int n1 = job.n[1], n2 = job.n[2];
-  const float* __restrict__ src = job.src;
-  const int64_t n = (int64_t)sx * sy * sz;
-  const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
-  const float inf = __int_as_float(0x7f800000);
-  float lo = inf, hi = -inf;
-  float vmax = 1.f, qmin = 0.f, den = 1.f;
-  if (!REDUCE && job.post > 0) {
-    vmax = job.minmax[1];
-    qmin = __fdiv_rn(job.minmax[0], vmax);
-    den = sub_rn(__fdiv_rn(vmax, vmax), qmin);
-  }
-  for (int64_t v = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; v < n; v += stride) {
-    const int k = (int)(v % sz);
-    const int64_t q = v / sz;
-    const int j = (int)(q % sy), i = (int)(q / sy);
-    const Tab tx = load_tab(job.tab[0], i), ty = load_tab(job.tab[1], j), tz = load_tab(job.tab[2], k);
-    float val = zoom_value(src, n1, n2, tx, ty, tz);
-    if (REDUCE) {
-      lo = fminf(lo, val);
-      hi = fmaxf(hi, val);
-    } else {
-      if (job.post >= 1) val = __fdiv_rn(val, vmax);
-      if (job.post >= 2) val = __fdiv_rn(sub_rn(val, qmin), den);
-      job.dst[v] = val;
-    }
-  }
-  if (REDUCE) {
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    __shared__ float slo[RS_THREADS / 32], shi[RS_THREADS / 32];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) {
-      slo[w] = lo;
-      shi[w] = hi;
-    }
-    __syncthreads();
-    if (w == 0) {
-      lo = l < RS_THREADS / 32 ? slo[l] : inf;
-      hi = l < RS_THREADS / 32 ? shi[l] : -inf;
-      lo = warp_min(lo);
-      hi = warp_max(hi);
-      if (l == 0) {
-        atomicMin(reinterpret_cast<int*>(job.minmax), float_to_ordered(lo));
-        atomicMax(reinterpret_cast<int*>(job.minmax) + 1, float_to_ordered(hi));
-      }
-    }
-  }
-}
-
-__global__ void zoom_mm_init_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int njobs) {
-  const int t = threadIdx.x;
-  if (t < njobs) {
-    int* p = reinterpret_cast<int*>(batch.j[t].minmax);
-    p[0] = float_to_ordered(__int_as_float(0x7f800000));
-    p[1] = float_to_ordered(__int_as_float(0xff800000));
-  }
-}
-__global__ void zoom_mm_final_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int njobs) {
-  const int t = threadIdx.x;
-  if (t < njobs * 2) {
-    float* p = batch.j[t / 2].minmax + (t % 2);
-    *p = ordered_to_float(*reinterpret_cast<int*>(p));
-  }
-}
-
 static unsigned grid_x(int64_t work) {
   const int64_t want = (work + RS_THREADS - 1) / RS_THREADS;
   return (unsigned)(want < 148 * 32 ? (want < 1 ? 1 : want) : 148 * 32);
-}
-
-static int check_zoom(const fsg_zoom_job* jobs, int njobs, int sx, int sy, int sz, bool need_dst, const char* who) {
-  FSG_REQUIRE(sx >= 1 && sy >= 1 && sz >= 1, "%s: bad shape", who);
-  for (int i = 0; i < njobs; ++i) {
-    const fsg_zoom_job& j = jobs[i];
-    FSG_REQUIRE(j.n[0] >= 1 && j.n[1] >= 1 && j.n[2] >= 1, "%s: job %d bad source shape", who, i);
-    FSG_REQUIRE(j.n[0] <= 32767 && j.n[1] <= 32767 && j.n[2] <= 32767, "%s: source extent exceeds the int16 table range", who);
-    FSG_REQUIRE(j.src && j.tab[0] && j.tab[1] && j.tab[2], "%s: job %d has a NULL src/table", who, i);
-    FSG_REQUIRE(!need_dst || j.dst, "%s: job %d has a NULL dst", who, i);
-    FSG_REQUIRE(j.post >= 0 && j.post <= 2, "%s: job %d post must be 0..2", who, i);
-    FSG_REQUIRE((j.post == 0 && need_dst) || j.minmax, "%s: job %d needs a minmax buffer", who, i);
-  }
-  return 0;
 }
 
 }  // namespace fsg
@@ -206,7 +107,7 @@ extern "C" int fsg_resample(const fsg_resample_job* jobs, int njobs, int sx, int
     if (j.has_noise && j.noise) inject = true;
   }
   for (int i = 0; i < njobs; ++i) FSG_REQUIRE(!jobs[i].has_noise || ((jobs[i].noise != nullptr) == inject), "fsg_resample: jobs mix injected and Philox noise");
-  FSG_REQUIRE(n / 4 < (int64_t)1 << 32, "fsg_resample: volume too large");
+  FSG_REQUIRE(n < ((int64_t)1 << 31), "fsg_resample: volume too large");
   dim3 grid(grid_x((n + 3) / 4), (unsigned)njobs);
   if (inject)
     resample_kernel<true><<<grid, RS_THREADS, 0, as_stream(stream)>>>(b, sx, sy, sz);
@@ -232,23 +133,3 @@ extern "C" int fsg_add_noise(const fsg_noise_job* jobs, int njobs, int64_t nvox,
   return check_launch("fsg_add_noise");
 }
 
-extern "C" int fsg_zoom_minmax(const fsg_zoom_job* jobs, int njobs, int sx, int sy, int sz, void* stream) {
-  Batch<fsg_zoom_job> b;
-  if (int rc = fill_batch(b, jobs, njobs)) return rc;
-  if (int rc = check_zoom(jobs, njobs, sx, sy, sz, false, "fsg_zoom_minmax")) return rc;
-  cudaStream_t s = as_stream(stream);
-  zoom_mm_init_kernel<<<1, 32, 0, s>>>(b, njobs);
-  dim3 grid(grid_x((int64_t)sx * sy * sz), (unsigned)njobs);
-  zoom_kernel<true><<<grid, RS_THREADS, 0, s>>>(b, sx, sy, sz);
-  zoom_mm_final_kernel<<<1, 32, 0, s>>>(b, njobs);
-  return check_launch("fsg_zoom_minmax");
-}
-
-extern "C" int fsg_zoom(const fsg_zoom_job* jobs, int njobs, int sx, int sy, int sz, void* stream) {
-  Batch<fsg_zoom_job> b;
-  if (int rc = fill_batch(b, jobs, njobs)) return rc;
-  if (int rc = check_zoom(jobs, njobs, sx, sy, sz, true, "fsg_zoom")) return rc;
-  dim3 grid(grid_x((int64_t)sx * sy * sz), (unsigned)njobs);
-  zoom_kernel<false><<<grid, RS_THREADS, 0, as_stream(stream)>>>(b, sx, sy, sz);
-  return check_launch("fsg_zoom");
-}

@@ -1,0 +1,418 @@
+// K4ab — separable banded resampling: out = (Rx (x) Ry (x) Rz) in.
+//
+// The reference blurs the full-resolution volume with three zero-padded 1-D Gaussian
+// convolutions and then samples it trilinearly on the coarse grid
+// (augmentation/synthseg.py:63-107 -> utils/generation.py:84-110, 227-285).  Both steps are
+// linear and separable, so per axis they compose into ONE banded matrix R_a (n_out x n_in)
+// whose row I holds  w_f*taps(. - f_I) + w_c*taps(. - c_I)  (zero rows where the reference's
+// linear sampler returns 0, zero padding = dropped taps).  The host builds the rows in float64
+// (fetalsyngen_b200/tables.py:sep_axis_table); the device applies them axis by axis, shrinking
+// the volume at every pass:
+//     x: [sx][sy][sz] -> [n0][sy][sz]     streaming, register sliding window, 4N + 4fN bytes
+//     y: [n0][sy][sz] -> [n0][n1][sz]     streaming, register sliding window
+//     z: [n0][n1][sz] -> [n0][n1][n2]     rows staged in shared memory, + RandNoise epilogue
+// instead of 3 full-resolution blur passes + a gather (24 N + 4(N+n^3) bytes before).
+// With identity positions the same kernels are a plain separable blur (BlurCortex).
+// Float image path: FMA accumulation, parity is the 1e-4 tolerance (tests/test_gpu_base.py).
+#include "common.cuh"
+
+namespace fsg {
+
+constexpr int SEP_THREADS = 128;
+constexpr int SEPZ_THREADS = 256;
+constexpr int SEPZ_ROWS = 32;
+
+struct SepPass {
+  const float* src[FSG_MAX_JOBS];
+  float* dst[FSG_MAX_JOBS];
+  const int16_t* q0[FSG_MAX_JOBS];
+  const float* w[FSG_MAX_JOBS];
+  int n_out[FSG_MAX_JOBS];
+  int width[FSG_MAX_JOBS];
+  int outer[FSG_MAX_JOBS];  // slow dimension count of this pass (1 for x, n0 for y, n0*n1 for z)
+};
+
+struct SepNoise {
+  const float* noise[FSG_MAX_JOBS];
+  fsg_rng rng[FSG_MAX_JOBS];
+  float std[FSG_MAX_JOBS];
+  int has[FSG_MAX_JOBS];
+};
+
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ void fma(T& a, float w, const T& v) { a = __fmaf_rn(w, v, a); }
+};
+template <>
+struct VecT<2> {
+  using T = float2;
+  static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ void fma(T& a, float w, const T& v) {
+    a.x = __fmaf_rn(w, v.x, a.x);
+    a.y = __fmaf_rn(w, v.y, a.y);
+  }
+};
+
+// Streaming pass along a slow axis.  The volume is viewed as [outer][a_in][inner]; a thread owns
+// VEC consecutive inner elements of one `outer` slab and walks the axis once, keeping the last W
+// planes in a rotating register window (slot = plane index mod W, static after unrolling).
+// Output I is emitted when its last source plane has been loaded; its weights are stored
+// right-aligned in a W-wide row, so the tap loop is W FMAs on statically indexed registers.
+template <int W, int VEC>
+__global__ void __launch_bounds__(SEP_THREADS) sep_stream_kernel(const __grid_constant__ SepPass p, int a_in, int inner) {
+  using V = VecT<VEC>;
+  using T = typename V::T;
+  const int jb = blockIdx.y;
+  const int n_out = p.n_out[jb], width = p.width[jb], outer = p.outer[jb];
+  extern __shared__ float s_mem[];
+  float* s_w = s_mem;                                       // [n_out][W], right-aligned
+  int* s_last = reinterpret_cast<int*>(s_mem + n_out * W);  // [n_out] last source plane of each output
+  for (int e = threadIdx.x; e < n_out * W; e += SEP_THREADS) {
+    const int I = e / W, t = e - I * W - (W - width);
+    s_w[e] = t >= 0 ? p.w[jb][I * width + t] : 0.f;
+  }
+  for (int I = threadIdx.x; I < n_out; I += SEP_THREADS) s_last[I] = (int)p.q0[jb][I] + width - 1;
+  __syncthreads();
+
+  const int cols = inner / VEC;
+  const int chunks = (cols + SEP_THREADS - 1) / SEP_THREADS;
+  for (int chunk = blockIdx.x; chunk < outer * chunks; chunk += gridDim.x) {
+    const int o = chunk / chunks, c = (chunk - o * chunks) * SEP_THREADS + threadIdx.x;
+    if (c >= cols) continue;
+    const T* __restrict__ in = reinterpret_cast<const T*>(p.src[jb] + (size_t)o * a_in * inner) + c;
+    T* __restrict__ out = reinterpret_cast<T*>(p.dst[jb] + (size_t)o * n_out * inner) + c;
+    T win[W];
+#pragma unroll
+    for (int u = 0; u < W; ++u) win[u] = V::zero();
+    int I = 0;
+    int next_last = s_last[0];
+    for (int qb = 0; qb < a_in; qb += W) {
+      T cur[W];
+#pragma unroll
+      for (int u = 0; u < W; ++u) cur[u] = (qb + u < a_in) ? __ldcs(in + (size_t)(qb + u) * cols) : V::zero();
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        win[u] = cur[u];
+        const int q = qb + u;
+        while (next_last == q) {
+          const float4* wr = reinterpret_cast<const float4*>(s_w + I * W);
+          T acc = V::zero();
+#pragma unroll
+          for (int t4 = 0; t4 < W / 4; ++t4) {
+            const float4 w4 = wr[t4];
+            V::fma(acc, w4.x, win[(u + 1 + 4 * t4 + 0) % W]);
+            V::fma(acc, w4.y, win[(u + 1 + 4 * t4 + 1) % W]);
+            V::fma(acc, w4.z, win[(u + 1 + 4 * t4 + 2) % W]);
+            V::fma(acc, w4.w, win[(u + 1 + 4 * t4 + 3) % W]);
+          }
+          out[(size_t)I * cols] = acc;
+          ++I;
+          next_last = I < n_out ? s_last[I] : -1;
+        }
+      }
+    }
+  }
+}
+
+// Last pass: rows of the fast axis staged in shared memory.  Thread = one output position K
+// (its W weights live in registers) looping over the block's rows; lanes are consecutive K,
+// so the stores are coalesced and the shared-memory reads stride by ~1/factor.
+// RandNoise epilogue (synthseg.py:217-235): out = max(0, out + std*N).  Philox counter layout of
+// this stream: block = row * ceil(n2/4) + K/4, component K%4; every lane draws one block per
+// four rows and the normals are handed out by shuffles, so no draw is computed twice.
+template <int W, bool INJECT>
+__global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_constant__ SepPass p, const __grid_constant__ SepNoise nz, int a_in) {
+  const int jb = blockIdx.y;
+  const int n_out = p.n_out[jb], width = p.width[jb], rows = p.outer[jb];
+  extern __shared__ float s_rows[];  // [SEPZ_ROWS][a_in]
+  const int row0 = blockIdx.x * SEPZ_ROWS;
+  if (row0 >= rows) return;
+  const int nrow = min(SEPZ_ROWS, rows - row0);
+  {
+    const float* __restrict__ src = p.src[jb] + (size_t)row0 * a_in;
+    const int n = nrow * a_in;
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (n % 4 == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(s_rows);
+      for (int e = threadIdx.x; e < n / 4; e += SEPZ_THREADS) d4[e] = __ldcs(s4 + e);
+    } else {
+      for (int e = threadIdx.x; e < n; e += SEPZ_THREADS) s_rows[e] = __ldcs(src + e);
+    }
+  }
+  __syncthreads();
+
+  const int kw = (n_out + 31) & ~31;                        // K extent rounded to whole warps
+  const int groups = kw <= SEPZ_THREADS ? SEPZ_THREADS / kw : 1;  // row groups working in parallel
+  const int g = threadIdx.x / kw;
+  const bool has_noise = nz.has[jb] != 0;
+  const float nstd = nz.std[jb];
+  const int kgroups = (n_out + 3) >> 2;
+  const int lane = threadIdx.x & 31;
+  if (g >= groups) return;  // whole warps only (kw is a multiple of 32)
+  for (int kb = threadIdx.x - g * kw; kb < kw; kb += (groups == 1 ? SEPZ_THREADS : kw)) {
+    const int K = kb;
+    const bool live = K < n_out;
+    float wreg[W];
+    int q0 = 0;
+    if (live) {
+      q0 = (int)p.q0[jb][K] - (W - width);  // right-aligned window start (may be < 0: zero weights there)
+#pragma unroll
+      for (int t = 0; t < W; ++t) wreg[t] = (t >= W - width) ? __ldg(p.w[jb] + K * width + (t - (W - width))) : 0.f;
+    } else {
+#pragma unroll
+      for (int t = 0; t < W; ++t) wreg[t] = 0.f;
+    }
+    const int qlo = max(q0, 0);
+    const int skip = qlo - q0;  // leading window slots that fall before the row start
+    const int kbase = K - lane;
+    float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+    int m = 0;
+    for (int r = g; r < nrow; r += groups, ++m) {
+      float acc = 0.f;
+      if (live) {
+        const float* row = s_rows + r * a_in + q0;
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+          const float v = (t >= skip) ? row[t] : 0.f;
+          acc = __fmaf_rn(wreg[t], v, acc);
+        }
+      }
+      if (has_noise) {
+        float nv;
+        if (INJECT) {
+          nv = live ? __ldg(nz.noise[jb] + (size_t)(row0 + r) * n_out + K) : 0.f;
+        } else {
+          if ((m & 3) == 0) {
+            // lane l draws the block of row slot (l>>3) and K-group (l&7) of this warp's 32 outputs
+            const int rr = r + (lane >> 3) * groups;
+            const uint32_t blk = (uint32_t)(row0 + rr) * (uint32_t)kgroups + (uint32_t)((kbase >> 2) + (lane & 7));
+            nrm = philox_normal4(nz.rng[jb], blk);
+          }
+          const int srcl = (m & 3) * 8 + (lane >> 2);
+          const float a = __shfl_sync(0xffffffffu, nrm.x, srcl), b = __shfl_sync(0xffffffffu, nrm.y, srcl);
+          const float c = __shfl_sync(0xffffffffu, nrm.z, srcl), d = __shfl_sync(0xffffffffu, nrm.w, srcl);
+          const int comp = lane & 3;
+          nv = comp == 0 ? a : (comp == 1 ? b : (comp == 2 ? c : d));
+        }
+        acc = __fmaf_rn(nstd, nv, acc);
+        acc = acc < 0.f ? 0.f : acc;
+      }
+      if (live) p.dst[jb][(size_t)(row0 + r) * n_out + K] = acc;
+    }
+  }
+}
+
+// Generic fallback for windows wider than the register variants (very wide blurs): one thread
+// per output element, taps read through L1.  View [outer][a_in][inner] -> [outer][n_out][inner].
+template <bool INJECT>
+__global__ void __launch_bounds__(256) sep_generic_kernel(const __grid_constant__ SepPass p, const __grid_constant__ SepNoise nz, int a_in, int inner, int last) {
+  const int jb = blockIdx.y;
+  const int n_out = p.n_out[jb], width = p.width[jb], outer = p.outer[jb];
+  const int64_t total = (int64_t)outer * n_out * inner;
+  const int kgroups = (n_out + 3) >> 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % inner);
+    const int64_t oi = e / inner;
+    const int I = (int)(oi % n_out), o = (int)(oi / n_out);
+    const float* __restrict__ in = p.src[jb] + ((size_t)o * a_in + p.q0[jb][I]) * inner + c;
+    const float* __restrict__ w = p.w[jb] + I * width;
+    float acc = 0.f;
+    for (int t = 0; t < width; ++t) acc = __fmaf_rn(__ldg(w + t), __ldg(in + (size_t)t * inner), acc);
+    if (last && nz.has[jb]) {
+      float nv;
+      if (INJECT) {
+        nv = __ldg(nz.noise[jb] + e);
+      } else {
+        const float4 q = philox_normal4(nz.rng[jb], (uint32_t)o * (uint32_t)kgroups + (uint32_t)(I >> 2));
+        const int comp = I & 3;
+        nv = comp == 0 ? q.x : (comp == 1 ? q.y : (comp == 2 ? q.z : q.w));
+      }
+      acc = __fmaf_rn(nz.std[jb], nv, acc);
+      acc = acc < 0.f ? 0.f : acc;
+    }
+    p.dst[jb][e] = acc;
+  }
+}
+
+// Builds the banded rows on the device: row I = w_f*taps(. - f_I) + w_c*taps(. - c_I) restricted
+// to the window [q0, q0+width) (taps falling outside [0, n_in) are the zero padding).
+struct ComposeBatch {
+  fsg_sepcompose_job j[3 * FSG_MAX_JOBS];
+};
+__global__ void __launch_bounds__(128) sep_compose_kernel(const __grid_constant__ ComposeBatch b) {
+  const fsg_sepcompose_job& job = b.j[blockIdx.y];
+  const int nt = job.taps ? job.ntaps : 1, r = nt / 2, width = job.width;
+  for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < job.n_out; I += gridDim.x * blockDim.x) {
+    int f = I, c = I;
+    float wc = 0.f;
+    if (job.pos) {
+      const fsg_tab e = job.pos[I];
+      f = e.f;
+      c = e.c;
+      wc = e.wc;
+    }
+    const bool outside = f < 0;
+    const float wf = __fsub_rn(1.0f, wc);
+    int q0 = outside ? (2 * I < job.n_out ? 0 : job.n_in - width) : min(max(f - r, 0), job.n_in - width);
+    job.q0_out[I] = (int16_t)q0;
+    for (int s = 0; s < width; ++s) {
+      const int q = q0 + s;
+      float w = 0.f;
+      if (!outside) {
+        const int t1 = q - (f - r), t2 = q - (c - r);
+        if (t1 >= 0 && t1 < nt) w = __fmul_rn(wf, job.taps ? job.taps[t1] : 1.0f);
+        if (t2 >= 0 && t2 < nt) w = __fmaf_rn(wc, job.taps ? job.taps[t2] : 1.0f, w);
+      }
+      job.w_out[I * width + s] = w;
+    }
+  }
+}
+
+template <int W, int VEC>
+static void launch_stream(const SepPass& p, int njobs, int a_in, int inner, int max_nout, int max_outer, cudaStream_t s) {
+  const size_t smem = (size_t)max_nout * (W + 1) * sizeof(float);
+  auto k = sep_stream_kernel<W, VEC>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int chunks = ((inner / VEC) + SEP_THREADS - 1) / SEP_THREADS;
+  int64_t want = (int64_t)max_outer * chunks;
+  const int cap = 148 * 12;
+  const unsigned gx = (unsigned)(want < cap ? want : cap);
+  k<<<dim3(gx, njobs), SEP_THREADS, smem, s>>>(p, a_in, inner);
+}
+
+template <int W>
+static void launch_z(const SepPass& p, const SepNoise& nz, int njobs, int a_in, int max_rows, bool inject, cudaStream_t s) {
+  const size_t smem = (size_t)SEPZ_ROWS * a_in * sizeof(float);
+  const unsigned gx = (unsigned)((max_rows + SEPZ_ROWS - 1) / SEPZ_ROWS);
+  if (inject) {
+    auto k = sep_z_kernel<W, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<dim3(gx, njobs), SEPZ_THREADS, smem, s>>>(p, nz, a_in);
+  } else {
+    auto k = sep_z_kernel<W, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<dim3(gx, njobs), SEPZ_THREADS, smem, s>>>(p, nz, a_in);
+  }
+}
+
+}  // namespace fsg
+
+using namespace fsg;
+
+extern "C" int fsg_sep_compose(const fsg_sepcompose_job* jobs, int njobs, void* stream) {
+  FSG_REQUIRE(jobs != nullptr, "fsg_sep_compose: jobs pointer is NULL");
+  FSG_REQUIRE(njobs >= 1 && njobs <= 3 * FSG_MAX_JOBS, "fsg_sep_compose: njobs=%d outside [1,%d]", njobs, 3 * FSG_MAX_JOBS);
+  ComposeBatch b;
+  memset(&b, 0, sizeof(b));
+  int max_n = 1;
+  for (int i = 0; i < njobs; ++i) {
+    const fsg_sepcompose_job& j = jobs[i];
+    FSG_REQUIRE(j.q0_out && j.w_out, "fsg_sep_compose: job %d has a NULL output", i);
+    FSG_REQUIRE(j.n_in >= 1 && j.n_in <= 32767 && j.n_out >= 1 && j.n_out <= 32767, "fsg_sep_compose: job %d bad extents", i);
+    FSG_REQUIRE(j.pos || j.n_out == j.n_in, "fsg_sep_compose: job %d identity positions need n_out == n_in", i);
+    const int nt = j.taps ? j.ntaps : 1;
+    FSG_REQUIRE(nt >= 1 && nt % 2 == 1 && nt <= FSG_MAX_TAPS, "fsg_sep_compose: job %d needs an odd tap count <= %d", i, FSG_MAX_TAPS);
+    const int need = nt + (j.pos ? 1 : 0);
+    FSG_REQUIRE(j.width == (need < j.n_in ? need : j.n_in), "fsg_sep_compose: job %d width must be min(n_in, ntaps + (pos != NULL))", i);
+    b.j[i] = j;
+    if (j.n_out > max_n) max_n = j.n_out;
+  }
+  sep_compose_kernel<<<dim3((max_n + 127) / 128, njobs), 128, 0, as_stream(stream)>>>(b);
+  return check_launch("fsg_sep_compose");
+}
+
+extern "C" int fsg_sepconv(const fsg_sepconv_job* jobs, int njobs, int sx, int sy, int sz, void* stream) {
+  FSG_REQUIRE(jobs != nullptr, "fsg_sepconv: jobs pointer is NULL");
+  FSG_REQUIRE(njobs >= 1 && njobs <= FSG_MAX_JOBS, "fsg_sepconv: njobs=%d outside [1,%d]", njobs, FSG_MAX_JOBS);
+  FSG_REQUIRE(sx >= 1 && sy >= 1 && sz >= 1 && sx <= 32767 && sy <= 32767 && sz <= 32767, "fsg_sepconv: bad shape");
+  cudaStream_t s = as_stream(stream);
+  const int n_in[3] = {sx, sy, sz};
+  bool inject = false, any_noise = false;
+  for (int i = 0; i < njobs; ++i) {
+    const fsg_sepconv_job& j = jobs[i];
+    FSG_REQUIRE(j.src && j.dst && j.tmp1 && j.tmp2, "fsg_sepconv: job %d has a NULL buffer", i);
+    FSG_REQUIRE(j.src != j.dst && j.src != j.tmp1 && j.tmp1 != j.tmp2 && j.tmp2 != j.dst, "fsg_sepconv: job %d: adjacent passes must not alias", i);
+    for (int a = 0; a < 3; ++a) {
+      const fsg_sepaxis& ax = j.ax[a];
+      FSG_REQUIRE(ax.q0 && ax.w, "fsg_sepconv: job %d axis %d has a NULL table", i, a);
+      FSG_REQUIRE(ax.n_out >= 1 && ax.n_out <= 32767, "fsg_sepconv: job %d axis %d bad n_out", i, a);
+      FSG_REQUIRE(ax.width >= 1 && ax.width <= n_in[a] && ax.width <= 2 * FSG_MAX_TAPS, "fsg_sepconv: job %d axis %d width %d outside [1,min(%d,%d)]", i, a, ax.width, n_in[a], 2 * FSG_MAX_TAPS);
+    }
+    if (j.has_noise) {
+      any_noise = true;
+      if (j.noise) inject = true;
+    }
+  }
+  for (int i = 0; i < njobs; ++i) FSG_REQUIRE(!jobs[i].has_noise || ((jobs[i].noise != nullptr) == inject), "fsg_sepconv: jobs mix injected and Philox noise");
+  (void)any_noise;
+
+  SepNoise nz;
+  memset(&nz, 0, sizeof(nz));
+  for (int i = 0; i < njobs; ++i) {
+    nz.noise[i] = jobs[i].noise;
+    nz.rng[i] = jobs[i].rng;
+    nz.std[i] = jobs[i].noise_std;
+    nz.has[i] = jobs[i].has_noise;
+  }
+  SepNoise none;
+  memset(&none, 0, sizeof(none));
+
+  for (int a = 0; a < 3; ++a) {
+    SepPass p;
+    memset(&p, 0, sizeof(p));
+    int maxw = 0, max_nout = 0, max_outer = 0;
+    for (int i = 0; i < njobs; ++i) {
+      const fsg_sepconv_job& j = jobs[i];
+      p.src[i] = a == 0 ? j.src : (a == 1 ? j.tmp1 : j.tmp2);
+      p.dst[i] = a == 0 ? j.tmp1 : (a == 1 ? j.tmp2 : j.dst);
+      p.q0[i] = j.ax[a].q0;
+      p.w[i] = j.ax[a].w;
+      p.n_out[i] = j.ax[a].n_out;
+      p.width[i] = j.ax[a].width;
+      p.outer[i] = a == 0 ? 1 : (a == 1 ? j.ax[0].n_out : j.ax[0].n_out * j.ax[1].n_out);
+      maxw = p.width[i] > maxw ? p.width[i] : maxw;
+      max_nout = p.n_out[i] > max_nout ? p.n_out[i] : max_nout;
+      max_outer = p.outer[i] > max_outer ? p.outer[i] : max_outer;
+    }
+    const int a_in = n_in[a];
+    if (a < 2) {
+      const int inner = a == 0 ? sy * sz : sz;
+      bool vec2 = (inner % 2 == 0);
+      for (int i = 0; i < njobs && vec2; ++i) vec2 = ((reinterpret_cast<uintptr_t>(p.src[i]) | reinterpret_cast<uintptr_t>(p.dst[i])) & 7) == 0;
+      if (maxw <= 8) {
+        if (vec2) launch_stream<8, 2>(p, njobs, a_in, inner, max_nout, max_outer, s);
+        else launch_stream<8, 1>(p, njobs, a_in, inner, max_nout, max_outer, s);
+      } else if (maxw <= 16) {
+        if (vec2) launch_stream<16, 2>(p, njobs, a_in, inner, max_nout, max_outer, s);
+        else launch_stream<16, 1>(p, njobs, a_in, inner, max_nout, max_outer, s);
+      } else if (maxw <= 32) {
+        launch_stream<32, 1>(p, njobs, a_in, inner, max_nout, max_outer, s);
+      } else {
+        int64_t tot = (int64_t)max_outer * max_nout * inner;
+        int64_t want = (tot + 255) / 256;
+        sep_generic_kernel<false><<<dim3((unsigned)(want < 148 * 32 ? want : 148 * 32), njobs), 256, 0, s>>>(p, none, a_in, inner, 0);
+      }
+    } else {
+      if (maxw <= 8 && a_in >= 8) {
+        launch_z<8>(p, nz, njobs, a_in, max_outer, inject, s);
+      } else if (maxw <= 16 && a_in >= 16) {
+        launch_z<16>(p, nz, njobs, a_in, max_outer, inject, s);
+      } else if (maxw <= 32 && a_in >= 32) {
+        launch_z<32>(p, nz, njobs, a_in, max_outer, inject, s);
+      } else {
+        int64_t tot = (int64_t)max_outer * max_nout;
+        int64_t want = (tot + 255) / 256;
+        dim3 grid((unsigned)(want < 148 * 32 ? want : 148 * 32), njobs);
+        if (inject)
+          sep_generic_kernel<true><<<grid, 256, 0, s>>>(p, nz, a_in, 1, 1);
+        else
+          sep_generic_kernel<false><<<grid, 256, 0, s>>>(p, nz, a_in, 1, 1);
+      }
+    }
+  }
+  return check_launch("fsg_sepconv");
+}

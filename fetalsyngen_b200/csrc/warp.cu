@@ -6,204 +6,330 @@
 //   F      = separable linear up-sampling of the control grid Fsmall (x, then y, then z;
 //            every w_f*a + w_c*b rounded exactly like myzoom_torch's three loops)
 //   coord  = ((A_r0*(xc+Fx) + A_r1*(yc+Fy)) + A_r2*(zc+Fz)) + c2_r, clamp [0,S-1], -shift
-//   image  = trilinear gather (blend x, y, z; 0 where any coord <= 0 or > S-1)
-//   seg    = nearest gather (rint = half-to-even, clamp)
+//   image  = trilinear gather (blend x, y, z; 0 where any coord <= 0)
+//   seg    = nearest gather (round-half-even)
 //   flip   = sources mirrored along x before sampling
 //   image  = 300*(image/300)^gamma ; image *= exp(zoom(bf_low))       (optional epilogues)
-// No coordinate / field volume ever exists in HBM; the control grids are staged per tile in
-// shared memory.  Algorithmic HBM bytes: read img 4 + seg 1, write img 4 + seg 1 = 10 B/voxel.
+// No coordinate / field volume ever exists in HBM.  Algorithmic HBM bytes: read img 4 + seg 1,
+// write img 4 + seg 1 = 10 B/voxel.
+//
+// Work decomposition (round-1 ncu: the first version was issue-bound at ~550 instr/voxel):
+//   * a block owns WX x-planes x WY rows x the whole z extent, so the x/y blends of the two
+//     control grids (phase A) are amortised over S_z voxels per row instead of 32;
+//   * coordinates use separately rounded mul/add (bit-exact segmentation), but floor/round are
+//     magic-number adds on the FP32 pipe instead of F2I/I2F conversions, the flip is folded
+//     into the x stride, and the float image path uses FMA lerps and ex2/lg2 approximations
+//     (image parity is a tolerance, not bit-exactness);
+//   * floor(min coordinate) (the reference's crop-shift quirk) is resolved by a pre-pass over
+//     the six faces of the volume; the full-volume pre-pass only runs for jobs whose faces do
+//     not already prove the shift to be 0.
 #include "common.cuh"
 
 namespace fsg {
 
-constexpr int WT_X = 8, WT_Y = 8, WT_Z = 32;
-constexpr int WARP_THREADS = WT_Y * WT_Z;
+constexpr int WX = 8, WY = 4;
+constexpr int WARP_THREADS = 256;
 constexpr int MAX_FZ = 32;  // control-grid extent along z kept in smem (reference: <= 0.06*S)
 constexpr int MAX_BZ = 16;  // bias-grid extent along z (reference: <= 0.02*S)
+constexpr float MAGIC = 8388608.0f;  // 2^23: x + MAGIC has a unit ulp for 0 <= x < 2^23
 
 enum { PASS_SHIFT = 0, PASS_WARP = 1, PASS_COORDS = 2 };
 
-struct Coord3 {
-  float x, y, z;
-};
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lerp_fma(float a, float b, float w) { return __fmaf_rn(w, __fsub_rn(b, a), a); }
 
-// Trilinear sample of `src` at (ii,jj,kk); arithmetic order of utils/generation.py:227-285.
-__device__ __forceinline__ float sample_linear(const float* __restrict__ src, int sx, int sy, int sz, bool flip, float ii, float jj, float kk) {
-  const bool ok = (ii > 0.f) && (jj > 0.f) && (kk > 0.f) && (ii <= (float)(sx - 1)) && (jj <= (float)(sy - 1)) && (kk <= (float)(sz - 1));
-  if (!ok) return 0.f;
-  const float ffx = floorf(ii), ffy = floorf(jj), ffz = floorf(kk);
-  int fx = (int)ffx, fy = (int)ffy, fz = (int)ffz;
-  int cx = min(fx + 1, sx - 1);
-  const int cy = min(fy + 1, sy - 1), cz = min(fz + 1, sz - 1);
-  const float wcx = sub_rn(ii, ffx), wcy = sub_rn(jj, ffy), wcz = sub_rn(kk, ffz);
-  const float wfx = sub_rn(1.f, wcx), wfy = sub_rn(1.f, wcy), wfz = sub_rn(1.f, wcz);
-  if (flip) {
-    fx = sx - 1 - fx;
-    cx = sx - 1 - cx;
+// Exact control-grid value at voxel (i,j,k): x-, y-, z-blend in myzoom_torch's order.  Used by
+// the face pre-pass only (the main kernel stages the x/y blends in shared memory).
+__device__ __forceinline__ void field_at(const fsg_warp_job& job, int i, int j, int k, float& fx, float& fy, float& fz) {
+  const Tab tx = load_tab(job.ftab[0], i), ty = load_tab(job.ftab[1], j), tz = load_tab(job.ftab[2], k);
+  const int n1 = job.fs[1], n2 = job.fs[2];
+  float out[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float* g = job.fsmall + ch;
+    auto at = [&](int a, int b, int c) { return __ldg(g + ((size_t)(a * n1 + b) * n2 + c) * 3); };
+    const float a_ff = blend(tx.wf, at(tx.f, ty.f, tz.f), tx.wc, at(tx.c, ty.f, tz.f));
+    const float a_fc = blend(tx.wf, at(tx.f, ty.f, tz.c), tx.wc, at(tx.c, ty.f, tz.c));
+    const float a_cf = blend(tx.wf, at(tx.f, ty.c, tz.f), tx.wc, at(tx.c, ty.c, tz.f));
+    const float a_cc = blend(tx.wf, at(tx.f, ty.c, tz.c), tx.wc, at(tx.c, ty.c, tz.c));
+    const float b_f = blend(ty.wf, a_ff, ty.wc, a_cf);
+    const float b_c = blend(ty.wf, a_fc, ty.wc, a_cc);
+    out[ch] = blend(tz.wf, b_f, tz.wc, b_c);
   }
-  const size_t rf = (size_t)fx * sy, rc = (size_t)cx * sy;
-  const float* pff = src + (rf + fy) * sz;
-  const float* pcf = src + (rc + fy) * sz;
-  const float* pfc = src + (rf + cy) * sz;
-  const float* pcc = src + (rc + cy) * sz;
-  const float c000 = __ldg(pff + fz), c001 = __ldg(pff + cz);
-  const float c100 = __ldg(pcf + fz), c101 = __ldg(pcf + cz);
-  const float c010 = __ldg(pfc + fz), c011 = __ldg(pfc + cz);
-  const float c110 = __ldg(pcc + fz), c111 = __ldg(pcc + cz);
-  const float c00 = lerp2(c000, wfx, c100, wcx);
-  const float c01 = lerp2(c001, wfx, c101, wcx);
-  const float c10 = lerp2(c010, wfx, c110, wcx);
-  const float c11 = lerp2(c011, wfx, c111, wcx);
-  const float c0 = lerp2(c00, wfy, c10, wcy);
-  const float c1 = lerp2(c01, wfy, c11, wcy);
-  return lerp2(c0, wfz, c1, wcz);
+  fx = out[0];
+  fy = out[1];
+  fz = out[2];
 }
 
-__device__ __forceinline__ uint8_t sample_nearest(const uint8_t* __restrict__ src, int sx, int sy, int sz, bool flip, float ii, float jj, float kk) {
-  int ir = min(max((int)rintf(ii), 0), sx - 1);
-  const int jr = min(max((int)rintf(jj), 0), sy - 1);
-  const int kr = min(max((int)rintf(kk), 0), sz - 1);
-  if (flip) ir = sx - 1 - ir;
-  return __ldg(src + ((size_t)ir * sy + jr) * sz + kr);
+// Clamped (not yet shifted) sample coordinate of one voxel from its centred position + field.
+__device__ __forceinline__ void affine_clamp(const fsg_warp_job& job, float x1, float y1, float z1, float mx, float my, float mz, float& ii, float& jj, float& kk) {
+  ii = add_rn(add_rn(add_rn(mul_rn(job.A[0], x1), mul_rn(job.A[1], y1)), mul_rn(job.A[2], z1)), job.c2[0]);
+  jj = add_rn(add_rn(add_rn(mul_rn(job.A[3], x1), mul_rn(job.A[4], y1)), mul_rn(job.A[5], z1)), job.c2[1]);
+  kk = add_rn(add_rn(add_rn(mul_rn(job.A[6], x1), mul_rn(job.A[7], y1)), mul_rn(job.A[8], z1)), job.c2[2]);
+  ii = fminf(fmaxf(ii, 0.f), mx);
+  jj = fminf(fmaxf(jj, 0.f), my);
+  kk = fminf(fmaxf(kk, 0.f), mz);
 }
+
+// ---------------------------------------------------------------------------------- face pre-pass
+// One thread per voxel of the six faces; atomicMin of the clamped coordinates into job.shift.
+__global__ void __launch_bounds__(256) shift_faces_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
+  const fsg_warp_job& job = batch.j[blockIdx.y];
+  const int n_yz = sy * sz, n_xz = sx * sz, n_xy = sx * sy;
+  const int total = 2 * (n_yz + n_xz + n_xy);
+  const float inf = __int_as_float(0x7f800000);
+  float mnx = inf, mny = inf, mnz = inf;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int i, j, k, r = t;
+    if (r < 2 * n_yz) {
+      i = (r >= n_yz) ? sx - 1 : 0;
+      r -= (r >= n_yz) ? n_yz : 0;
+      j = r / sz;
+      k = r - j * sz;
+    } else if ((r -= 2 * n_yz) < 2 * n_xz) {
+      j = (r >= n_xz) ? sy - 1 : 0;
+      r -= (r >= n_xz) ? n_xz : 0;
+      i = r / sz;
+      k = r - i * sz;
+    } else {
+      r -= 2 * n_xz;
+      k = (r >= n_xy) ? sz - 1 : 0;
+      r -= (r >= n_xy) ? n_xy : 0;
+      i = r / sy;
+      j = r - i * sy;
+    }
+    float x1 = sub_rn((float)i, job.center[0]), y1 = sub_rn((float)j, job.center[1]), z1 = sub_rn((float)k, job.center[2]);
+    if (job.fsmall != nullptr) {
+      float fx, fy, fz;
+      field_at(job, i, j, k, fx, fy, fz);
+      x1 = add_rn(x1, fx);
+      y1 = add_rn(y1, fy);
+      z1 = add_rn(z1, fz);
+    }
+    float ii, jj, kk;
+    affine_clamp(job, x1, y1, z1, (float)(sx - 1), (float)(sy - 1), (float)(sz - 1), ii, jj, kk);
+    mnx = fminf(mnx, ii);
+    mny = fminf(mny, jj);
+    mnz = fminf(mnz, kk);
+  }
+  mnx = warp_min(mnx);
+  mny = warp_min(mny);
+  mnz = warp_min(mnz);
+  if ((threadIdx.x & 31) == 0) {
+    // clamped coordinates are >= 0, so the int view of the float orders correctly
+    int* sh = reinterpret_cast<int*>(const_cast<float*>(job.shift));
+    atomicMin(sh + 0, __float_as_int(mnx));
+    atomicMin(sh + 1, __float_as_int(mny));
+    atomicMin(sh + 2, __float_as_int(mnz));
+  }
+}
+
+// ---------------------------------------------------------------------------------- main kernel
+struct ZTab {  // per-thread z table entry of a control grid, pre-scaled for float4 rows
+  int f, c;
+  float wc, wf;
+};
 
 template <int PASS>
 __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz, float* __restrict__ dbg_x,
                                                              float* __restrict__ dbg_y, float* __restrict__ dbg_z) {
-  const int ntx = (sx + WT_X - 1) / WT_X;
-  const fsg_warp_job& job = batch.j[blockIdx.z / ntx];
-  const int x0 = (blockIdx.z % ntx) * WT_X, y0 = blockIdx.y * WT_Y, z0 = blockIdx.x * WT_Z;
-  const int tid = threadIdx.y * WT_Z + threadIdx.x;
+  const fsg_warp_job& job = batch.j[blockIdx.z];
+  const int tid = threadIdx.x;
 
-  __shared__ float s_f[WT_X][WT_Y][MAX_FZ][3];  // control grid blended along x and y
-  __shared__ float s_b[WT_X][WT_Y][MAX_BZ];     // bias grid blended along x and y
+  extern __shared__ float4 s_dyn[];
+  float4* s_f = s_dyn;  // [WX*WY][fz_n] control grid blended along x and y (xyz + pad)
+  __shared__ float s_b[WX * WY][MAX_BZ];  // bias grid blended along x and y
   __shared__ float s_red[3][WARP_THREADS / 32];
 
   const bool deform = job.mode == 1;
   const bool has_field = deform && job.fsmall != nullptr;
   const bool has_bias = (PASS == PASS_WARP) && job.bf_low != nullptr && job.dst_img != nullptr;
 
-  // ---- phase A: x- and y-blends of the low-resolution grids for the tile's 64 (x,y) rows
-  if (has_field) {
-    const int fy_n = job.fs[1], fz_n = job.fs[2];
-    const int per_row = fz_n * 3;
-    for (int e = tid; e < WT_X * WT_Y * per_row; e += WARP_THREADS) {
-      const int row = e / per_row, rem = e - row * per_row;
-      const int rx = row / WT_Y, ry = row - rx * WT_Y;
-      const int i = min(x0 + rx, sx - 1), j = min(y0 + ry, sy - 1);
-      const Tab tx = load_tab(job.ftab[0], i), ty = load_tab(job.ftab[1], j);
-      const float* g = job.fsmall + rem;  // rem = zc*3 + ch
-      const size_t sxs = (size_t)fy_n * per_row;
-      const float t1f = blend(tx.wf, __ldg(g + tx.f * sxs + (size_t)ty.f * per_row), tx.wc, __ldg(g + tx.c * sxs + (size_t)ty.f * per_row));
-      const float t1c = blend(tx.wf, __ldg(g + tx.f * sxs + (size_t)ty.c * per_row), tx.wc, __ldg(g + tx.c * sxs + (size_t)ty.c * per_row));
-      (&s_f[rx][ry][0][0])[rem] = blend(ty.wf, t1f, ty.wc, t1c);
-    }
+  if (PASS == PASS_SHIFT) {
+    // the face pre-pass already proved floor(min) == 0 on every axis: nothing to do
+    const float* sh = job.shift;
+    if (sh[0] < 1.f && sh[1] < 1.f && sh[2] < 1.f) return;
   }
-  if (has_bias) {
-    const int by_n = job.bs[1], bz_n = job.bs[2];
-    for (int e = tid; e < WT_X * WT_Y * bz_n; e += WARP_THREADS) {
-      const int row = e / bz_n, zc = e - row * bz_n;
-      const int rx = row / WT_Y, ry = row - rx * WT_Y;
-      const int i = min(x0 + rx, sx - 1), j = min(y0 + ry, sy - 1);
-      const Tab tx = load_tab(job.btab[0], i), ty = load_tab(job.btab[1], j);
-      const float* g = job.bf_low + zc;
-      const size_t sxs = (size_t)by_n * bz_n;
-      const float t1f = blend(tx.wf, __ldg(g + tx.f * sxs + (size_t)ty.f * bz_n), tx.wc, __ldg(g + tx.c * sxs + (size_t)ty.f * bz_n));
-      const float t1c = blend(tx.wf, __ldg(g + tx.f * sxs + (size_t)ty.c * bz_n), tx.wc, __ldg(g + tx.c * sxs + (size_t)ty.c * bz_n));
-      s_b[rx][ry][zc] = blend(ty.wf, t1f, ty.wc, t1c);
-    }
-  }
-  __syncthreads();
 
-  // ---- phase B: one thread per (y,z) column of the tile, marching over x
-  const int k = z0 + threadIdx.x, j = y0 + threadIdx.y;
-  const bool in_yz = (k < sz) && (j < sy);
-  const int kc = min(k, sz - 1), jc = min(j, sy - 1);
-  Tab tfz = {0, 0, 0.f, 1.f}, tbz = {0, 0, 0.f, 1.f};
-  if (has_field) tfz = load_tab(job.ftab[2], kc);
-  if (has_bias) tbz = load_tab(job.btab[2], kc);
-  const float yc = sub_rn((float)jc, job.center[1]);
-  const float zc = sub_rn((float)kc, job.center[2]);
-  const float shx = (PASS != PASS_SHIFT && deform) ? job.shift[0] : 0.f;
-  const float shy = (PASS != PASS_SHIFT && deform) ? job.shift[1] : 0.f;
-  const float shz = (PASS != PASS_SHIFT && deform) ? job.shift[2] : 0.f;
-  const bool flip = job.flip != 0;
+  const int fz_n = has_field ? job.fs[2] : 0;
   const float inf = __int_as_float(0x7f800000);
   float mnx = inf, mny = inf, mnz = inf;
 
-#pragma unroll 2
-  for (int rx = 0; rx < WT_X; ++rx) {
-    const int i = x0 + rx;
-    if (i >= sx) break;
-    float ii, jj, kk;
-    if (deform) {
-      float x1 = sub_rn((float)i, job.center[0]), y1 = yc, z1 = zc;
+  const float shx = (PASS != PASS_SHIFT && deform) ? job.shift[0] : 0.f;
+  const float shy = (PASS != PASS_SHIFT && deform) ? job.shift[1] : 0.f;
+  const float shz = (PASS != PASS_SHIFT && deform) ? job.shift[2] : 0.f;
+  const bool has_shift = (shx != 0.f) || (shy != 0.f) || (shz != 0.f);
+  const float mx = (float)(sx - 1), my = (float)(sy - 1), mz = (float)(sz - 1);
+  // flip folded into the x stride: element offset of source plane p is xb + p * xs
+  const int plane = sy * sz;
+  const int xs = job.flip ? -plane : plane;
+  const int xb = job.flip ? (sx - 1) * plane : 0;
+  const float gamma = job.gamma;
+  const bool has_gamma = (PASS == PASS_WARP) && job.has_gamma;
+
+  const int ntile_y = (sy + WY - 1) / WY;
+  const int ntiles = ntile_y * ((sx + WX - 1) / WX);
+  // PASS_SHIFT runs a bounded grid and strides over the tiles; the other passes use one tile per block
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int x0 = (tile / ntile_y) * WX, y0 = (tile % ntile_y) * WY;
+    if (tile != (int)blockIdx.x) __syncthreads();  // previous tile's readers are done
+
+    // ---- phase A: x- and y-blends of the low-resolution grids for the tile's WX*WY rows
+    if (has_field) {
+      const int fy_n = job.fs[1];
+      const int per_row = fz_n * 3;
+      float* sf = reinterpret_cast<float*>(s_f);
+      for (int e = tid; e < WX * WY * per_row; e += WARP_THREADS) {
+        const int row = e / per_row, rem = e - row * per_row;
+        const int rx = row / WY, ry = row - rx * WY;
+        const int i = min(x0 + rx, sx - 1), j = min(y0 + ry, sy - 1);
+        const Tab tx = load_tab(job.ftab[0], i), ty = load_tab(job.ftab[1], j);
+        const float* g = job.fsmall + rem;  // rem = zc*3 + ch
+        const int sxs = fy_n * per_row;
+        const float t1f = blend(tx.wf, __ldg(g + tx.f * sxs + ty.f * per_row), tx.wc, __ldg(g + tx.c * sxs + ty.f * per_row));
+        const float t1c = blend(tx.wf, __ldg(g + tx.f * sxs + ty.c * per_row), tx.wc, __ldg(g + tx.c * sxs + ty.c * per_row));
+        const int zc = rem / 3, ch = rem - zc * 3;
+        sf[(row * fz_n + zc) * 4 + ch] = blend(ty.wf, t1f, ty.wc, t1c);
+      }
+    }
+    if (has_bias) {
+      const int by_n = job.bs[1], bz_n = job.bs[2];
+      for (int e = tid; e < WX * WY * bz_n; e += WARP_THREADS) {
+        const int row = e / bz_n, zc = e - row * bz_n;
+        const int rx = row / WY, ry = row - rx * WY;
+        const int i = min(x0 + rx, sx - 1), j = min(y0 + ry, sy - 1);
+        const Tab tx = load_tab(job.btab[0], i), ty = load_tab(job.btab[1], j);
+        const float* g = job.bf_low + zc;
+        const int sxs = by_n * bz_n;
+        const float t1f = blend(tx.wf, __ldg(g + tx.f * sxs + ty.f * bz_n), tx.wc, __ldg(g + tx.c * sxs + ty.f * bz_n));
+        const float t1c = blend(tx.wf, __ldg(g + tx.f * sxs + ty.c * bz_n), tx.wc, __ldg(g + tx.c * sxs + ty.c * bz_n));
+        s_b[row][zc] = blend(ty.wf, t1f, ty.wc, t1c);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B: thread = z column (strided by the block size), marching over the tile's rows
+    for (int k = tid; k < sz; k += WARP_THREADS) {
+      ZTab tfz = {0, 0, 0.f, 1.f}, tbz = {0, 0, 0.f, 1.f};
       if (has_field) {
-        const float* f0 = &s_f[rx][threadIdx.y][tfz.f][0];
-        const float* f1 = &s_f[rx][threadIdx.y][tfz.c][0];
-        x1 = add_rn(x1, blend(tfz.wf, f0[0], tfz.wc, f1[0]));
-        y1 = add_rn(y1, blend(tfz.wf, f0[1], tfz.wc, f1[1]));
-        z1 = add_rn(z1, blend(tfz.wf, f0[2], tfz.wc, f1[2]));
+        const Tab t = load_tab(job.ftab[2], k);
+        tfz.f = t.f; tfz.c = t.c; tfz.wc = t.wc; tfz.wf = t.wf;
       }
-      ii = add_rn(add_rn(add_rn(mul_rn(job.A[0], x1), mul_rn(job.A[1], y1)), mul_rn(job.A[2], z1)), job.c2[0]);
-      jj = add_rn(add_rn(add_rn(mul_rn(job.A[3], x1), mul_rn(job.A[4], y1)), mul_rn(job.A[5], z1)), job.c2[1]);
-      kk = add_rn(add_rn(add_rn(mul_rn(job.A[6], x1), mul_rn(job.A[7], y1)), mul_rn(job.A[8], z1)), job.c2[2]);
-      ii = ii < 0.f ? 0.f : ii;
-      jj = jj < 0.f ? 0.f : jj;
-      kk = kk < 0.f ? 0.f : kk;
-      ii = ii > (float)(sx - 1) ? (float)(sx - 1) : ii;
-      jj = jj > (float)(sy - 1) ? (float)(sy - 1) : jj;
-      kk = kk > (float)(sz - 1) ? (float)(sz - 1) : kk;
-      if (PASS == PASS_SHIFT) {
-        if (in_yz) {
-          mnx = fminf(mnx, ii);
-          mny = fminf(mny, jj);
-          mnz = fminf(mnz, kk);
+      if (has_bias) {
+        const Tab t = load_tab(job.btab[2], k);
+        tbz.f = t.f; tbz.c = t.c; tbz.wc = t.wc; tbz.wf = t.wf;
+      }
+      const float zc = sub_rn((float)k, job.center[2]);
+#pragma unroll 1
+      for (int ry = 0; ry < WY; ++ry) {
+        const int j = y0 + ry;
+        if (j >= sy) break;
+        const float yc = sub_rn((float)j, job.center[1]);
+#pragma unroll 2
+        for (int rx = 0; rx < WX; ++rx) {
+          const int i = x0 + rx;
+          if (i >= sx) break;
+          const int row = rx * WY + ry;
+          const int o = (i * sy + j) * sz + k;
+          float ii, jj, kk;
+          if (deform) {
+            float x1 = sub_rn((float)i, job.center[0]), y1 = yc, z1 = zc;
+            if (has_field) {
+              const float4 f0 = s_f[row * fz_n + tfz.f], f1 = s_f[row * fz_n + tfz.c];
+              x1 = add_rn(x1, blend(tfz.wf, f0.x, tfz.wc, f1.x));
+              y1 = add_rn(y1, blend(tfz.wf, f0.y, tfz.wc, f1.y));
+              z1 = add_rn(z1, blend(tfz.wf, f0.z, tfz.wc, f1.z));
+            }
+            affine_clamp(job, x1, y1, z1, mx, my, mz, ii, jj, kk);
+            if (PASS == PASS_SHIFT) {
+              mnx = fminf(mnx, ii);
+              mny = fminf(mny, jj);
+              mnz = fminf(mnz, kk);
+              continue;
+            }
+            if (has_shift) {
+              ii = sub_rn(ii, shx);
+              jj = sub_rn(jj, shy);
+              kk = sub_rn(kk, shz);
+            }
+          } else {
+            ii = (float)i;
+            jj = (float)j;
+            kk = (float)k;
+          }
+          if (PASS == PASS_COORDS) {
+            dbg_x[o] = ii;
+            dbg_y[o] = jj;
+            dbg_z[o] = kk;
+            continue;
+          }
+          if (PASS == PASS_WARP) {
+            if (!deform) {
+              // identity sampling: only flip + epilogues (deformation gate off)
+              const int so = xb + i * xs + j * sz + k;
+              if (job.dst_img) {
+                float v = __ldg(job.src_img + so);
+                if (has_gamma) v = mul_rn(300.0f, ex2_approx(mul_rn(gamma, lg2_approx(mul_rn(v, 1.0f / 300.0f)))));
+                if (has_bias) v = mul_rn(v, ex2_approx(mul_rn(1.4426950408889634f, blend(tbz.wf, s_b[row][tbz.f], tbz.wc, s_b[row][tbz.c]))));
+                job.dst_img[o] = v;
+              }
+              if (job.dst_seg) job.dst_seg[o] = __ldg(job.src_seg + so);
+              if (job.dst_img2) job.dst_img2[o] = __ldg(job.src_img2 + so);
+              continue;
+            }
+            if (job.dst_img || job.dst_img2) {
+              // coordinates are in [0, S-1]: floor via a round-toward-zero magic add
+              const float tx_ = __fadd_rz(ii, MAGIC), ty_ = __fadd_rz(jj, MAGIC), tz_ = __fadd_rz(kk, MAGIC);
+              const int fx = __float_as_int(tx_) - 0x4B000000, fy = __float_as_int(ty_) - 0x4B000000, fz = __float_as_int(tz_) - 0x4B000000;
+              const float wcx = sub_rn(ii, sub_rn(tx_, MAGIC)), wcy = sub_rn(jj, sub_rn(ty_, MAGIC)), wcz = sub_rn(kk, sub_rn(tz_, MAGIC));
+              const int cx = min(fx + 1, sx - 1), cy = min(fy + 1, sy - 1), cz = min(fz + 1, sz - 1);
+              const bool ok = fminf(fminf(ii, jj), kk) > 0.f;
+              const int of = xb + fx * xs, oc = xb + cx * xs;
+              const int off = of + fy * sz, ofc = of + cy * sz, ocf = oc + fy * sz, occ = oc + cy * sz;
+              if (job.dst_img) {
+                const float* __restrict__ s = job.src_img;
+                const float c000 = __ldg(s + off + fz), c001 = __ldg(s + off + cz);
+                const float c100 = __ldg(s + ocf + fz), c101 = __ldg(s + ocf + cz);
+                const float c010 = __ldg(s + ofc + fz), c011 = __ldg(s + ofc + cz);
+                const float c110 = __ldg(s + occ + fz), c111 = __ldg(s + occ + cz);
+                const float c00 = lerp_fma(c000, c100, wcx), c01 = lerp_fma(c001, c101, wcx);
+                const float c10 = lerp_fma(c010, c110, wcx), c11 = lerp_fma(c011, c111, wcx);
+                float v = lerp_fma(lerp_fma(c00, c10, wcy), lerp_fma(c01, c11, wcy), wcz);
+                v = ok ? v : 0.f;
+                if (has_gamma) v = mul_rn(300.0f, ex2_approx(mul_rn(gamma, lg2_approx(mul_rn(v, 1.0f / 300.0f)))));
+                if (has_bias) v = mul_rn(v, ex2_approx(mul_rn(1.4426950408889634f, blend(tbz.wf, s_b[row][tbz.f], tbz.wc, s_b[row][tbz.c]))));
+                job.dst_img[o] = v;
+              }
+              if (job.dst_img2) {
+                const float* __restrict__ s = job.src_img2;
+                const float c000 = __ldg(s + off + fz), c001 = __ldg(s + off + cz);
+                const float c100 = __ldg(s + ocf + fz), c101 = __ldg(s + ocf + cz);
+                const float c010 = __ldg(s + ofc + fz), c011 = __ldg(s + ofc + cz);
+                const float c110 = __ldg(s + occ + fz), c111 = __ldg(s + occ + cz);
+                const float c00 = lerp_fma(c000, c100, wcx), c01 = lerp_fma(c001, c101, wcx);
+                const float c10 = lerp_fma(c010, c110, wcx), c11 = lerp_fma(c011, c111, wcx);
+                const float v = lerp_fma(lerp_fma(c00, c10, wcy), lerp_fma(c01, c11, wcy), wcz);
+                job.dst_img2[o] = ok ? v : 0.f;
+              }
+            }
+            if (job.dst_seg) {
+              // round-half-even of a coordinate in [0, S-1] via a round-to-nearest magic add
+              const int ir = __float_as_int(add_rn(ii, MAGIC)) - 0x4B000000;
+              const int jr = __float_as_int(add_rn(jj, MAGIC)) - 0x4B000000;
+              const int kr = __float_as_int(add_rn(kk, MAGIC)) - 0x4B000000;
+              job.dst_seg[o] = __ldg(job.src_seg + xb + ir * xs + jr * sz + kr);
+            }
+          }
         }
-        continue;
-      }
-      ii = sub_rn(ii, shx);
-      jj = sub_rn(jj, shy);
-      kk = sub_rn(kk, shz);
-    } else {
-      ii = (float)i;
-      jj = (float)jc;
-      kk = (float)kc;
-    }
-    if (!in_yz) continue;
-    const size_t o = ((size_t)i * sy + j) * sz + k;
-    if (PASS == PASS_COORDS) {
-      dbg_x[o] = ii;
-      dbg_y[o] = jj;
-      dbg_z[o] = kk;
-      continue;
-    }
-    if (PASS == PASS_WARP) {
-      if (job.dst_img) {
-        float v;
-        if (deform)
-          v = sample_linear(job.src_img, sx, sy, sz, flip, ii, jj, kk);
-        else
-          v = __ldg(job.src_img + ((size_t)(flip ? sx - 1 - i : i) * sy + j) * sz + k);
-        if (job.has_gamma) v = mul_rn(300.0f, powf(__fdiv_rn(v, 300.0f), job.gamma));
-        if (has_bias) v = mul_rn(v, expf(blend(tbz.wf, s_b[rx][threadIdx.y][tbz.f], tbz.wc, s_b[rx][threadIdx.y][tbz.c])));
-        job.dst_img[o] = v;
-      }
-      if (job.dst_seg) {
-        uint8_t l;
-        if (deform)
-          l = sample_nearest(job.src_seg, sx, sy, sz, flip, ii, jj, kk);
-        else
-          l = __ldg(job.src_seg + ((size_t)(flip ? sx - 1 - i : i) * sy + j) * sz + k);
-        job.dst_seg[o] = l;
-      }
-      if (job.dst_img2) {
-        float v;
-        if (deform)
-          v = sample_linear(job.src_img2, sx, sy, sz, flip, ii, jj, kk);
-        else
-          v = __ldg(job.src_img2 + ((size_t)(flip ? sx - 1 - i : i) * sy + j) * sz + k);
-        job.dst_img2[o] = v;
       }
     }
   }
@@ -222,7 +348,6 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
     if (tid < 3) {
       float m = inf;
       for (int q = 0; q < WARP_THREADS / 32; ++q) m = fminf(m, s_red[tid][q]);
-      // clamped coordinates are >= 0, so the int view of the float orders correctly
       atomicMin(reinterpret_cast<int*>(const_cast<float*>(job.shift)) + tid, __float_as_int(m));
     }
   }
@@ -242,6 +367,7 @@ __global__ void shift_final_kernel(const __grid_constant__ Batch<fsg_warp_job> b
 
 static int validate(const fsg_warp_job* jobs, int njobs, int sx, int sy, int sz, bool need_io, const char* who) {
   FSG_REQUIRE(sx >= 1 && sy >= 1 && sz >= 1 && sx <= 32767 && sy <= 32767 && sz <= 32767, "%s: bad shape %dx%dx%d", who, sx, sy, sz);
+  FSG_REQUIRE((int64_t)sx * sy * sz < ((int64_t)1 << 31), "%s: volume exceeds 2^31 voxels", who);
   for (int n = 0; n < njobs; ++n) {
     const fsg_warp_job& j = jobs[n];
     FSG_REQUIRE(j.mode == 0 || j.mode == 1, "%s: job %d mode must be 0 or 1", who, n);
@@ -265,9 +391,14 @@ static int validate(const fsg_warp_job* jobs, int njobs, int sx, int sy, int sz,
   return 0;
 }
 
-static dim3 warp_grid(int njobs, int sx, int sy, int sz) {
-  return dim3((sz + WT_Z - 1) / WT_Z, (sy + WT_Y - 1) / WT_Y, ((sx + WT_X - 1) / WT_X) * njobs);
+static size_t field_smem(const fsg_warp_job* jobs, int njobs) {
+  int fz = 1;
+  for (int n = 0; n < njobs; ++n)
+    if (jobs[n].fsmall && jobs[n].fs[2] > fz) fz = jobs[n].fs[2];
+  return (size_t)WX * WY * fz * sizeof(float4);
 }
+
+static dim3 warp_grid(int njobs, int sx, int sy) { return dim3(((sy + WY - 1) / WY) * ((sx + WX - 1) / WX), 1, njobs); }
 
 }  // namespace fsg
 
@@ -280,7 +411,12 @@ extern "C" int fsg_warp_shift(const fsg_warp_job* jobs, int njobs, int sx, int s
   for (int n = 0; n < njobs; ++n) FSG_REQUIRE(jobs[n].mode == 1, "fsg_warp_shift: job %d is not a deformation job", n);
   cudaStream_t s = as_stream(stream);
   shift_init_kernel<<<1, 64, 0, s>>>(b, njobs);
-  warp_kernel<PASS_SHIFT><<<warp_grid(njobs, sx, sy, sz), dim3(WT_Z, WT_Y), 0, s>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  const int faces = 2 * (sy * sz + sx * sz + sx * sy);
+  shift_faces_kernel<<<dim3((faces + 255) / 256, njobs), 256, 0, s>>>(b, sx, sy, sz);
+  // full-volume pass on a bounded grid; blocks of jobs already resolved by the faces return at once
+  const int ntiles = ((sy + WY - 1) / WY) * ((sx + WX - 1) / WX);
+  const int gx = ntiles < 148 * 2 ? ntiles : 148 * 2;
+  warp_kernel<PASS_SHIFT><<<dim3(gx, 1, njobs), WARP_THREADS, field_smem(jobs, njobs), s>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
   shift_final_kernel<<<1, 64, 0, s>>>(b, njobs);
   return check_launch("fsg_warp_shift");
 }
@@ -289,7 +425,7 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
   Batch<fsg_warp_job> b;
   if (int rc = fill_batch(b, jobs, njobs)) return rc;
   if (int rc = validate(jobs, njobs, sx, sy, sz, true, "fsg_warp")) return rc;
-  warp_kernel<PASS_WARP><<<warp_grid(njobs, sx, sy, sz), dim3(WT_Z, WT_Y), 0, as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  warp_kernel<PASS_WARP><<<warp_grid(njobs, sx, sy), WARP_THREADS, field_smem(jobs, njobs), as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
   return check_launch("fsg_warp");
 }
 
@@ -298,6 +434,6 @@ extern "C" int fsg_warp_coords(const fsg_warp_job* job, int sx, int sy, int sz, 
   if (int rc = fill_batch(b, job, 1)) return rc;
   if (int rc = validate(job, 1, sx, sy, sz, false, "fsg_warp_coords")) return rc;
   FSG_REQUIRE(xx && yy && zz, "fsg_warp_coords: NULL output");
-  warp_kernel<PASS_COORDS><<<warp_grid(1, sx, sy, sz), dim3(WT_Z, WT_Y), 0, as_stream(stream)>>>(b, sx, sy, sz, xx, yy, zz);
+  warp_kernel<PASS_COORDS><<<warp_grid(1, sx, sy), WARP_THREADS, field_smem(job, 1), as_stream(stream)>>>(b, sx, sy, sz, xx, yy, zz);
   return check_launch("fsg_warp_coords");
 }

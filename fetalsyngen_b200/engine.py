@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .tables import DeviceTables, resample_size, zoom_size
+from .tables import DeviceTables, gaussian_taps_np, resample_size, zoom_size
 
 STAGE_GMM, STAGE_NOISE = 1, 2
 
@@ -214,6 +214,71 @@ class SynthEngine:
                     j.taps[a], j.ntaps[a] = t.data_ptr(), t.numel() // 4
         _lib.call("fsg_blur3d", jobs, B, sx, sy, sz, _stream())
 
+    # ------------------------------------------------------------------ K4ab (fused)
+    def sepconv(self, plans, src, dst, tmp1, tmp2, positions=True):
+        """Fused blur + trilinear down-sampling (+noise): plan.stds gives the blur, plan.spacing the
+        coarse grid (positions=False: plain blur at full resolution).  tmp1 may alias dst.
+        Returns per-sample (coarse shape, factors) like ``resample``."""
+        B = len(plans)
+        sx, sy, sz = self.shape
+        tap_arrays, tap_slot, maxw = [], [], 2
+        for p in plans:
+            slots, seen = [], {}
+            for a in range(3):
+                sd = float(p.stds[a]) if p.stds is not None else 0.0
+                if sd > 0:
+                    if sd not in seen:  # isotropic spacing gives three identical widths: upload once
+                        seen[sd] = len(tap_arrays)
+                        tap_arrays.append(gaussian_taps_np(sd))
+                    slots.append(seen[sd])
+                    maxw = max(maxw, tap_arrays[seen[sd]].size + 1)
+                else:
+                    slots.append(None)
+            tap_slot.append(slots)
+        taps_dev = self.upload(tap_arrays) if tap_arrays else []
+        # workspace per job and axis: float w[nmax][maxw] then int16 q0[nmax]
+        nmax = max(self.shape)
+        maxw = max(32, (maxw + 3) // 4 * 4)
+        per_axis = (nmax * maxw + (nmax + 1) // 2 + 3) // 4 * 4
+        ws = self.scratch("sep_tables", B, torch.float32, 3 * per_axis)
+        cjobs = (_lib.SepComposeJob * (3 * B))()
+        jobs = (_lib.SepconvJob * B)()
+        info = []
+        for b, p in enumerate(plans):
+            j = jobs[b]
+            n, factors = [], []
+            for a in range(3):
+                cj = cjobs[3 * b + a]
+                n_in = self.shape[a]
+                if positions:
+                    t, fac = self.tables.resample(n_in, self.resolution[a], p.spacing[a])
+                    n_out = resample_size(n_in, self.resolution[a], p.spacing[a])
+                    cj.pos = t.data_ptr()
+                else:
+                    n_out, fac = n_in, 1.0
+                ntaps = 1
+                if tap_slot[b][a] is not None:
+                    td = taps_dev[tap_slot[b][a]]
+                    cj.taps, ntaps = td.data_ptr(), int(td.numel())
+                width = min(n_in, ntaps + (1 if positions else 0))
+                w_ptr = ws[b].data_ptr() + 4 * a * per_axis
+                q_ptr = w_ptr + 4 * nmax * maxw
+                cj.q0_out, cj.w_out = q_ptr, w_ptr
+                cj.ntaps, cj.n_in, cj.n_out, cj.width = ntaps, n_in, n_out, width
+                j.ax[a].q0, j.ax[a].w, j.ax[a].n_out, j.ax[a].width = q_ptr, w_ptr, n_out, width
+                n.append(n_out)
+                factors.append(fac)
+            j.src, j.dst, j.tmp1, j.tmp2 = src[b].data_ptr(), dst[b].data_ptr(), tmp1[b].data_ptr(), tmp2[b].data_ptr()
+            if p.noise_std is not None and positions:
+                j.has_noise, j.noise_std = 1, float(np.float32(p.noise_std))
+                j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
+                j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_NOISE, 0)
+            info.append((tuple(n), np.asarray(factors, dtype=np.float64)))
+        _lib.call("fsg_sep_compose", cjobs, 3 * B, _stream())
+        _lib.call("fsg_sepconv", jobs, B, sx, sy, sz, _stream())
+        self._keep_sep = taps_dev
+        return info
+
     # ------------------------------------------------------------------ K4b
     def lowres_shape(self, spacing):
         return tuple(resample_size(self.shape[a], self.resolution[a], spacing[a]) for a in range(3))
@@ -326,9 +391,9 @@ class SynthEngine:
         self.warp(plans, buf0, segs, warp_dst, out_seg)
         if rs:
             sub = [plans[b] for b in rs]
-            self.blur([p.stds for p in sub], [buf1[b] for b in rs], [buf2[b] for b in rs], [buf0[b] for b in rs])
-            info = self.resample(sub, [buf2[b] for b in rs], [buf0[b] for b in rs])
-            self.zoom([buf0[b] for b in rs], [i[0] for i in info], [1 / i[1] for i in info], [out_img[b].view(-1) for b in rs], post=2 if scale else 1)
+            # x pass -> buf2, y pass -> buf0 (the GMM image is dead), z pass (+noise) -> buf2
+            info = self.sepconv(sub, [buf1[b] for b in rs], [buf2[b] for b in rs], [buf2[b] for b in rs], [buf0[b] for b in rs])
+            self.zoom([buf2[b] for b in rs], [i[0] for i in info], [1 / i[1] for i in info], [out_img[b].view(-1) for b in rs], post=2 if scale else 1)
         nz = [b for b in no_rs if plans[b].noise_std is not None]
         if nz:
             self.add_noise([plans[b] for b in nz], [buf1[b] for b in nz], [out_img[b].view(-1) for b in nz])

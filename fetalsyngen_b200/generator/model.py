@@ -139,11 +139,9 @@ class FetalSynthGen:
     def _run_augment_tail(self, eng, plan, x):
         """blur + down-sample (+noise) + up-sample (/max), or full-resolution noise."""
         if plan.spacing is not None:
-            blurred = torch.empty_like(x)
-            tmp = eng.scratch("buf0", 1)
-            eng.blur([plan.stds], x, blurred, tmp)
             low = eng.scratch("buf1", 1)
-            info = eng.resample([plan], blurred, low)
+            tmp = eng.scratch("buf0", 1)
+            info = eng.sepconv([plan], x, low, low, tmp)
             out = torch.empty_like(x)
             eng.zoom([low[0]], [info[0][0]], [1 / info[0][1]], out, post=1)
             return out

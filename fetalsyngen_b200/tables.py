@@ -67,6 +67,15 @@ def gaussian_taps(sigma: float) -> np.ndarray:
     return (g / g.sum()).numpy()
 
 
+def gaussian_taps_np(sigma: float) -> np.ndarray:
+    """Same taps as ``gaussian_taps`` in plain numpy float32 (no torch dispatch on the hot host
+    path); differs from torch's by at most an ulp of exp()."""
+    sl = int(np.ceil(3 * sigma))
+    ts = np.arange(-sl, sl + 1, dtype=np.float32)
+    g = np.exp(-((ts / np.float32(sigma)) ** 2) / np.float32(2))
+    return (g / g.sum(dtype=np.float32)).astype(np.float32)
+
+
 def resample_stds(spacing, res_in, blur_u: float) -> np.ndarray:
     """Blur widths of the resolution simulation (synthseg.py:78-80)."""
     spacing = np.asarray(spacing, dtype=np.float64)
@@ -114,7 +123,7 @@ class DeviceTables:
         return self._put(("zoom", n_in, float(factor)), zoom_table(n_in, factor))
 
     def resample(self, n_in: int, res_in: float, spacing: float):
-        key = ("resample", n_in, float(res_in), float(spacing))
+        key = ("resample", n_in, resample_size(n_in, res_in, spacing))
         if key not in self._cache:
             tab, factor = resample_table(n_in, res_in, spacing)
             self._put(key, tab)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FSG_VERSION 100
+#define FSG_VERSION 101
 #define FSG_MAX_JOBS 16
 #define FSG_MAX_TAPS 127
 
@@ -113,6 +113,48 @@ typedef struct fsg_blur_job {
   int32_t _pad;
 } fsg_blur_job;
 int fsg_blur3d(const fsg_blur_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+
+/* K4ab — fused resolution simulation: separable banded resampling out = (Rx (x) Ry (x) Rz) in,
+ * with the RandNoise epilogue.  Replaces gaussian_blur_3d followed by the trilinear
+ * down-sampling of RandResample.__call__ (synthseg.py:63-107; utils/generation.py:84-110,
+ * 227-285) and RandNoise (synthseg.py:217-235): per axis the Gaussian taps and the two linear
+ * interpolation weights compose into one banded matrix whose rows the host supplies
+ * (window start q0 and `width` weights per output; zero weights = zero padding / positions the
+ * reference's sampler maps to 0).  With identity positions it is a plain separable blur.
+ * Requirements: q0 non-decreasing, 0 <= q0, q0 + width <= n_in.  Passes run x, y, z through
+ * tmp1 (>= n_out[0]*sy*sz floats) and tmp2 (>= n_out[0]*n_out[1]*sz floats). */
+typedef struct fsg_sepaxis {
+  const int16_t* q0; /* [n_out] first source index of each output's window */
+  const float* w;    /* [n_out][width] window weights */
+  int32_t n_out;
+  int32_t width;
+} fsg_sepaxis;
+typedef struct fsg_sepconv_job {
+  const float* src;  /* [sx][sy][sz] */
+  float* dst;        /* [n_out0][n_out1][n_out2] */
+  float* tmp1;
+  float* tmp2;
+  fsg_sepaxis ax[3];
+  const float* noise; /* [n_out0*n_out1*n_out2] injected draws or NULL -> Philox (when has_noise) */
+  fsg_rng rng;
+  float noise_std;
+  int32_t has_noise;
+} fsg_sepconv_job;
+int fsg_sepconv(const fsg_sepconv_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
+
+/* Builds one axis table of fsg_sepconv on the device: row I = w_f*taps(.-f_I) + w_c*taps(.-c_I)
+ * over the window [q0, q0+width), width = min(n_in, ntaps + (pos != NULL)).
+ * `pos` is the 1-D sampling table of the coarse grid (f < 0: the output is 0), NULL = identity
+ * positions; `taps` are the zero-padded Gaussian taps (make_gaussian_kernel,
+ * utils/generation.py:74-81), NULL = no blur on this axis.  Up to 3*FSG_MAX_JOBS tables per call. */
+typedef struct fsg_sepcompose_job {
+  const fsg_tab* pos;
+  const float* taps;
+  int16_t* q0_out; /* [n_out] */
+  float* w_out;    /* [n_out][width] */
+  int32_t ntaps, n_in, n_out, width;
+} fsg_sepcompose_job;
+int fsg_sep_compose(const fsg_sepcompose_job* jobs_host, int njobs, void* stream);
 
 /* K4b — trilinear resampling onto a regular coarse grid + additive noise.
  * Replaces RandResample.__call__'s interpolation (synthseg.py:84-107 ->

@@ -17,7 +17,7 @@ if torch.cuda.is_available():
 
 def test_library_loaded_and_abi():
     lib = _lib.load(build_if_missing=False)
-    assert lib.fsg_version() == 100
+    assert lib.fsg_version() == 101
 
 
 def test_philox_raw_matches_published_algorithm():
@@ -135,6 +135,65 @@ def test_stage_outputs_vs_reference_golden(name):
         eng.zoom([noisy], [d["noisy"].shape], [1 / d["factors"]], up, post=1)
         assert rel_err(up.view(shape), d["final"]) <= 1e-6
         assert up.max().item() == 1.0
+
+
+@pytest.mark.parametrize("name", [c for c in BASE_CASES if "blurred" in load_case(c)])
+def test_fused_blur_resample_vs_reference_golden(name):
+    """fsg_sep_compose + fsg_sepconv (blur composed with the down-sampling, noise epilogue) against
+    the reference's blur -> interp -> noise outputs."""
+    d = load_case(name)
+    eng = engine_from_golden(d)
+    plan = plan_from_golden(d)
+    shape = d["labels"].shape
+    src = torch.from_numpy(d["bias_out"]).to(DEV).contiguous().view(1, -1)
+    low, tmp = torch.empty_like(src), torch.empty_like(src)
+    info = eng.sepconv([plan], src, low, low, tmp)
+    assert info[0][0] == d["lowres"].shape
+    np.testing.assert_allclose(info[0][1], d["factors"], rtol=0, atol=0)
+    got = low[0, : d["noisy"].size].view(d["noisy"].shape)
+    assert rel_err(got, d["noisy"]) <= TOL
+    # the same kernels with identity positions are the plain separable blur
+    bl = torch.empty_like(src)
+    tmp1 = torch.empty_like(src)
+    eng.sepconv([SamplePlan(stds=plan.stds)], src, bl, tmp1, tmp, positions=False)
+    assert rel_err(bl.view(shape), d["blurred"]) <= TOL
+
+
+@pytest.mark.parametrize("shape,sigma", [((40, 36, 44), 0.6), ((40, 36, 44), 2.4), ((31, 45, 38), 4.9), ((64, 48, 80), 11.0)])
+def test_sepconv_blur_all_window_widths(shape, sigma):
+    """Window widths 5..67 taps: the W=8/16/32 register kernels and the generic fallback."""
+    rs = np.random.RandomState(int(sigma * 10))
+    x = (rs.rand(*shape) * 300).astype(np.float32)
+    stds = np.array([sigma, sigma * 0.5, sigma])
+    want = O.gaussian_blur_3d(x, stds)
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    src = torch.from_numpy(x).to(DEV).view(1, -1)
+    out, t1, t2 = torch.empty_like(src), torch.empty_like(src), torch.empty_like(src)
+    eng.sepconv([SamplePlan(stds=stds)], src, out, t1, t2, positions=False)
+    assert rel_err(out.view(shape), want) <= 1e-5
+
+
+def test_sepconv_philox_noise_moments():
+    """Philox-mode noise of the fused kernel: N(0, std) residuals, clamp at 0, fresh per sample."""
+    shape = (96, 96, 96)
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    src = torch.full((2, eng.nvox), 200.0, dtype=torch.float32, device=DEV)
+    plans = []
+    for sid in (1, 2):
+        p = SamplePlan(spacing=np.array([0.8] * 3), stds=np.array([0.0] * 3), noise_std=10.0, rng_seed=77, sample_id=sid)
+        plans.append(p)
+    low, tmp = torch.empty_like(src), torch.empty_like(src)
+    info = eng.sepconv(plans, src, low, low, tmp)
+    n = int(np.prod(info[0][0]))
+    a, b = low[0, :n].double(), low[1, :n].double()
+    # interior voxels are exactly 200 before the noise (weights sum to 1); borders are partly zero padded
+    vol = a.view(info[0][0])[2:-2, 2:-2, 2:-2].reshape(-1)
+    assert abs(vol.mean().item() - 200) < 0.05 and abs(vol.std().item() - 10) < 0.05
+    r = (vol - 200) / 10
+    assert abs((r**3).mean().item()) < 0.03 and abs((r**4).mean().item() - 3) < 0.08
+    for lag in (1, 2, 3, 4, info[0][0][2]):
+        assert abs((r[:-lag] * r[lag:]).mean().item()) < 5 / np.sqrt(r.numel())
+    assert not torch.equal(a, b) and (low[:, :n] >= 0).all()
 
 
 def _random_plan(rs, shape, dev, deform=True, resample=True):
