@@ -86,19 +86,33 @@ struct Philox {
   }
 };
 
+__device__ __forceinline__ float lg2_approx_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx_ftz(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Four standard normals for counter block `blk` of stream (stage, sample): Box-Muller on the
-// two word pairs.  u1 in (0,1], u2 in [0,1).
+// two word pairs.  Uniforms are built from mantissa bits (no int->float conversion):
+// u1 = 2 - [1,2) in (0,1] with 23 bits, u2 = [1,2) - 1 in [0,1); ln via lg2.approx.
 __device__ __forceinline__ float4 philox_normal4(const fsg_rng& r, uint32_t blk) {
   const Philox ph(r.seed);
   const uint4 w = ph(blk, r.stage, (uint32_t)r.sample, (uint32_t)(r.sample >> 32));
-  const float inv = 2.3283064365386963e-10f;  // 2^-32
-  const float u1a = ((float)(w.x >> 8) + 1.0f) * 5.9604644775390625e-08f;  // (0,1], 24 bit
-  const float u1b = ((float)(w.z >> 8) + 1.0f) * 5.9604644775390625e-08f;
-  const float ra = sqrtf(-2.0f * __logf(u1a));
-  const float rb = sqrtf(-2.0f * __logf(u1b));
+  const float u1a = 2.0f - __uint_as_float(0x3f800000u | (w.x >> 9));
+  const float u1b = 2.0f - __uint_as_float(0x3f800000u | (w.z >> 9));
+  const float u2a = __uint_as_float(0x3f800000u | (w.y >> 9)) - 1.0f;
+  const float u2b = __uint_as_float(0x3f800000u | (w.w >> 9)) - 1.0f;
+  // -2 ln u = (-2 ln 2) * log2 u
+  const float ra = sqrt_approx_ftz(-1.3862943611198906f * lg2_approx_ftz(u1a));
+  const float rb = sqrt_approx_ftz(-1.3862943611198906f * lg2_approx_ftz(u1b));
   float sa, ca, sb, cb;
-  __sincosf(6.283185307179586f * ((float)w.y * inv), &sa, &ca);
-  __sincosf(6.283185307179586f * ((float)w.w * inv), &sb, &cb);
+  __sincosf(6.283185307179586f * u2a, &sa, &ca);
+  __sincosf(6.283185307179586f * u2b, &sb, &cb);
   return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
 }
 

@@ -10,61 +10,60 @@ namespace fsg {
 constexpr int GMM_THREADS = 256;
 constexpr int GMM_MAX_LABELS = 256;
 
-template <bool INJECT>
+// NSEED = number of leading non-NULL seed pointers (the host entry compacts them).
+template <bool INJECT, int NSEED>
 __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant__ Batch<fsg_gmm_job> batch, int64_t nvox) {
   const fsg_gmm_job& job = batch.j[blockIdx.y];
-  __shared__ float s_mu[GMM_MAX_LABELS], s_sg[GMM_MAX_LABELS];
+  __shared__ float2 s_ms[GMM_MAX_LABELS];  // (mu, sigma) per label
   for (int i = threadIdx.x; i < GMM_MAX_LABELS; i += GMM_THREADS) {
     const bool in = i < job.nlabels;
-    s_mu[i] = in ? job.mus[i] : 0.f;
-    s_sg[i] = in ? job.sigmas[i] : 0.f;
+    s_ms[i] = make_float2(in ? job.mus[i] : 0.f, in ? job.sigmas[i] : 0.f);
   }
   __syncthreads();
 
-  const int64_t ngroups = (nvox + 3) / 4;
+  const int8_t* __restrict__ sp[4] = {job.seed[0], job.seed[1], job.seed[2], job.seed[3]};
+  const float* __restrict__ noise = job.noise;
+  float* __restrict__ out = job.out;
+  uint8_t* __restrict__ lab_out = job.labels_out;
+  const fsg_rng rng = job.rng;
+
+  const int64_t ngroups = nvox >> 2;  // whole groups of 4 voxels; the tail is handled below
   const int64_t stride = (int64_t)gridDim.x * GMM_THREADS;
   for (int64_t g = (int64_t)blockIdx.x * GMM_THREADS + threadIdx.x; g < ngroups; g += stride) {
     const int64_t v0 = g * 4;
-    const bool full = v0 + 4 <= nvox;
-    int lab[4] = {0, 0, 0, 0};
+    // labels of the seed volumes are disjoint small non-negative codes: one byte-wise SIMD add sums 4 voxels
+    uint32_t lab4 = 0;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int8_t* sp = job.seed[m];
-      if (sp == nullptr) continue;
-      if (full) {
-        const char4 c = __ldg(reinterpret_cast<const char4*>(sp + v0));
-        lab[0] += c.x; lab[1] += c.y; lab[2] += c.z; lab[3] += c.w;
-      } else {
-        for (int e = 0; e < 4 && v0 + e < nvox; ++e) lab[e] += sp[v0 + e];
-      }
+    for (int m = 0; m < NSEED; ++m) lab4 = __vadd4(lab4, __ldcs(reinterpret_cast<const uint32_t*>(sp[m] + v0)));
+    float4 n;
+    if (INJECT)
+      n = __ldcs(reinterpret_cast<const float4*>(noise + v0));
+    else
+      n = philox_normal4(rng, (uint32_t)g);
+    const float2 m0 = s_ms[lab4 & 0xff], m1 = s_ms[(lab4 >> 8) & 0xff], m2 = s_ms[(lab4 >> 16) & 0xff], m3 = s_ms[lab4 >> 24];
+    float4 o;
+    o.x = fmaxf(add_rn(m0.x, mul_rn(m0.y, n.x)), 0.f);
+    o.y = fmaxf(add_rn(m1.x, mul_rn(m1.y, n.y)), 0.f);
+    o.z = fmaxf(add_rn(m2.x, mul_rn(m2.y, n.z)), 0.f);
+    o.w = fmaxf(add_rn(m3.x, mul_rn(m3.y, n.w)), 0.f);
+    *reinterpret_cast<float4*>(out + v0) = o;
+    if (lab_out) *reinterpret_cast<uint32_t*>(lab_out + v0) = lab4;
+  }
+  // tail (nvox % 4 voxels): one thread, scalar
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (nvox & 3)) {
+    const int64_t v0 = ngroups * 4;
+    float nn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!INJECT) {
+      const float4 q = philox_normal4(rng, (uint32_t)ngroups);
+      nn[0] = q.x; nn[1] = q.y; nn[2] = q.z; nn[3] = q.w;
     }
-    float n[4];
-    if (INJECT) {
-      if (full) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(job.noise + v0));
-        n[0] = q.x; n[1] = q.y; n[2] = q.z; n[3] = q.w;
-      } else {
-        for (int e = 0; e < 4; ++e) n[e] = (v0 + e < nvox) ? job.noise[v0 + e] : 0.f;
-      }
-    } else {
-      const float4 q = philox_normal4(job.rng, (uint32_t)g);
-      n[0] = q.x; n[1] = q.y; n[2] = q.z; n[3] = q.w;
-    }
-    float o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int l = lab[e] & (GMM_MAX_LABELS - 1);
-      const float v = add_rn(s_mu[l], mul_rn(s_sg[l], n[e]));
-      o[e] = v < 0.f ? 0.f : v;
-    }
-    if (full) {
-      *reinterpret_cast<float4*>(job.out + v0) = make_float4(o[0], o[1], o[2], o[3]);
-      if (job.labels_out) *reinterpret_cast<uchar4*>(job.labels_out + v0) = make_uchar4(lab[0], lab[1], lab[2], lab[3]);
-    } else {
-      for (int e = 0; e < 4 && v0 + e < nvox; ++e) {
-        job.out[v0 + e] = o[e];
-        if (job.labels_out) job.labels_out[v0 + e] = (uint8_t)lab[e];
-      }
+    for (int e = 0; v0 + e < nvox; ++e) {
+      int l = 0;
+      for (int m = 0; m < NSEED; ++m) l += sp[m][v0 + e];
+      const float nz = INJECT ? noise[v0 + e] : nn[e];
+      const float2 ms = s_ms[l & (GMM_MAX_LABELS - 1)];
+      out[v0 + e] = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
+      if (lab_out) lab_out[v0 + e] = (uint8_t)l;
     }
   }
 }
@@ -91,30 +90,48 @@ __global__ void __launch_bounds__(256) philox_fill_kernel(fsg_rng rng, float* ou
 
 using namespace fsg;
 
+template <bool INJECT>
+static void launch_gmm(const Batch<fsg_gmm_job>& b, int nseed, dim3 grid, int64_t nvox, cudaStream_t s) {
+  switch (nseed) {
+    case 1: gmm_kernel<INJECT, 1><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
+    case 2: gmm_kernel<INJECT, 2><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
+    case 3: gmm_kernel<INJECT, 3><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
+    default: gmm_kernel<INJECT, 4><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
+  }
+}
+
 extern "C" int fsg_gmm(const fsg_gmm_job* jobs, int njobs, int64_t nvox, void* stream) {
   Batch<fsg_gmm_job> b;
   if (int rc = fill_batch(b, jobs, njobs)) return rc;
   FSG_REQUIRE(nvox > 0, "fsg_gmm: nvox must be positive");
   FSG_REQUIRE(nvox / 4 < (int64_t)1 << 32, "fsg_gmm: volume too large for the 32-bit Philox block counter");
   bool inject = jobs[0].noise != nullptr;
+  int nseed = -1;
   for (int i = 0; i < njobs; ++i) {
     const fsg_gmm_job& j = jobs[i];
     FSG_REQUIRE(j.out && j.mus && j.sigmas, "fsg_gmm: job %d has a NULL out/mus/sigmas", i);
-    FSG_REQUIRE(j.seed[0] || j.seed[1] || j.seed[2] || j.seed[3], "fsg_gmm: job %d has no seed volume", i);
     FSG_REQUIRE(j.nlabels >= 1 && j.nlabels <= GMM_MAX_LABELS, "fsg_gmm: nlabels=%d outside [1,%d]", j.nlabels, GMM_MAX_LABELS);
     FSG_REQUIRE((j.noise != nullptr) == inject, "fsg_gmm: jobs mix injected and Philox noise");
+    // compact the seed pointers of the launch copy to the front
+    int n = 0;
+    for (int m = 0; m < 4; ++m)
+      if (j.seed[m]) b.j[i].seed[n++] = j.seed[m];
+    for (int m = n; m < 4; ++m) b.j[i].seed[m] = nullptr;
+    FSG_REQUIRE(n >= 1, "fsg_gmm: job %d has no seed volume", i);
+    FSG_REQUIRE(nseed < 0 || nseed == n, "fsg_gmm: jobs of one launch must have the same number of seed volumes");
+    nseed = n;
     for (int m = 0; m < 4; ++m) FSG_REQUIRE((reinterpret_cast<uintptr_t>(j.seed[m]) & 3) == 0, "fsg_gmm: seed pointers must be 4-byte aligned");
     FSG_REQUIRE((reinterpret_cast<uintptr_t>(j.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.noise) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.labels_out) & 3) == 0,
                 "fsg_gmm: out/noise must be 16-byte aligned");
   }
   const int64_t ngroups = (nvox + 3) / 4;
   int64_t want = (ngroups + GMM_THREADS - 1) / GMM_THREADS;
-  const int64_t cap = 148 * 32;
+  const int64_t cap = 148 * 16;
   dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)njobs);
   if (inject)
-    gmm_kernel<true><<<grid, GMM_THREADS, 0, as_stream(stream)>>>(b, nvox);
+    launch_gmm<true>(b, nseed, grid, nvox, as_stream(stream));
   else
-    gmm_kernel<false><<<grid, GMM_THREADS, 0, as_stream(stream)>>>(b, nvox);
+    launch_gmm<false>(b, nseed, grid, nvox, as_stream(stream));
   return check_launch("fsg_gmm");
 }
 

@@ -5,9 +5,9 @@
 // (augmentation/synthseg.py:63-107 -> utils/generation.py:84-110, 227-285).  Both steps are
 // linear and separable, so per axis they compose into ONE banded matrix R_a (n_out x n_in)
 // whose row I holds  w_f*taps(. - f_I) + w_c*taps(. - c_I)  (zero rows where the reference's
-// linear sampler returns 0, zero padding = dropped taps).  The host builds the rows in float64
-// (fetalsyngen_b200/tables.py:sep_axis_table); the device applies them axis by axis, shrinking
-// the volume at every pass:
+// linear sampler returns 0, zero padding = dropped taps).  fsg_sep_compose builds the rows on the
+// device from the host's 1-D position tables and taps; fsg_sepconv applies them axis by axis,
+// shrinking the volume at every pass:
 //     x: [sx][sy][sz] -> [n0][sy][sz]     streaming, register sliding window, 4N + 4fN bytes
 //     y: [n0][sy][sz] -> [n0][n1][sz]     streaming, register sliding window
 //     z: [n0][n1][sz] -> [n0][n1][n2]     rows staged in shared memory, + RandNoise epilogue
@@ -128,20 +128,29 @@ template <int W, bool INJECT>
 __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_constant__ SepPass p, const __grid_constant__ SepNoise nz, int a_in) {
   const int jb = blockIdx.y;
   const int n_out = p.n_out[jb], width = p.width[jb], rows = p.outer[jb];
-  extern __shared__ float s_rows[];  // [SEPZ_ROWS][a_in]
+  // rows are stored with W zero floats in front (pitch a_in + W), so a right-aligned window that
+  // starts before the row reads zeros and the tap loop needs no bounds logic
+  extern __shared__ float s_rows[];  // [SEPZ_ROWS][W + a_in]
+  const int pitch = a_in + W;
   const int row0 = blockIdx.x * SEPZ_ROWS;
   if (row0 >= rows) return;
   const int nrow = min(SEPZ_ROWS, rows - row0);
   {
     const float* __restrict__ src = p.src[jb] + (size_t)row0 * a_in;
-    const int n = nrow * a_in;
-    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (n % 4 == 0)) {
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (a_in % 4 == 0)) {
       const float4* s4 = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(s_rows);
-      for (int e = threadIdx.x; e < n / 4; e += SEPZ_THREADS) d4[e] = __ldcs(s4 + e);
+      const int a4 = a_in / 4;
+      for (int e = threadIdx.x; e < nrow * a4; e += SEPZ_THREADS) {
+        const int r = e / a4, c = e - r * a4;
+        *reinterpret_cast<float4*>(s_rows + r * pitch + W + 4 * c) = __ldcs(s4 + e);
+      }
     } else {
-      for (int e = threadIdx.x; e < n; e += SEPZ_THREADS) s_rows[e] = __ldcs(src + e);
+      for (int e = threadIdx.x; e < nrow * a_in; e += SEPZ_THREADS) {
+        const int r = e / a_in, c = e - r * a_in;
+        s_rows[r * pitch + W + c] = __ldcs(src + e);
+      }
     }
+    for (int e = threadIdx.x; e < nrow * W; e += SEPZ_THREADS) s_rows[(e / W) * pitch + (e % W)] = 0.f;
   }
   __syncthreads();
 
@@ -166,20 +175,20 @@ __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_consta
 #pragma unroll
       for (int t = 0; t < W; ++t) wreg[t] = 0.f;
     }
-    const int qlo = max(q0, 0);
-    const int skip = qlo - q0;  // leading window slots that fall before the row start
     const int kbase = K - lane;
     float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
     int m = 0;
     for (int r = g; r < nrow; r += groups, ++m) {
       float acc = 0.f;
-      if (live) {
-        const float* row = s_rows + r * a_in + q0;
+      {
+        const float* row = s_rows + r * pitch + W + q0;  // q0 >= -W (dead lanes: q0 = 0, zero weights)
+        float acc2 = 0.f;
 #pragma unroll
-        for (int t = 0; t < W; ++t) {
-          const float v = (t >= skip) ? row[t] : 0.f;
-          acc = __fmaf_rn(wreg[t], v, acc);
+        for (int t = 0; t < W; t += 2) {
+          acc = __fmaf_rn(wreg[t], row[t], acc);
+          acc2 = __fmaf_rn(wreg[t + 1], row[t + 1], acc2);
         }
+        acc = __fadd_rn(acc, acc2);
       }
       if (has_noise) {
         float nv;
@@ -286,7 +295,7 @@ static void launch_stream(const SepPass& p, int njobs, int a_in, int inner, int 
 
 template <int W>
 static void launch_z(const SepPass& p, const SepNoise& nz, int njobs, int a_in, int max_rows, bool inject, cudaStream_t s) {
-  const size_t smem = (size_t)SEPZ_ROWS * a_in * sizeof(float);
+  const size_t smem = (size_t)SEPZ_ROWS * (a_in + W) * sizeof(float);
   const unsigned gx = (unsigned)((max_rows + SEPZ_ROWS - 1) / SEPZ_ROWS);
   if (inject) {
     auto k = sep_z_kernel<W, true>;

@@ -21,7 +21,7 @@
 //     into the x stride, and the float image path uses FMA lerps and ex2/lg2 approximations
 //     (image parity is a tolerance, not bit-exactness);
 //   * floor(min coordinate) (the reference's crop-shift quirk) is resolved by a pre-pass over
-//     the six faces of the volume; the full-volume pre-pass only runs for jobs whose faces do
+//     the twelve edges of the volume; the full-volume pre-pass only runs for jobs whose edges do
 //     not already prove the shift to be 0.
 #include "common.cuh"
 
@@ -48,7 +48,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float lerp_fma(float a, float b, float w) { return __fmaf_rn(w, __fsub_rn(b, a), a); }
 
 // Exact control-grid value at voxel (i,j,k): x-, y-, z-blend in myzoom_torch's order.  Used by
-// the face pre-pass only (the main kernel stages the x/y blends in shared memory).
+// the edge pre-pass only (the main kernel stages the x/y blends in shared memory).
 __device__ __forceinline__ void field_at(const fsg_warp_job& job, int i, int j, int k, float& fx, float& fy, float& fz) {
   const Tab tx = load_tab(job.ftab[0], i), ty = load_tab(job.ftab[1], j), tz = load_tab(job.ftab[2], k);
   const int n1 = job.fs[1], n2 = job.fs[2];
@@ -70,42 +70,53 @@ __device__ __forceinline__ void field_at(const fsg_warp_job& job, int i, int j, 
   fz = out[2];
 }
 
+// Affine part of the deformation, copied out of the kernel-parameter space once per thread.
+struct Affine {
+  float a[9], c[3];
+  __device__ __forceinline__ explicit Affine(const fsg_warp_job& job) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a[q] = job.A[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) c[q] = job.c2[q];
+  }
+};
 // Clamped (not yet shifted) sample coordinate of one voxel from its centred position + field.
-__device__ __forceinline__ void affine_clamp(const fsg_warp_job& job, float x1, float y1, float z1, float mx, float my, float mz, float& ii, float& jj, float& kk) {
-  ii = add_rn(add_rn(add_rn(mul_rn(job.A[0], x1), mul_rn(job.A[1], y1)), mul_rn(job.A[2], z1)), job.c2[0]);
-  jj = add_rn(add_rn(add_rn(mul_rn(job.A[3], x1), mul_rn(job.A[4], y1)), mul_rn(job.A[5], z1)), job.c2[1]);
-  kk = add_rn(add_rn(add_rn(mul_rn(job.A[6], x1), mul_rn(job.A[7], y1)), mul_rn(job.A[8], z1)), job.c2[2]);
+__device__ __forceinline__ void affine_clamp(const Affine& t, float x1, float y1, float z1, float mx, float my, float mz, float& ii, float& jj, float& kk) {
+  ii = add_rn(add_rn(add_rn(mul_rn(t.a[0], x1), mul_rn(t.a[1], y1)), mul_rn(t.a[2], z1)), t.c[0]);
+  jj = add_rn(add_rn(add_rn(mul_rn(t.a[3], x1), mul_rn(t.a[4], y1)), mul_rn(t.a[5], z1)), t.c[1]);
+  kk = add_rn(add_rn(add_rn(mul_rn(t.a[6], x1), mul_rn(t.a[7], y1)), mul_rn(t.a[8], z1)), t.c[2]);
   ii = fminf(fmaxf(ii, 0.f), mx);
   jj = fminf(fmaxf(jj, 0.f), my);
   kk = fminf(fmaxf(kk, 0.f), mz);
 }
 
-// ---------------------------------------------------------------------------------- face pre-pass
-// One thread per voxel of the six faces; atomicMin of the clamped coordinates into job.shift.
-__global__ void __launch_bounds__(256) shift_faces_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
+// ---------------------------------------------------------------------------------- edge pre-pass
+// One thread per voxel of the twelve edges of the volume; atomicMin of the clamped coordinates
+// into job.shift.  The minimum of an affine map over a box sits on its boundary, and with the
+// smooth control-grid field added it stays next to it, so an edge voxel with a coordinate < 1
+// proves floor(min) == 0 for that axis (coordinates are clamped at 0).  This is only a
+// sufficient test: jobs it does not resolve run the exact full-volume pass.
+__global__ void __launch_bounds__(128) shift_edges_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
   const fsg_warp_job& job = batch.j[blockIdx.y];
-  const int n_yz = sy * sz, n_xz = sx * sz, n_xy = sx * sy;
-  const int total = 2 * (n_yz + n_xz + n_xy);
+  const int total = 4 * (sx + sy + sz);
   const float inf = __int_as_float(0x7f800000);
   float mnx = inf, mny = inf, mnz = inf;
+  const Affine aff(job);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     int i, j, k, r = t;
-    if (r < 2 * n_yz) {
-      i = (r >= n_yz) ? sx - 1 : 0;
-      r -= (r >= n_yz) ? n_yz : 0;
-      j = r / sz;
-      k = r - j * sz;
-    } else if ((r -= 2 * n_yz) < 2 * n_xz) {
-      j = (r >= n_xz) ? sy - 1 : 0;
-      r -= (r >= n_xz) ? n_xz : 0;
-      i = r / sz;
-      k = r - i * sz;
+    if (r < 4 * sx) {
+      i = r >> 2;
+      j = (r & 1) ? sy - 1 : 0;
+      k = (r & 2) ? sz - 1 : 0;
+    } else if ((r -= 4 * sx) < 4 * sy) {
+      j = r >> 2;
+      i = (r & 1) ? sx - 1 : 0;
+      k = (r & 2) ? sz - 1 : 0;
     } else {
-      r -= 2 * n_xz;
-      k = (r >= n_xy) ? sz - 1 : 0;
-      r -= (r >= n_xy) ? n_xy : 0;
-      i = r / sy;
-      j = r - i * sy;
+      r -= 4 * sy;
+      k = r >> 2;
+      i = (r & 1) ? sx - 1 : 0;
+      j = (r & 2) ? sy - 1 : 0;
     }
     float x1 = sub_rn((float)i, job.center[0]), y1 = sub_rn((float)j, job.center[1]), z1 = sub_rn((float)k, job.center[2]);
     if (job.fsmall != nullptr) {
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(256) shift_faces_kernel(const __grid_constant_
       z1 = add_rn(z1, fz);
     }
     float ii, jj, kk;
-    affine_clamp(job, x1, y1, z1, (float)(sx - 1), (float)(sy - 1), (float)(sz - 1), ii, jj, kk);
+    affine_clamp(aff, x1, y1, z1, (float)(sx - 1), (float)(sy - 1), (float)(sz - 1), ii, jj, kk);
     mnx = fminf(mnx, ii);
     mny = fminf(mny, jj);
     mnz = fminf(mnz, kk);
@@ -139,7 +150,7 @@ struct ZTab {  // per-thread z table entry of a control grid, pre-scaled for flo
   float wc, wf;
 };
 
-template <int PASS>
+template <int PASS, bool IMG2>
 __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz, float* __restrict__ dbg_x,
                                                              float* __restrict__ dbg_y, float* __restrict__ dbg_z) {
   const fsg_warp_job& job = batch.j[blockIdx.z];
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
   const bool has_bias = (PASS == PASS_WARP) && job.bf_low != nullptr && job.dst_img != nullptr;
 
   if (PASS == PASS_SHIFT) {
-    // the face pre-pass already proved floor(min) == 0 on every axis: nothing to do
+    // the edge pre-pass already proved floor(min) == 0 on every axis: nothing to do
     const float* sh = job.shift;
     if (sh[0] < 1.f && sh[1] < 1.f && sh[2] < 1.f) return;
   }
@@ -175,6 +186,15 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
   const int xb = job.flip ? (sx - 1) * plane : 0;
   const float gamma = job.gamma;
   const bool has_gamma = (PASS == PASS_WARP) && job.has_gamma;
+  const Affine aff(job);
+  const float cen_x = job.center[0], cen_y = job.center[1], cen_z = job.center[2];
+  const float* __restrict__ const src_img = job.src_img;
+  const float* __restrict__ const src_img2 = IMG2 ? job.src_img2 : nullptr;
+  const uint8_t* __restrict__ const src_seg = job.src_seg;
+  float* __restrict__ const dst_img = job.dst_img;
+  float* __restrict__ const dst_img2 = IMG2 ? job.dst_img2 : nullptr;
+  uint8_t* __restrict__ const dst_seg = job.dst_seg;
+  const bool do_img = dst_img != nullptr, do_seg = dst_seg != nullptr, do_img2 = IMG2 && dst_img2 != nullptr;
 
   const int ntile_y = (sy + WY - 1) / WY;
   const int ntiles = ntile_y * ((sx + WX - 1) / WX);
@@ -228,28 +248,28 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
         const Tab t = load_tab(job.btab[2], k);
         tbz.f = t.f; tbz.c = t.c; tbz.wc = t.wc; tbz.wf = t.wf;
       }
-      const float zc = sub_rn((float)k, job.center[2]);
+      const float zc = sub_rn((float)k, cen_z);
 #pragma unroll 1
       for (int ry = 0; ry < WY; ++ry) {
         const int j = y0 + ry;
         if (j >= sy) break;
-        const float yc = sub_rn((float)j, job.center[1]);
+        const float yc = sub_rn((float)j, cen_y);
 #pragma unroll 2
         for (int rx = 0; rx < WX; ++rx) {
           const int i = x0 + rx;
           if (i >= sx) break;
           const int row = rx * WY + ry;
-          const int o = (i * sy + j) * sz + k;
+          const unsigned o = (unsigned)((i * sy + j) * sz + k);
           float ii, jj, kk;
           if (deform) {
-            float x1 = sub_rn((float)i, job.center[0]), y1 = yc, z1 = zc;
+            float x1 = sub_rn((float)i, cen_x), y1 = yc, z1 = zc;
             if (has_field) {
               const float4 f0 = s_f[row * fz_n + tfz.f], f1 = s_f[row * fz_n + tfz.c];
               x1 = add_rn(x1, blend(tfz.wf, f0.x, tfz.wc, f1.x));
               y1 = add_rn(y1, blend(tfz.wf, f0.y, tfz.wc, f1.y));
               z1 = add_rn(z1, blend(tfz.wf, f0.z, tfz.wc, f1.z));
             }
-            affine_clamp(job, x1, y1, z1, mx, my, mz, ii, jj, kk);
+            affine_clamp(aff, x1, y1, z1, mx, my, mz, ii, jj, kk);
             if (PASS == PASS_SHIFT) {
               mnx = fminf(mnx, ii);
               mny = fminf(mny, jj);
@@ -275,18 +295,18 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
           if (PASS == PASS_WARP) {
             if (!deform) {
               // identity sampling: only flip + epilogues (deformation gate off)
-              const int so = xb + i * xs + j * sz + k;
-              if (job.dst_img) {
-                float v = __ldg(job.src_img + so);
+              const unsigned so = (unsigned)(xb + i * xs + j * sz + k);
+              if (do_img) {
+                float v = __ldg(src_img + so);
                 if (has_gamma) v = mul_rn(300.0f, ex2_approx(mul_rn(gamma, lg2_approx(mul_rn(v, 1.0f / 300.0f)))));
                 if (has_bias) v = mul_rn(v, ex2_approx(mul_rn(1.4426950408889634f, blend(tbz.wf, s_b[row][tbz.f], tbz.wc, s_b[row][tbz.c]))));
-                job.dst_img[o] = v;
+                dst_img[o] = v;
               }
-              if (job.dst_seg) job.dst_seg[o] = __ldg(job.src_seg + so);
-              if (job.dst_img2) job.dst_img2[o] = __ldg(job.src_img2 + so);
+              if (do_seg) dst_seg[o] = __ldg(src_seg + so);
+              if (do_img2) dst_img2[o] = __ldg(src_img2 + so);
               continue;
             }
-            if (job.dst_img || job.dst_img2) {
+            if (do_img || do_img2) {
               // coordinates are in [0, S-1]: floor via a round-toward-zero magic add
               const float tx_ = __fadd_rz(ii, MAGIC), ty_ = __fadd_rz(jj, MAGIC), tz_ = __fadd_rz(kk, MAGIC);
               const int fx = __float_as_int(tx_) - 0x4B000000, fy = __float_as_int(ty_) - 0x4B000000, fz = __float_as_int(tz_) - 0x4B000000;
@@ -294,39 +314,42 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
               const int cx = min(fx + 1, sx - 1), cy = min(fy + 1, sy - 1), cz = min(fz + 1, sz - 1);
               const bool ok = fminf(fminf(ii, jj), kk) > 0.f;
               const int of = xb + fx * xs, oc = xb + cx * xs;
-              const int off = of + fy * sz, ofc = of + cy * sz, ocf = oc + fy * sz, occ = oc + cy * sz;
-              if (job.dst_img) {
-                const float* __restrict__ s = job.src_img;
-                const float c000 = __ldg(s + off + fz), c001 = __ldg(s + off + cz);
-                const float c100 = __ldg(s + ocf + fz), c101 = __ldg(s + ocf + cz);
-                const float c010 = __ldg(s + ofc + fz), c011 = __ldg(s + ofc + cz);
-                const float c110 = __ldg(s + occ + fz), c111 = __ldg(s + occ + cz);
+              const int rf = fy * sz, rc = cy * sz;
+              // all element offsets are non-negative: unsigned indices keep the address math 32-bit
+              const unsigned i000 = (unsigned)(of + rf + fz), i001 = (unsigned)(of + rf + cz);
+              const unsigned i100 = (unsigned)(oc + rf + fz), i101 = (unsigned)(oc + rf + cz);
+              const unsigned i010 = (unsigned)(of + rc + fz), i011 = (unsigned)(of + rc + cz);
+              const unsigned i110 = (unsigned)(oc + rc + fz), i111 = (unsigned)(oc + rc + cz);
+              if (do_img) {
+                const float c000 = __ldg(src_img + i000), c001 = __ldg(src_img + i001);
+                const float c100 = __ldg(src_img + i100), c101 = __ldg(src_img + i101);
+                const float c010 = __ldg(src_img + i010), c011 = __ldg(src_img + i011);
+                const float c110 = __ldg(src_img + i110), c111 = __ldg(src_img + i111);
                 const float c00 = lerp_fma(c000, c100, wcx), c01 = lerp_fma(c001, c101, wcx);
                 const float c10 = lerp_fma(c010, c110, wcx), c11 = lerp_fma(c011, c111, wcx);
                 float v = lerp_fma(lerp_fma(c00, c10, wcy), lerp_fma(c01, c11, wcy), wcz);
                 v = ok ? v : 0.f;
                 if (has_gamma) v = mul_rn(300.0f, ex2_approx(mul_rn(gamma, lg2_approx(mul_rn(v, 1.0f / 300.0f)))));
                 if (has_bias) v = mul_rn(v, ex2_approx(mul_rn(1.4426950408889634f, blend(tbz.wf, s_b[row][tbz.f], tbz.wc, s_b[row][tbz.c]))));
-                job.dst_img[o] = v;
+                dst_img[o] = v;
               }
-              if (job.dst_img2) {
-                const float* __restrict__ s = job.src_img2;
-                const float c000 = __ldg(s + off + fz), c001 = __ldg(s + off + cz);
-                const float c100 = __ldg(s + ocf + fz), c101 = __ldg(s + ocf + cz);
-                const float c010 = __ldg(s + ofc + fz), c011 = __ldg(s + ofc + cz);
-                const float c110 = __ldg(s + occ + fz), c111 = __ldg(s + occ + cz);
+              if (do_img2) {
+                const float c000 = __ldg(src_img2 + i000), c001 = __ldg(src_img2 + i001);
+                const float c100 = __ldg(src_img2 + i100), c101 = __ldg(src_img2 + i101);
+                const float c010 = __ldg(src_img2 + i010), c011 = __ldg(src_img2 + i011);
+                const float c110 = __ldg(src_img2 + i110), c111 = __ldg(src_img2 + i111);
                 const float c00 = lerp_fma(c000, c100, wcx), c01 = lerp_fma(c001, c101, wcx);
                 const float c10 = lerp_fma(c010, c110, wcx), c11 = lerp_fma(c011, c111, wcx);
                 const float v = lerp_fma(lerp_fma(c00, c10, wcy), lerp_fma(c01, c11, wcy), wcz);
-                job.dst_img2[o] = ok ? v : 0.f;
+                dst_img2[o] = ok ? v : 0.f;
               }
             }
-            if (job.dst_seg) {
+            if (do_seg) {
               // round-half-even of a coordinate in [0, S-1] via a round-to-nearest magic add
               const int ir = __float_as_int(add_rn(ii, MAGIC)) - 0x4B000000;
               const int jr = __float_as_int(add_rn(jj, MAGIC)) - 0x4B000000;
               const int kr = __float_as_int(add_rn(kk, MAGIC)) - 0x4B000000;
-              job.dst_seg[o] = __ldg(job.src_seg + xb + ir * xs + jr * sz + kr);
+              dst_seg[o] = __ldg(src_seg + (unsigned)(xb + ir * xs + jr * sz + kr));
             }
           }
         }
@@ -411,12 +434,12 @@ extern "C" int fsg_warp_shift(const fsg_warp_job* jobs, int njobs, int sx, int s
   for (int n = 0; n < njobs; ++n) FSG_REQUIRE(jobs[n].mode == 1, "fsg_warp_shift: job %d is not a deformation job", n);
   cudaStream_t s = as_stream(stream);
   shift_init_kernel<<<1, 64, 0, s>>>(b, njobs);
-  const int faces = 2 * (sy * sz + sx * sz + sx * sy);
-  shift_faces_kernel<<<dim3((faces + 255) / 256, njobs), 256, 0, s>>>(b, sx, sy, sz);
+  const int edges = 4 * (sx + sy + sz);
+  shift_edges_kernel<<<dim3((edges + 127) / 128, njobs), 128, 0, s>>>(b, sx, sy, sz);
   // full-volume pass on a bounded grid; blocks of jobs already resolved by the faces return at once
   const int ntiles = ((sy + WY - 1) / WY) * ((sx + WX - 1) / WX);
   const int gx = ntiles < 148 * 2 ? ntiles : 148 * 2;
-  warp_kernel<PASS_SHIFT><<<dim3(gx, 1, njobs), WARP_THREADS, field_smem(jobs, njobs), s>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  warp_kernel<PASS_SHIFT, false><<<dim3(gx, 1, njobs), WARP_THREADS, field_smem(jobs, njobs), s>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
   shift_final_kernel<<<1, 64, 0, s>>>(b, njobs);
   return check_launch("fsg_warp_shift");
 }
@@ -425,7 +448,12 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
   Batch<fsg_warp_job> b;
   if (int rc = fill_batch(b, jobs, njobs)) return rc;
   if (int rc = validate(jobs, njobs, sx, sy, sz, true, "fsg_warp")) return rc;
-  warp_kernel<PASS_WARP><<<warp_grid(njobs, sx, sy), WARP_THREADS, field_smem(jobs, njobs), as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  bool img2 = false;
+  for (int n = 0; n < njobs; ++n) img2 = img2 || jobs[n].dst_img2 != nullptr;
+  if (img2)
+    warp_kernel<PASS_WARP, true><<<warp_grid(njobs, sx, sy), WARP_THREADS, field_smem(jobs, njobs), as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  else
+    warp_kernel<PASS_WARP, false><<<warp_grid(njobs, sx, sy), WARP_THREADS, field_smem(jobs, njobs), as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
   return check_launch("fsg_warp");
 }
 
@@ -434,6 +462,6 @@ extern "C" int fsg_warp_coords(const fsg_warp_job* job, int sx, int sy, int sz, 
   if (int rc = fill_batch(b, job, 1)) return rc;
   if (int rc = validate(job, 1, sx, sy, sz, false, "fsg_warp_coords")) return rc;
   FSG_REQUIRE(xx && yy && zz, "fsg_warp_coords: NULL output");
-  warp_kernel<PASS_COORDS><<<warp_grid(1, sx, sy), WARP_THREADS, field_smem(job, 1), as_stream(stream)>>>(b, sx, sy, sz, xx, yy, zz);
+  warp_kernel<PASS_COORDS, false><<<warp_grid(1, sx, sy), WARP_THREADS, field_smem(job, 1), as_stream(stream)>>>(b, sx, sy, sz, xx, yy, zz);
   return check_launch("fsg_warp_coords");
 }

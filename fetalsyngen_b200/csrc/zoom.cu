@@ -24,7 +24,10 @@ __device__ __forceinline__ float div_nr(float a, float b, float rb) {
   return __fmaf_rn(e, rb, y);
 }
 
-template <bool REDUCE>
+// KG > 0: sz == 128*KG and every lane owns the same KG groups of 4 consecutive z positions for
+// all rows, so its z-table entries live in registers and the stores are 16-byte vectors.
+// KG == 0: generic extents, z table read from shared memory per voxel.
+template <bool REDUCE, int KG>
 __global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int sx, int sy, int sz) {
   const fsg_zoom_job& job = batch.j[blockIdx.y];
   const int n1 = job.n[1], n2 = job.n[2];
@@ -32,24 +35,42 @@ __global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_cons
   // layout: z table [sz] as (int f | c<<16, float wc), then one coarse row per warp
   int2* s_tz = reinterpret_cast<int2*>(s_zoom);
   float* s_row = s_zoom + 2 * sz + (threadIdx.x >> 5) * n2;
-  for (int k = threadIdx.x; k < sz; k += ZM_THREADS) {
-    const fsg_tab e = job.tab[2][k];
-    s_tz[k] = make_int2((int)e.f | ((int)e.c << 16), __float_as_int(e.wc));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NK = KG > 0 ? KG * 4 : 1;
+  int tf[NK], tc[NK];
+  float twc[NK], twf[NK];
+  if (KG > 0) {
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+      const fsg_tab e = job.tab[2][128 * (q >> 2) + 4 * lane + (q & 3)];
+      tf[q] = e.f;
+      tc[q] = e.c;
+      twc[q] = e.wc;
+      twf[q] = sub_rn(1.0f, e.wc);
+    }
+  } else {
+    for (int k = threadIdx.x; k < sz; k += ZM_THREADS) {
+      const fsg_tab e = job.tab[2][k];
+      s_tz[k] = make_int2((int)e.f | ((int)e.c << 16), __float_as_int(e.wc));
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   const float* __restrict__ src = job.src;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float inf = __int_as_float(0x7f800000);
   float lo = inf, hi = -inf;
-  float vmax = 1.f, rmax = 1.f, qmin = 0.f, den = 1.f, rden = 1.f;
+  // post 1: v / max (exactly 1 at the maximum).  post 2: ((v / max) - min / max) / (1 - min / max)
+  // folded into one FMA, clamped to [0, 1] (float path: tolerance, not bit parity).
+  float vmax = 1.f, rmax = 1.f, pa = 1.f, pb = 0.f;
   const int post = job.post;
   if (!REDUCE && post > 0) {
     vmax = job.minmax[1];
     rmax = __frcp_rn(vmax);
-    qmin = div_nr(job.minmax[0], vmax, rmax);
-    den = sub_rn(div_nr(vmax, vmax, rmax), qmin);
-    rden = __frcp_rn(den);
+    const float qmin = div_nr(job.minmax[0], vmax, rmax);
+    const float den = sub_rn(div_nr(vmax, vmax, rmax), qmin);
+    const bool flat = den == 0.f;  // constant image: ScaleIntensity returns x * minv = 0
+    pa = flat ? 0.f : __fdiv_rn(rmax, den);
+    pb = flat ? 0.f : -__fdiv_rn(qmin, den);
   }
   const int nrows = sx * sy;
   for (int row = blockIdx.x * ZM_WARPS + warp; row < nrows; row += gridDim.x * ZM_WARPS) {
@@ -66,18 +87,41 @@ __global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_cons
       s_row[K] = blend(ty.wf, a_f, ty.wc, a_c);                               // tmp2
     }
     __syncwarp();
-    float* __restrict__ out = REDUCE ? nullptr : job.dst + (size_t)row * sz;
-    for (int k = lane; k < sz; k += 32) {
-      const int2 e = s_tz[k];
-      const float wc = __int_as_float(e.y), wf = sub_rn(1.0f, wc);
-      float val = blend(wf, s_row[e.x & 0xffff], wc, s_row[e.x >> 16]);
-      if (REDUCE) {
-        lo = fminf(lo, val);
-        hi = fmaxf(hi, val);
-      } else {
-        if (post >= 1) val = div_nr(val, vmax, rmax);
-        if (post >= 2) val = div_nr(sub_rn(val, qmin), den, rden);
-        out[k] = val;
+    if (KG > 0) {
+#pragma unroll
+      for (int m = 0; m < (KG > 0 ? KG : 1); ++m) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = 4 * m + e;
+          v[e] = blend(twf[q], s_row[tf[q]], twc[q], s_row[tc[q]]);
+        }
+        if (REDUCE) {
+          lo = fminf(fminf(lo, v[0]), fminf(fminf(v[1], v[2]), v[3]));
+          hi = fmaxf(fmaxf(hi, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (post == 1) v[e] = div_nr(v[e], vmax, rmax);
+            if (post == 2) v[e] = fminf(fmaxf(__fmaf_rn(v[e], pa, pb), 0.f), 1.f);
+          }
+          __stcs(reinterpret_cast<float4*>(job.dst + (size_t)row * sz + 128 * m + 4 * lane), make_float4(v[0], v[1], v[2], v[3]));
+        }
+      }
+    } else {
+      float* __restrict__ out = REDUCE ? nullptr : job.dst + (size_t)row * sz;
+      for (int k = lane; k < sz; k += 32) {
+        const int2 e = s_tz[k];
+        const float wc = __int_as_float(e.y), wf = sub_rn(1.0f, wc);
+        float val = blend(wf, s_row[e.x & 0xffff], wc, s_row[e.x >> 16]);
+        if (REDUCE) {
+          lo = fminf(lo, val);
+          hi = fmaxf(hi, val);
+        } else {
+          if (post == 1) val = div_nr(val, vmax, rmax);
+          if (post == 2) val = fminf(fmaxf(__fmaf_rn(val, pa, pb), 0.f), 1.f);
+          out[k] = val;
+        }
       }
     }
   }
@@ -135,15 +179,29 @@ static int check_zoom(const fsg_zoom_job* jobs, int njobs, int sx, int sy, int s
   return 0;
 }
 
-template <bool REDUCE>
-static int launch_zoom(const Batch<fsg_zoom_job>& b, int njobs, int sx, int sy, int sz, int max_n2, cudaStream_t s, const char* who) {
-  const size_t smem = ((size_t)2 * sz + (size_t)ZM_WARPS * max_n2) * sizeof(float);
-  FSG_REQUIRE(smem <= 200 * 1024, "%s: rows of %d / %d voxels do not fit in shared memory", who, sz, max_n2);
-  auto k = zoom_rows_kernel<REDUCE>;
+template <bool REDUCE, int KG>
+static void launch_zoom_kg(const Batch<fsg_zoom_job>& b, int njobs, int sx, int sy, int sz, size_t smem, cudaStream_t s) {
+  auto k = zoom_rows_kernel<REDUCE, KG>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t want = ((int64_t)sx * sy + ZM_WARPS - 1) / ZM_WARPS;
   const int cap = 148 * 8;
   k<<<dim3((unsigned)(want < cap ? want : cap), njobs), ZM_THREADS, smem, s>>>(b, sx, sy, sz);
+}
+
+template <bool REDUCE>
+static int launch_zoom(const Batch<fsg_zoom_job>& b, const fsg_zoom_job* jobs, int njobs, int sx, int sy, int sz, int max_n2, cudaStream_t s, const char* who) {
+  const size_t smem = ((size_t)2 * sz + (size_t)ZM_WARPS * max_n2) * sizeof(float);
+  FSG_REQUIRE(smem <= 200 * 1024, "%s: rows of %d / %d voxels do not fit in shared memory", who, sz, max_n2);
+  bool vec = (sz % 128 == 0) && sz <= 512;
+  for (int i = 0; i < njobs && vec && !REDUCE; ++i) vec = (reinterpret_cast<uintptr_t>(jobs[i].dst) & 15) == 0;
+  const int kg = vec ? sz / 128 : 0;
+  switch (kg) {
+    case 1: launch_zoom_kg<REDUCE, 1>(b, njobs, sx, sy, sz, smem, s); break;
+    case 2: launch_zoom_kg<REDUCE, 2>(b, njobs, sx, sy, sz, smem, s); break;
+    case 3: launch_zoom_kg<REDUCE, 3>(b, njobs, sx, sy, sz, smem, s); break;
+    case 4: launch_zoom_kg<REDUCE, 4>(b, njobs, sx, sy, sz, smem, s); break;
+    default: launch_zoom_kg<REDUCE, 0>(b, njobs, sx, sy, sz, smem, s); break;
+  }
   return 0;
 }
 
@@ -158,7 +216,7 @@ extern "C" int fsg_zoom_minmax(const fsg_zoom_job* jobs, int njobs, int sx, int 
   if (int rc = check_zoom(jobs, njobs, sx, sy, sz, false, "fsg_zoom_minmax", &max_n2)) return rc;
   cudaStream_t s = as_stream(stream);
   zoom_mm_init_kernel<<<1, 32, 0, s>>>(b, njobs);
-  if (int rc = launch_zoom<true>(b, njobs, sx, sy, sz, max_n2, s, "fsg_zoom_minmax")) return rc;
+  if (int rc = launch_zoom<true>(b, jobs, njobs, sx, sy, sz, max_n2, s, "fsg_zoom_minmax")) return rc;
   zoom_mm_final_kernel<<<1, 32, 0, s>>>(b, njobs);
   return check_launch("fsg_zoom_minmax");
 }
@@ -168,6 +226,6 @@ extern "C" int fsg_zoom(const fsg_zoom_job* jobs, int njobs, int sx, int sy, int
   if (int rc = fill_batch(b, jobs, njobs)) return rc;
   int max_n2;
   if (int rc = check_zoom(jobs, njobs, sx, sy, sz, true, "fsg_zoom", &max_n2)) return rc;
-  if (int rc = launch_zoom<false>(b, njobs, sx, sy, sz, max_n2, as_stream(stream), "fsg_zoom")) return rc;
+  if (int rc = launch_zoom<false>(b, jobs, njobs, sx, sy, sz, max_n2, as_stream(stream), "fsg_zoom")) return rc;
   return check_launch("fsg_zoom");
 }

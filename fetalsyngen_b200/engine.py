@@ -87,20 +87,45 @@ class SynthEngine:
             self._scratch[key] = t
         return t
 
+    RING_SLOTS, RING_FLOATS = 8, 1 << 18
+
     def upload(self, arrays: list[np.ndarray]) -> list[torch.Tensor]:
-        """One H2D copy for a list of small float32 host arrays; returns device views."""
+        """One H2D copy for a list of small float32 host arrays; returns device views.  Staged
+        through a ring of pinned slots with a matching device ring (no allocation per call)."""
         sizes = [int(a.size) for a in arrays]
-        offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(int)
-        host = torch.empty(int(offs[-1]) or 4, dtype=torch.float32, pin_memory=True)
+        total = sum((s + 3) // 4 * 4 for s in sizes) or 4
+        if total > self.RING_FLOATS:  # oversized request: one-off buffers
+            host = torch.empty(total, dtype=torch.float32, pin_memory=True)
+            dev = torch.empty(total, dtype=torch.float32, device=self.device)
+            ev = None
+        else:
+            if not hasattr(self, "_ring"):
+                self._ring = (torch.empty((self.RING_SLOTS, self.RING_FLOATS), dtype=torch.float32, pin_memory=True),
+                              torch.empty((self.RING_SLOTS, self.RING_FLOATS), dtype=torch.float32, device=self.device),
+                              [None] * self.RING_SLOTS, [0])
+            hring, dring, events, pos = self._ring
+            slot = pos[0] % self.RING_SLOTS
+            pos[0] += 1
+            if events[slot] is not None:
+                events[slot].synchronize()  # the slot's previous copy and its consumers have run
+            host, dev = hring[slot, :total], dring[slot, :total]
+            ev = slot
         hv = host.numpy()
-        for a, o, s in zip(arrays, offs[:-1], sizes):
+        o, views = 0, []
+        for a, s in zip(arrays, sizes):
             hv[o : o + s] = np.asarray(a, dtype=np.float32).reshape(-1)
-        dev = host.to(self.device, non_blocking=True)
-        # keep the pinned staging buffer alive until the copy has run
-        ev = torch.cuda.Event()
-        ev.record()
-        self._pending = [(h, e) for h, e in getattr(self, "_pending", []) if not e.query()] + [(host, ev)]
-        return [dev[o : o + s] for o, s in zip(offs[:-1], sizes)]
+            views.append(dev[o : o + s])
+            o += (s + 3) // 4 * 4
+        dev.copy_(host, non_blocking=True)
+        if ev is not None:
+            # host slot: reusable once this copy has run; device slot: later copies into it are
+            # stream-ordered after the kernels that read it (everything runs on the current stream)
+            e = torch.cuda.Event()
+            e.record()
+            self._ring[2][ev] = e
+        else:
+            self._oversize_keep = (host, dev)
+        return views
 
     # ------------------------------------------------------------------ K1
     def gmm(self, plans, seeds, out: torch.Tensor, labels_out=None):
@@ -161,10 +186,7 @@ class SynthEngine:
                     j.fsmall = small[slots[b]["f"]].data_ptr()
                     j.fs = (C.c_int32 * 3)(*fs)
                     for a in range(3):
-                        t = self.tables.zoom(fs[a], self.shape[a] / fs[a])
-                        if t.numel() // 8 != self.shape[a]:
-                            raise ValueError("control-grid zoom does not reproduce the volume shape")
-                        j.ftab[a] = t.data_ptr()
+                        j.ftab[a] = self.tables.zoom(fs[a], self.shape[a] / fs[a], self.shape[a]).data_ptr()
             if epilogue and p.gamma is not None:
                 j.has_gamma, j.gamma = 1, float(np.float32(p.gamma))
             if "b" in slots[b]:
@@ -172,10 +194,7 @@ class SynthEngine:
                 j.bf_low = small[slots[b]["b"]].data_ptr()
                 j.bs = (C.c_int32 * 3)(*bs)
                 for a in range(3):
-                    t = self.tables.zoom(bs[a], self.shape[a] / bs[a])
-                    if t.numel() // 8 != self.shape[a]:
-                        raise ValueError("bias-grid zoom does not reproduce the volume shape")
-                    j.btab[a] = t.data_ptr()
+                    j.btab[a] = self.tables.zoom(bs[a], self.shape[a] / bs[a], self.shape[a]).data_ptr()
         return jobs, keep
 
     def warp(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True):
@@ -329,9 +348,7 @@ class SynthEngine:
             j = jobs[b]
             n = src_shapes[b]
             for a in range(3):
-                if zoom_size(n[a], factors_list[b][a]) != self.shape[a]:
-                    raise ValueError(f"zoom of extent {n[a]} by {factors_list[b][a]} does not give {self.shape[a]}")
-                j.tab[a] = self.tables.zoom(n[a], factors_list[b][a]).data_ptr()
+                j.tab[a] = self.tables.zoom(n[a], factors_list[b][a], self.shape[a]).data_ptr()
             j.n = (C.c_int32 * 3)(*n)
             j.src, j.dst = src_list[b].data_ptr(), dst[b].data_ptr()
             j.minmax, j.post = mm[b].data_ptr(), post

@@ -104,31 +104,44 @@ def make_affine_matrix(rot, sh, s) -> np.ndarray:
 
 
 class DeviceTables:
-    """Per-device cache of uploaded tables / tap arrays."""
+    """Per-device cache of uploaded tables / tap arrays (built lazily, keyed by their integer
+    extents so a continuous random spacing still hits the cache)."""
 
     def __init__(self, device):
         self.device = torch.device(device)
         self._cache: dict = {}
 
-    def _put(self, key, arr: np.ndarray) -> torch.Tensor:
+    def _put(self, key, make) -> torch.Tensor:
         t = self._cache.get(key)
         if t is None:
+            arr = make()
             t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy()).to(self.device)
-            if len(self._cache) > 4096:
+            if len(self._cache) > 8192:
                 self._cache.clear()
             self._cache[key] = t
         return t
 
-    def zoom(self, n_in: int, factor: float) -> torch.Tensor:
-        return self._put(("zoom", n_in, float(factor)), zoom_table(n_in, factor))
+    def zoom(self, n_in: int, factor: float, expect: int | None = None) -> torch.Tensor:
+        """Table of ``myzoom_torch`` along one axis; ``expect`` (checked when the table is built)
+        is the output extent the caller relies on."""
+        factor = float(factor)
+
+        def make():
+            if expect is not None and zoom_size(n_in, factor) != expect:
+                raise ValueError(f"zoom of extent {n_in} by {factor} does not give {expect}")
+            return zoom_table(n_in, factor)
+
+        return self._put(("zoom", n_in, factor, expect), make)
 
     def resample(self, n_in: int, res_in: float, spacing: float):
-        key = ("resample", n_in, resample_size(n_in, res_in, spacing))
-        if key not in self._cache:
+        n_out = resample_size(n_in, res_in, spacing)
+        key = ("resample", n_in, n_out)  # the positions only depend on the factor n_out / n_in
+        t = self._cache.get(key)
+        if t is None:
             tab, factor = resample_table(n_in, res_in, spacing)
-            self._put(key, tab)
+            t = self._put(key, lambda: tab)
             self._cache[key + ("factor",)] = factor
-        return self._cache[key], self._cache[key + ("factor",)]
+        return t, self._cache[key + ("factor",)]
 
     def taps(self, sigma: float) -> torch.Tensor:
-        return self._put(("taps", float(sigma)), gaussian_taps(sigma))
+        return self._put(("taps", float(sigma)), lambda: gaussian_taps(sigma))
