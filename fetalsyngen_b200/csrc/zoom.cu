@@ -28,7 +28,7 @@ __device__ __forceinline__ float div_nr(float a, float b, float rb) {
 // all rows, so its z-table entries live in registers and the stores are 16-byte vectors.
 // KG == 0: generic extents, z table read from shared memory per voxel.
 template <bool REDUCE, int KG>
-__global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int sx, int sy, int sz) {
+__global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int sx, int sy, int sz) {
   const fsg_zoom_job& job = batch.j[blockIdx.y];
   const int n1 = job.n[1], n2 = job.n[2];
   extern __shared__ float s_zoom[];
@@ -37,14 +37,13 @@ __global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_cons
   float* s_row = s_zoom + 2 * sz + (threadIdx.x >> 5) * n2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NK = KG > 0 ? KG * 4 : 1;
-  int tf[NK], tc[NK];
+  int tfc[NK];  // f | c << 16
   float twc[NK], twf[NK];
   if (KG > 0) {
 #pragma unroll
     for (int q = 0; q < NK; ++q) {
       const fsg_tab e = job.tab[2][128 * (q >> 2) + 4 * lane + (q & 3)];
-      tf[q] = e.f;
-      tc[q] = e.c;
+      tfc[q] = (int)e.f | ((int)e.c << 16);
       twc[q] = e.wc;
       twf[q] = sub_rn(1.0f, e.wc);
     }
@@ -81,10 +80,25 @@ __global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_cons
     const float* pfc = src + ((size_t)tx.f * n1 + ty.c) * n2;
     const float* pcc = src + ((size_t)tx.c * n1 + ty.c) * n2;
     __syncwarp();  // previous row's readers are done
-    for (int K = lane; K < n2; K += 32) {
-      const float a_f = blend(tx.wf, __ldg(pff + K), tx.wc, __ldg(pcf + K));  // tmp1[y=f]
-      const float a_c = blend(tx.wf, __ldg(pfc + K), tx.wc, __ldg(pcc + K));  // tmp1[y=c]
-      s_row[K] = blend(ty.wf, a_f, ty.wc, a_c);                               // tmp2
+    for (int K0 = lane; K0 < n2; K0 += 128) {
+      // four K positions per lane with all 16 loads issued before the first blend
+      float vff[4], vcf[4], vfc[4], vcc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int K = K0 + 32 * u;
+        const bool in = K < n2;
+        vff[u] = in ? __ldg(pff + K) : 0.f;
+        vcf[u] = in ? __ldg(pcf + K) : 0.f;
+        vfc[u] = in ? __ldg(pfc + K) : 0.f;
+        vcc[u] = in ? __ldg(pcc + K) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int K = K0 + 32 * u;
+        const float a_f = blend(tx.wf, vff[u], tx.wc, vcf[u]);  // tmp1[y=f]
+        const float a_c = blend(tx.wf, vfc[u], tx.wc, vcc[u]);  // tmp1[y=c]
+        if (K < n2) s_row[K] = blend(ty.wf, a_f, ty.wc, a_c);   // tmp2
+      }
     }
     __syncwarp();
     if (KG > 0) {
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(ZM_THREADS) zoom_rows_kernel(const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int q = 4 * m + e;
-          v[e] = blend(twf[q], s_row[tf[q]], twc[q], s_row[tc[q]]);
+          v[e] = blend(twf[q], s_row[tfc[q] & 0xffff], twc[q], s_row[tfc[q] >> 16]);
         }
         if (REDUCE) {
           lo = fminf(fminf(lo, v[0]), fminf(fminf(v[1], v[2]), v[3]));
