@@ -46,7 +46,7 @@ class ResampleJob(C.Structure):
 
 
 class NoiseJob(C.Structure):
-    _fields_ = [("src", _vp), ("dst", _vp), ("noise", _vp), ("rng", Rng), ("noise_std", _f32), ("_pad", _i32)]
+    _fields_ = [("src", _vp), ("dst", _vp), ("noise", _vp), ("rng", Rng), ("noise_std", _f32), ("flags", _i32)]
 
 
 class ZoomJob(C.Structure):
@@ -62,11 +62,20 @@ class SepconvJob(C.Structure):
                 ("noise_std", _f32), ("has_noise", _i32)]
 
 
+class SampleJob(C.Structure):
+    _fields_ = [("labels", _vp), ("labels2", _vp), ("centers_out", _vp), ("count_out", _vp), ("workspace", _vp), ("workspace_bytes", _i64), ("rng", Rng),
+                ("prior_centers", (_f32 * 3) * 4), ("prior_sigmas", (_f32 * 3) * 4), ("match", _i32), ("nprior", _i32), ("k", _i32), ("_pad", _i32)]
+
+
+class PerlinOctave(C.Structure):
+    _fields_ = [("grad", _vp), ("lin", _vp * 3), ("res", _i32 * 3), ("amp", _f32)]
+
+
 class SepComposeJob(C.Structure):
     _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32)]
 
 
-_STRUCTS = {"fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
+_STRUCTS = {"fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
@@ -90,6 +99,18 @@ SIGNATURES = {
     "fsg_f32_to_u8": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fsg_u8_to_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fsg_u8_to_i64": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fsg_mog": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "fsg_sample_voxels": (C.c_int, [C.POINTER(SampleJob), C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_perlin": (C.c_int, [C.POINTER(PerlinOctave), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "fsg_struct_blend": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _vp]),
+    "fsg_morph_box": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_morph_dist": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "fsg_morph_thresh": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp]),
+    "fsg_morph_ring": (C.c_int, [_vp, _vp, _vp, Rng, _f32, _vp, _i64, _vp]),
+    "fsg_morph_count_merge": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _vp]),
+    "fsg_boundary_select": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
+    "fsg_mask_mul": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "fsg_label_mask": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),
     "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
 }
 

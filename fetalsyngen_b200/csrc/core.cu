@@ -113,6 +113,8 @@ int fsg_sizeof(const char* name) {
   FSG_SZ(fsg_sepaxis)
   FSG_SZ(fsg_sepconv_job)
   FSG_SZ(fsg_sepcompose_job)
+  FSG_SZ(fsg_sample_job)
+  FSG_SZ(fsg_perlin_octave)
 #undef FSG_SZ
   return -1;
 }

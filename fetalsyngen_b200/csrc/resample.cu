@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(RS_THREADS) noise_kernel(const __grid_constant
     }
     for (int e = 0; e < 4 && g * 4 + e < n; ++e) {
       const float v = add_rn(job.src[g * 4 + e], mul_rn(job.noise_std, nz[e]));
-      job.dst[g * 4 + e] = v < 0.f ? 0.f : v;
+      job.dst[g * 4 + e] = (v < 0.f && !(job.flags & 1)) ? 0.f : v;
     }
   }
 }

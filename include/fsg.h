@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FSG_VERSION 101
+#define FSG_VERSION 102
 #define FSG_MAX_JOBS 16
 #define FSG_MAX_TAPS 127
 
@@ -179,7 +179,7 @@ typedef struct fsg_noise_job {
   const float* noise;
   fsg_rng rng;
   float noise_std;
-  int32_t _pad;
+  int32_t flags; /* bit 0: do not clamp at 0 (multi-scale noise accumulation of StructNoise) */
 } fsg_noise_job;
 int fsg_add_noise(const fsg_noise_job* jobs_host, int njobs, int64_t nvox, void* stream);
 
@@ -208,6 +208,76 @@ int fsg_scale_intensity(const float* x, float* out, int64_t n, const float* minm
 int fsg_f32_to_u8(const float* x, uint8_t* out, int64_t n, void* stream);
 int fsg_u8_to_f32(const uint8_t* x, float* out, int64_t n, void* stream);
 int fsg_u8_to_i64(const uint8_t* x, int64_t* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5 — SR-artifact building blocks (generator/augmentation/artifacts.py, generator/artifacts/utils.py).
+ * Single-volume calls (the artifacts run per sample after the batched base pipeline). */
+
+/* Mixture of anisotropic Gaussians clamp(sum_k exp(-d_k^2/2), 0, 1) (mog_3d_tensor,
+ * artifacts/utils.py:125-160).  centers/sigmas are [n][3] device arrays in AXIS order (axis 0,
+ * 1, 2): the host applies the reference's x<->last-axis unpacking.  out (optional) receives the
+ * weight g; if dst is given the BlurCortex blend dst = a*(1-g) + b*g is fused
+ * (augmentation/artifacts.py:124-126). */
+int fsg_mog(const float* centers, const float* sigmas, int n, int sx, int sy, int sz, float* out, const float* a, const float* b, float* dst, void* stream);
+
+/* Weighted sampling WITHOUT replacement of k voxel centres among the voxels selected by a label
+ * predicate (labels == match; match < 0: labels > 0; labels2 != NULL: labels2 > 0 && labels == 0),
+ * weights = a small MoG prior (nprior <= 4, axis order) or uniform.  Same distribution as
+ * torch.multinomial(p, k) / randperm(n)[:k] (artifacts.py:99-104, 558-560): exponential-race keys
+ * -ln(u)/w from Philox, the k smallest win.  centers_out: [k][3] floats (axis order), count_out:
+ * number actually drawn (min(k, candidates)).  workspace: >= 64 + 2048*8 bytes of device memory. */
+typedef struct fsg_sample_job {
+  const uint8_t* labels;
+  const uint8_t* labels2;
+  float* centers_out;
+  int32_t* count_out;
+  void* workspace;
+  int64_t workspace_bytes;
+  fsg_rng rng;
+  float prior_centers[4][3];
+  float prior_sigmas[4][3];
+  int32_t match;
+  int32_t nprior;
+  int32_t k;
+  int32_t _pad; /* != 0: write centres transposed (axis2, axis1, axis0), the order mog_3d_tensor's
+                   (x0, y0, z0) unpacking gives to voxel indices (artifacts/utils.py:137-156) */
+} fsg_sample_job;
+int fsg_sample_voxels(const fsg_sample_job* job_host, int sx, int sy, int sz, void* stream);
+
+/* Fractal Perlin noise sum_o amp_o * perlin_o (generate_fractal_noise_3d / generate_perlin_noise_3d,
+ * artifacts/utils.py:224-388) + its global min/max (minmax: [2] device floats).  Per octave the
+ * host supplies the unit gradient lattice [(r0+1)][(r1+1)][(r2+1)][3] (tile wrap applied) and the
+ * per-axis lattice coordinates of every voxel (torch.linspace(0, res, S)). */
+typedef struct fsg_perlin_octave {
+  const float* grad;
+  const float* lin[3];
+  int32_t res[3];
+  float amp;
+} fsg_perlin_octave;
+int fsg_perlin(const fsg_perlin_octave* octaves_host, int noct, int sx, int sy, int sz, float* out, float* minmax, void* stream);
+
+/* StructNoise merge (artifacts.py:322-339).  scal: 6 device floats = min/max of the multi-scale
+ * noise, min/max of the image, min/max of the raw fractal noise. */
+int fsg_struct_blend(const float* x, const uint8_t* seg, const float* lr, const float* perlin, const float* scal, float noise_std, float increase, float* out, int64_t n,
+                     void* stream);
+
+/* Exact binary morphology on uint8 volumes (dilate/erode/apply_kernel, artifacts/utils.py:163-210;
+ * build_halo / generate_fuzzy_boundaries / dilate_stack, artifacts.py:484-602).
+ * fsg_morph_box: k^3 box, op 0 = dilation, 1 = erosion (zero padded), 2 = count (k^3 <= 255).
+ * fsg_morph_dist: metric 0 = squared Euclidean distance to the mask (ball(r) dilation is dist <= r^2),
+ *                 metric 1 = L1 distance (k 6-neighbour dilations are dist <= k); window r per axis.
+ * fsg_morph_ring: (dilated && !mask), sub-sampled by an injected keep-mask or Bernoulli(p) (Philox).
+ * fsg_morph_count_merge: out = mask || count > thr.
+ * fsg_boundary_select: final mask and image of SimulatedBoundaries (artifacts.py:563-604). */
+int fsg_morph_box(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int k, int op, int sx, int sy, int sz, void* stream);
+int fsg_morph_dist(const uint8_t* mask, uint16_t* dist_out, uint16_t* tmp, int r, int metric, int sx, int sy, int sz, void* stream);
+int fsg_morph_thresh(const uint16_t* dist, uint8_t* out, int thr, int64_t n, void* stream);
+int fsg_morph_ring(const uint8_t* dilated, const uint8_t* mask, const uint8_t* keep, fsg_rng rng, float p, uint8_t* out, int64_t n, void* stream);
+int fsg_morph_count_merge(const uint8_t* count, const uint8_t* mask, int thr, uint8_t* out, int64_t n, void* stream);
+int fsg_boundary_select(const float* x, const uint8_t* halo, const uint8_t* modif, const uint16_t* l1, const float* mog, int len, float* out, uint8_t* mask_out, int64_t n,
+                        void* stream);
+int fsg_mask_mul(const float* x, const uint8_t* mask, float* out, int64_t n, void* stream);
+int fsg_label_mask(const uint8_t* labels, int match, uint8_t* out, int64_t n, void* stream);
 
 /* RNG self-test: fills out[n] with Philox standard normals exactly as the kernels draw them;
  * raw != 0 writes the raw 32-bit words instead (for the Random123 known-answer test). */

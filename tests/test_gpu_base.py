@@ -17,7 +17,7 @@ if torch.cuda.is_available():
 
 def test_library_loaded_and_abi():
     lib = _lib.load(build_if_missing=False)
-    assert lib.fsg_version() == 101
+    assert lib.fsg_version() == 102
 
 
 def test_philox_raw_matches_published_algorithm():
