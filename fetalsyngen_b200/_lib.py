@@ -111,6 +111,9 @@ SIGNATURES = {
     "fsg_boundary_select": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
     "fsg_mask_mul": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "fsg_label_mask": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),
+    "fsg_slice_acq_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, _f32, _vp] + [C.c_int] * 6 + [_f32, _vp]),
+    "fsg_slice_acq_adjoint": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _f32, _vp, _vp, _vp] + [C.c_int] * 6 + [_f32, C.c_int, _vp]),
+    "fsg_recon_merge": (C.c_int, [_vp, _vp, _vp, _vp, _f32, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
 }
 

@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libfsg.so"
-SOURCES = ["core.cu", "gmm.cu", "warp.cu", "blur.cu", "resample.cu", "sepconv.cu", "zoom.cu", "artifacts.cu"]
+SOURCES = ["core.cu", "gmm.cu", "warp.cu", "blur.cu", "resample.cu", "sepconv.cu", "zoom.cu", "artifacts.cu", "motion.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -1,0 +1,270 @@
+// K5-motion — slice acquisition (forward) and PSF reconstruction (adjoint) of SimulateMotion.
+//
+// Replaces the reference's JIT-built extension for the two call sites of the generation path
+// (svort/slice_acquisition/slice_acq_cuda_kernel.cu:17-171 forward with interp_psf = false,
+// called by Scanner.scan, simulate_reco.py:386-407; :472-693 adjoint with interp_psf = true and
+// equalize, called by PSFreconstruction, simulate_reco.py:38-54).  The backward kernels are not
+// on this path (nothing is differentiated).
+//
+// Geometry (identical for both): a slice pixel (ix, iy) of slice `in` sits at
+//   c = R * ((ix-(w-1)/2)*res + tx, (iy-(h-1)/2)*res + ty, tz) + (vol centre)
+// and every PSF tap p adds R * p.  Volume axes: x = fastest (W), y (H), z (D).
+//
+// forward : slice = sum_p psf_p * trilinear(vol, c + R p) / sum_p psf_p * (in-bounds weight)
+//           - only the non-zero taps are visited (compact list built on the host),
+//           - a block covers a 16x16 tile of ONE slice, so R p is staged once per block in smem,
+//           - tiles whose centre +- PSF radius misses the volume exit immediately.
+// adjoint : two passes over the taps per pixel (normalisation weight, then scatter of
+//           psf/weight * s to the nearest voxel with red.global.add) + equalisation vol /= weight.
+//           Summation order of the atomics is not deterministic (same as the reference).
+#include "common.cuh"
+
+namespace fsg {
+
+constexpr int ACQ_TILE = 16;
+constexpr int ACQ_MAX_TAPS = 4096;
+
+struct SliceGeom {
+  float r11, r12, r13, r21, r22, r23, r31, r32, r33;
+  float xc, yc, zc;
+};
+
+// centre of pixel (ix, iy): double intermediate like the reference's "(w - 1) / 2." expressions
+__device__ __forceinline__ SliceGeom slice_geom(const float* __restrict__ t, int ix, int iy, int h, int w, int D, int H, int W, float res) {
+  SliceGeom g;
+  g.r11 = t[0]; g.r12 = t[1]; g.r13 = t[2];
+  g.r21 = t[4]; g.r22 = t[5]; g.r23 = t[6];
+  g.r31 = t[8]; g.r32 = t[9]; g.r33 = t[10];
+  const float _x = (float)(((double)ix - (w - 1) / 2.) * (double)res + (double)t[3]);
+  const float _y = (float)(((double)iy - (h - 1) / 2.) * (double)res + (double)t[7]);
+  const float _z = t[11];
+  float xc = g.r11 * _x + g.r12 * _y + g.r13 * _z;
+  float yc = g.r21 * _x + g.r22 * _y + g.r23 * _z;
+  float zc = g.r31 * _x + g.r32 * _y + g.r33 * _z;
+  g.xc = (float)((double)xc + (W - 1) / 2.);
+  g.yc = (float)((double)yc + (H - 1) / 2.);
+  g.zc = (float)((double)zc + (D - 1) / 2.);
+  return g;
+}
+
+// ---------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const float* __restrict__ transforms, const float* __restrict__ vol, const float4* __restrict__ taps, int ntaps,
+                                                                        float radius, float* __restrict__ slices, int h, int w, int D, int H, int W, float res) {
+  extern __shared__ float4 s_tap[];  // R * tap offset (x, y, z) and weight
+  const int in = blockIdx.z;
+  const float* t = transforms + in * 12;
+  for (int p = threadIdx.y * ACQ_TILE + threadIdx.x; p < ntaps; p += ACQ_TILE * ACQ_TILE) {
+    const float4 q = taps[p];
+    float x = t[0] * q.x;
+    x = x + t[1] * q.y;
+    x = x + t[2] * q.z;
+    float y = t[4] * q.x;
+    y = y + t[5] * q.y;
+    y = y + t[6] * q.z;
+    float z = t[8] * q.x;
+    z = z + t[9] * q.y;
+    z = z + t[10] * q.z;
+    s_tap[p] = make_float4(x, y, z, q.w);
+  }
+  __syncthreads();
+  const int ix = blockIdx.x * ACQ_TILE + threadIdx.x, iy = blockIdx.y * ACQ_TILE + threadIdx.y;
+  if (ix >= w || iy >= h) return;
+  const SliceGeom g = slice_geom(t, ix, iy, h, w, D, H, W, res);
+  // no tap of this pixel can land inside [0, W-1) x [0, H-1) x [0, D-1): the slice keeps its zero
+  if (g.xc + radius < 0.f || g.yc + radius < 0.f || g.zc + radius < 0.f || g.xc - radius >= (float)(W - 1) || g.yc - radius >= (float)(H - 1) || g.zc - radius >= (float)(D - 1)) return;
+  const int Sy = W, Sz = H * W;
+  const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
+  float val = 0.f, weight = 0.f;
+  for (int p = 0; p < ntaps; ++p) {
+    const float4 q = s_tap[p];
+    const float x = g.xc + q.x, y = g.yc + q.y, z = g.zc + q.z;
+    if (x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz) continue;
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    const float wx = x - fx, wy = y - fy, wz = z - fz;
+    const float* v = vol + ((int)fz * Sz + (int)fy * Sy + (int)fx);
+    const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
+    const float p000 = ux * uy * uz * q.w, p100 = wx * uy * uz * q.w, p010 = ux * wy * uz * q.w, p001 = ux * uy * wz * q.w;
+    const float p110 = wx * wy * uz * q.w, p101 = wx * uy * wz * q.w, p011 = ux * wy * wz * q.w, p111 = wx * wy * wz * q.w;
+    val += p000 * __ldg(v);
+    weight += p000;
+    val += p100 * __ldg(v + 1);
+    weight += p100;
+    val += p010 * __ldg(v + Sy);
+    weight += p010;
+    val += p001 * __ldg(v + Sz);
+    weight += p001;
+    val += p110 * __ldg(v + 1 + Sy);
+    weight += p110;
+    val += p101 * __ldg(v + 1 + Sz);
+    weight += p101;
+    val += p011 * __ldg(v + Sy + Sz);
+    weight += p011;
+    val += p111 * __ldg(v + Sy + Sz + 1);
+    weight += p111;
+  }
+  if (weight > 0.f) slices[((size_t)in * h + iy) * w + ix] = __fdiv_rn(val, weight);
+}
+
+// ---------------------------------------------------------------------------------- adjoint
+// interpolated PSF value at the voxel nearest to (x, y, z), or -1 when it falls off the PSF grid
+__device__ __forceinline__ float psf_at_voxel(const SliceGeom& g, const float* __restrict__ psf, int dp, int hp, int wp, float xr, float yr, float zr) {
+  const float dx = xr - g.xc, dy = yr - g.yc, dz = zr - g.zc;
+  const float xp = (float)((double)(g.r11 * dx + g.r21 * dy + g.r31 * dz) + (wp - 1) / 2.);
+  const float yp = (float)((double)(g.r12 * dx + g.r22 * dy + g.r32 * dz) + (hp - 1) / 2.);
+  const float zp = (float)((double)(g.r13 * dx + g.r23 * dy + g.r33 * dz) + (dp - 1) / 2.);
+  if (xp < 0.f || yp < 0.f || zp < 0.f || xp >= (float)(wp - 1) || yp >= (float)(hp - 1) || zp >= (float)(dp - 1)) return -1.f;
+  const float fx = floorf(xp), fy = floorf(yp), fz = floorf(zp);
+  const float wx = xp - fx, wy = yp - fy, wz = zp - fz;
+  const float* q = psf + ((int)fz * wp * hp + (int)fy * wp + (int)fx);
+  float v = 0.f;
+  v += (1 - wx) * (1 - wy) * (1 - wz) * q[0];
+  v += wx * (1 - wy) * (1 - wz) * q[1];
+  v += (1 - wx) * wy * (1 - wz) * q[wp];
+  v += (1 - wx) * (1 - wy) * wz * q[wp * hp];
+  v += wx * wy * (1 - wz) * q[1 + wp];
+  v += wx * (1 - wy) * wz * q[1 + wp * hp];
+  v += (1 - wx) * wy * wz * q[wp + wp * hp];
+  v += wx * wy * wz * q[wp + wp * hp + 1];
+  return v;
+}
+
+__global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const float* __restrict__ transforms, const float* __restrict__ psf, int dp, int hp, int wp,
+                                                                        const float4* __restrict__ taps, int ntaps, float radius, const float* __restrict__ slices,
+                                                                        float* __restrict__ vol, float* __restrict__ vol_weight, int h, int w, int D, int H, int W, float res) {
+  extern __shared__ float4 s_tap[];
+  const int in = blockIdx.z;
+  const float* t = transforms + in * 12;
+  for (int p = threadIdx.y * ACQ_TILE + threadIdx.x; p < ntaps; p += ACQ_TILE * ACQ_TILE) {
+    const float4 q = taps[p];
+    float x = t[0] * q.x;
+    x = x + t[1] * q.y;
+    x = x + t[2] * q.z;
+    float y = t[4] * q.x;
+    y = y + t[5] * q.y;
+    y = y + t[6] * q.z;
+    float z = t[8] * q.x;
+    z = z + t[9] * q.y;
+    z = z + t[10] * q.z;
+    s_tap[p] = make_float4(x, y, z, q.w);
+  }
+  __syncthreads();
+  const int ix = blockIdx.x * ACQ_TILE + threadIdx.x, iy = blockIdx.y * ACQ_TILE + threadIdx.y;
+  if (ix >= w || iy >= h) return;
+  const SliceGeom g = slice_geom(t, ix, iy, h, w, D, H, W, res);
+  if (g.xc + radius < 0.f || g.yc + radius < 0.f || g.zc + radius < 0.f || g.xc - radius >= (float)(W - 1) || g.yc - radius >= (float)(H - 1) || g.zc - radius >= (float)(D - 1)) return;
+  const float s = slices[((size_t)in * h + iy) * w + ix];
+  const int Sy = W, Sz = H * W;
+  const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
+  float weight = 0.f;
+  for (int p = 0; p < ntaps; ++p) {
+    const float4 q = s_tap[p];
+    const float x = g.xc + q.x, y = g.yc + q.y, z = g.zc + q.z;
+    if (x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz) continue;
+    const float pv = psf_at_voxel(g, psf, dp, hp, wp, roundf(x), roundf(y), roundf(z));
+    if (pv >= 0.f) weight += pv;
+  }
+  if (weight < 0.5f) return;  // border
+  for (int p = 0; p < ntaps; ++p) {
+    const float4 q = s_tap[p];
+    const float x = g.xc + q.x, y = g.yc + q.y, z = g.zc + q.z;
+    if (x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz) continue;
+    const float xr = roundf(x), yr = roundf(y), zr = roundf(z);
+    float pv = psf_at_voxel(g, psf, dp, hp, wp, xr, yr, zr);
+    if (pv < 0.f) continue;
+    pv = __fdiv_rn(pv, weight);
+    const int iv = (int)zr * Sz + (int)yr * Sy + (int)xr;
+    atomicAdd(vol + iv, pv * s);
+    if (vol_weight) atomicAdd(vol_weight + iv, pv);
+  }
+}
+
+__global__ void __launch_bounds__(256) equalize_kernel(float* __restrict__ vol, const float* __restrict__ wgt, unsigned n) {
+  for (unsigned v = blockIdx.x * 256 + threadIdx.x; v < n; v += gridDim.x * 256) {
+    const float wv = wgt[v];
+    if (wv > 0.f) vol[v] = __fdiv_rn(vol[v], wv);
+  }
+}
+
+// 3^3 mean with zero padding (PSFReconstructor.smooth_volume, simulate_reco.py:584-595) followed by
+// the merge with the clean volume: out = wgt * rec + (1 - wgt) * gt (merge_volumes, :692-709),
+// wgt = clamp((perlin + increase - pmin) / (pmax - pmin), 0, 1) or a ready MoG weight.
+__global__ void __launch_bounds__(256) recon_merge_kernel(const float* __restrict__ rec, const float* __restrict__ gt, const float* __restrict__ wraw, const float* __restrict__ mm,
+                                                          float increase, int smooth, int D, int H, int W, float* __restrict__ out) {
+  const unsigned n = (unsigned)D * H * W;
+  const float pmin = mm ? mm[0] : 0.f, prange = mm ? mm[1] - mm[0] : 1.f;
+  for (unsigned v = blockIdx.x * 256 + threadIdx.x; v < n; v += gridDim.x * 256) {
+    float r = rec[v];
+    if (smooth) {
+      const int x = (int)(v % (unsigned)W), y = (int)((v / (unsigned)W) % (unsigned)H), z = (int)(v / ((unsigned)W * H));
+      float acc = 0.f;
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx, yy = y + dy, zz = z + dz;
+            if (xx < 0 || yy < 0 || zz < 0 || xx >= W || yy >= H || zz >= D) continue;
+            acc += rec[(zz * H + yy) * W + xx] * (1.0f / 27.0f);
+          }
+      r = acc;
+    }
+    float wv = 0.f;
+    if (wraw) wv = fminf(fmaxf(__fdividef(wraw[v] + increase - pmin, prange), 0.f), 1.f);
+    out[v] = wraw ? wv * r + (1.f - wv) * gt[v] : r;
+  }
+}
+
+}  // namespace fsg
+
+using namespace fsg;
+
+static int check_acq(const char* who, int ntaps, int n, int h, int w, int D, int H, int W) {
+  FSG_REQUIRE(n >= 1 && n <= 65535 && h >= 1 && w >= 1, "%s: bad slice stack shape", who);
+  FSG_REQUIRE(D >= 2 && H >= 2 && W >= 2 && (int64_t)D * H * W < ((int64_t)1 << 31), "%s: bad volume shape", who);
+  FSG_REQUIRE(ntaps >= 1 && ntaps <= ACQ_MAX_TAPS, "%s: ntaps=%d outside [1,%d]", who, ntaps, ACQ_MAX_TAPS);
+  return 0;
+}
+
+extern "C" int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
+                                     float res_slice, void* stream) {
+  if (int rc = check_acq("fsg_slice_acq_forward", ntaps, n, h, w, D, H, W)) return rc;
+  FSG_REQUIRE(transforms && vol && taps && slices, "fsg_slice_acq_forward: NULL pointer");
+  FSG_REQUIRE((reinterpret_cast<uintptr_t>(taps) & 15) == 0, "fsg_slice_acq_forward: taps must be 16-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(slices, 0, sizeof(float) * (size_t)n * h * w, s);
+  dim3 grid((w + ACQ_TILE - 1) / ACQ_TILE, (h + ACQ_TILE - 1) / ACQ_TILE, n);
+  const size_t smem = sizeof(float4) * ntaps;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(slice_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  slice_fwd_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, vol, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, h, w, D, H, W, res_slice);
+  return check_launch("fsg_slice_acq_forward");
+}
+
+extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices, float* vol,
+                                     float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream) {
+  if (int rc = check_acq("fsg_slice_acq_adjoint", ntaps, n, h, w, D, H, W)) return rc;
+  FSG_REQUIRE(transforms && psf && taps && slices && vol, "fsg_slice_acq_adjoint: NULL pointer");
+  FSG_REQUIRE(!equalize || vol_weight, "fsg_slice_acq_adjoint: equalize needs vol_weight");
+  FSG_REQUIRE(dp >= 2 && hp >= 2 && wp >= 2, "fsg_slice_acq_adjoint: PSF must be at least 2 voxels wide per axis");
+  FSG_REQUIRE((reinterpret_cast<uintptr_t>(taps) & 15) == 0, "fsg_slice_acq_adjoint: taps must be 16-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  const size_t nv = (size_t)D * H * W;
+  cudaMemsetAsync(vol, 0, sizeof(float) * nv, s);
+  if (vol_weight) cudaMemsetAsync(vol_weight, 0, sizeof(float) * nv, s);
+  dim3 grid((w + ACQ_TILE - 1) / ACQ_TILE, (h + ACQ_TILE - 1) / ACQ_TILE, n);
+  const size_t smem = sizeof(float4) * ntaps;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  slice_adj_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, vol, vol_weight, h, w, D, H, W,
+                                                               res_slice);
+  if (equalize) {
+    const size_t want = (nv + 255) / 256;
+    equalize_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(vol, vol_weight, (unsigned)nv);
+  }
+  return check_launch("fsg_slice_acq_adjoint");
+}
+
+extern "C" int fsg_recon_merge(const float* rec, const float* gt, const float* weight_raw, const float* minmax, float increase, int smooth, int D, int H, int W, float* out,
+                               void* stream) {
+  FSG_REQUIRE(rec && out && rec != out && (!weight_raw || gt), "fsg_recon_merge: bad pointers");
+  FSG_REQUIRE(D >= 1 && H >= 1 && W >= 1 && (int64_t)D * H * W < ((int64_t)1 << 31), "fsg_recon_merge: bad shape");
+  const size_t want = ((size_t)D * H * W + 255) / 256;
+  recon_merge_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, as_stream(stream)>>>(rec, gt, weight_raw, minmax, increase, smooth, D, H, W, out);
+  return check_launch("fsg_recon_merge");
+}

@@ -279,6 +279,26 @@ int fsg_boundary_select(const float* x, const uint8_t* halo, const uint8_t* modi
 int fsg_mask_mul(const float* x, const uint8_t* mask, float* out, int64_t n, void* stream);
 int fsg_label_mask(const uint8_t* labels, int match, uint8_t* out, int64_t n, void* stream);
 
+/* K5-motion — SimulateMotion (artifacts.py:345-425): slice acquisition and PSF reconstruction.
+ * Replace the reference's pybind11 module slice_acq_cuda (slice_acq_cuda.cpp:156-161) for the two
+ * modes the generator uses:
+ *   forward (slice_acq_cuda_kernel.cu:17-171) with interp_psf = false, no masks, no weights
+ *     — slice_acq_cuda.forward(transforms, vol, [], [], psf, (h, w), res_slice, false, false);
+ *   adjoint (:472-693) with interp_psf = true, equalize = true, no masks
+ *     — slice_acq_cuda.adjoint_forward(transforms, psf, slices, [], [], (D,H,W), res_slice, true, true).
+ * transforms: [n][3][4] row-major device floats.  vol: [D][H][W] (W fastest).  taps: [ntaps][4]
+ * device floats = the NON-ZERO PSF entries in the reference's loop order as (ix_p, iy_p, iz_p, value),
+ * 16-byte aligned; radius >= max |tap offset| (pixels farther than that from the volume are skipped).
+ * slices: [n][h][w].  fsg_slice_acq_adjoint zero-fills vol / vol_weight itself. */
+int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
+                          float res_slice, void* stream);
+int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices, float* vol,
+                          float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream);
+/* Optional 3^3 mean (smooth_volume, simulate_reco.py:584-595) + merge with the clean volume
+ * out = w*rec + (1-w)*gt (merge_volumes, :692-709); w = clamp((weight_raw + increase - min)/(max - min), 0, 1)
+ * with minmax = [2] device floats (NULL: weight_raw is used as is); weight_raw NULL: no merge. */
+int fsg_recon_merge(const float* rec, const float* gt, const float* weight_raw, const float* minmax, float increase, int smooth, int D, int H, int W, float* out, void* stream);
+
 /* RNG self-test: fills out[n] with Philox standard normals exactly as the kernels draw them;
  * raw != 0 writes the raw 32-bit words instead (for the Random123 known-answer test). */
 int fsg_philox_fill(fsg_rng rng, float* out, int64_t n, int raw, void* stream);
