@@ -262,18 +262,19 @@ def run_ours(args, shape):
 
     hp = HostPipeline(gen, B)
     hp.set_inputs([seg_h] * B, [seeds_h] * B)
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else args.steps  # --no-e2e: profiling runs only
+    for _ in range(2 if e2e_steps else 0):
         hp.step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         hp.step()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
+    e2e_value = world * B * e2e_steps / float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -323,6 +324,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
     shape = (args.shape,) * 3
     if args.impl == "reference":
