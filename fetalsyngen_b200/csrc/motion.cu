@@ -130,10 +130,11 @@ __device__ __forceinline__ float psf_at_voxel(const SliceGeom& g, const float* _
 
 __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const float* __restrict__ transforms, const float* __restrict__ psf, int dp, int hp, int wp,
                                                                         const float4* __restrict__ taps, int ntaps, float radius, const float* __restrict__ slices,
-                                                                        float* __restrict__ vol, float* __restrict__ vol_weight, int h, int w, int D, int H, int W, float res) {
+                                                                        const int* __restrict__ slice_idx, float* __restrict__ vol, float* __restrict__ vol_weight, int h, int w,
+                                                                        int D, int H, int W, float res) {
   extern __shared__ float4 s_tap[];
   const int in = blockIdx.z;
-  const float* t = transforms + in * 12;
+  const float* t = transforms + in * 12;  // transforms are already gathered: [n][3][4]
   for (int p = threadIdx.y * ACQ_TILE + threadIdx.x; p < ntaps; p += ACQ_TILE * ACQ_TILE) {
     const float4 q = taps[p];
     float x = t[0] * q.x;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const flo
   if (ix >= w || iy >= h) return;
   const SliceGeom g = slice_geom(t, ix, iy, h, w, D, H, W, res);
   if (g.xc + radius < 0.f || g.yc + radius < 0.f || g.zc + radius < 0.f || g.xc - radius >= (float)(W - 1) || g.yc - radius >= (float)(H - 1) || g.zc - radius >= (float)(D - 1)) return;
-  const float s = slices[((size_t)in * h + iy) * w + ix];
+  const float s = slices[((size_t)(slice_idx ? slice_idx[in] : in) * h + iy) * w + ix];
   const int Sy = W, Sz = H * W;
   const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
   float weight = 0.f;
@@ -212,6 +213,85 @@ __global__ void __launch_bounds__(256) recon_merge_kernel(const float* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------- slice stack ops
+// per-slice sums (Scanner.scan, simulate_reco.py:408: nnz = slices_no_psf.sum((1,2,3)))
+__global__ void __launch_bounds__(256) slice_sums_kernel(const float* __restrict__ slices, int hw, float* __restrict__ sums) {
+  const float* s = slices + (size_t)blockIdx.x * hw;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < hw; i += 256) acc += s[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// Scanner.random_gamma (:225-236): s = 300 (s/300)^gamma, then s / max(s).  Pass 1 writes the power
+// and reduces the max (values are >= 0: the int view of a non-negative float is order-preserving).
+__global__ void __launch_bounds__(256) slice_gamma_kernel(float* __restrict__ s, unsigned n, float gamma, int* __restrict__ max_bits) {
+  float m = 0.f;
+  for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const float v = 300.0f * powf(s[i] / 300.0f, gamma);
+    s[i] = v;
+    m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_int(m));
+}
+__global__ void __launch_bounds__(256) slice_div_kernel(float* __restrict__ s, unsigned n, const int* __restrict__ max_bits) {
+  const float m = __int_as_float(*max_bits);
+  for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) s[i] = __fdiv_rn(s[i], m);
+}
+
+// Scanner.add_noise (:248-257): Rician noise where the slice exceeds the threshold.  The reference
+// draws randn only for the masked pixels; here every pixel owns two counter-based draws
+// (block = pixel / 2) or reads the injected full-size arrays.
+__global__ void __launch_bounds__(256) slice_rician_kernel(float* __restrict__ s, unsigned n, float threshold, float sigma, const float* __restrict__ n1, const float* __restrict__ n2,
+                                                           fsg_rng rng) {
+  for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const float v = s[i];
+    if (!(v > threshold)) continue;
+    float a, b;
+    if (n1) {
+      a = n1[i];
+      b = n2[i];
+    } else {
+      const float4 g = philox_normal4(rng, i >> 1);
+      a = (i & 1) ? g.z : g.x;
+      b = (i & 1) ? g.w : g.y;
+    }
+    const float p = v + a * sigma, q = b * sigma;
+    s[i] = sqrtf(p * p + q * q);
+  }
+}
+
+// Scanner.signal_void (:273-297): slice idx[k] *= 1 - A exp(sx x'^2 + sy y'^2) in a rotated frame.
+// params[k] = (yc, xc, theta, a, A, sx) as drawn by the reference.
+__global__ void __launch_bounds__(256) slice_void_kernel(float* __restrict__ slices, int h, int w, const int* __restrict__ idx, const float* __restrict__ params) {
+  const int k = blockIdx.y;
+  const float* p = params + 6 * k;
+  float* s = slices + (size_t)idx[k] * h * w;
+  const float yc = p[0], xc = p[1], a = p[3], A = p[4], sx0 = p[5];
+  float sn, cs;
+  sincosf(p[2], &sn, &cs);
+  const float sy0 = a * a / sx0;
+  const float gx = -0.5f / (sx0 * sx0), gy = -0.5f / (sy0 * sy0);
+  const float y0 = -(float)(h - 1) / 2, x0 = -(float)(w - 1) / 2;
+  const float ystep = h > 1 ? (float)(h - 1) / (float)(h - 1) : 0.f, xstep = w > 1 ? 1.f : 0.f;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < h * w; i += gridDim.x * 256) {
+    const int iy = i / w, ix = i - iy * w;
+    const float y = (y0 + ystep * iy) - yc, x = (x0 + xstep * ix) - xc;
+    const float xr = cs * x - sn * y, yr = sn * x + cs * y;
+    s[i] = s[i] * (1.0f - A * expf(gx * xr * xr + gy * yr * yr));
+  }
+}
+
 }  // namespace fsg
 
 using namespace fsg;
@@ -237,8 +317,8 @@ extern "C" int fsg_slice_acq_forward(const float* transforms, const float* vol, 
   return check_launch("fsg_slice_acq_forward");
 }
 
-extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices, float* vol,
-                                     float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream) {
+extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,
+                                     const int32_t* slice_idx, float* vol, float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream) {
   if (int rc = check_acq("fsg_slice_acq_adjoint", ntaps, n, h, w, D, H, W)) return rc;
   FSG_REQUIRE(transforms && psf && taps && slices && vol, "fsg_slice_acq_adjoint: NULL pointer");
   FSG_REQUIRE(!equalize || vol_weight, "fsg_slice_acq_adjoint: equalize needs vol_weight");
@@ -251,13 +331,46 @@ extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, 
   dim3 grid((w + ACQ_TILE - 1) / ACQ_TILE, (h + ACQ_TILE - 1) / ACQ_TILE, n);
   const size_t smem = sizeof(float4) * ntaps;
   if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  slice_adj_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, vol, vol_weight, h, w, D, H, W,
-                                                               res_slice);
+  slice_adj_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, slice_idx, vol, vol_weight, h, w,
+                                                               D, H, W, res_slice);
   if (equalize) {
     const size_t want = (nv + 255) / 256;
     equalize_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(vol, vol_weight, (unsigned)nv);
   }
   return check_launch("fsg_slice_acq_adjoint");
+}
+
+static unsigned grid_for(size_t n) {
+  const size_t want = (n + 255) / 256;
+  return (unsigned)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+}
+
+extern "C" int fsg_slice_sums(const float* slices, int n, int hw, float* sums, void* stream) {
+  FSG_REQUIRE(slices && sums && n >= 1 && hw >= 1, "fsg_slice_sums: bad arguments");
+  slice_sums_kernel<<<n, 256, 0, as_stream(stream)>>>(slices, hw, sums);
+  return check_launch("fsg_slice_sums");
+}
+
+extern "C" int fsg_slice_gamma(float* slices, int64_t count, float gamma, float* workspace, void* stream) {
+  FSG_REQUIRE(slices && workspace && count >= 1 && count < ((int64_t)1 << 32), "fsg_slice_gamma: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(workspace, 0, sizeof(float), s);
+  slice_gamma_kernel<<<grid_for(count), 256, 0, s>>>(slices, (unsigned)count, gamma, reinterpret_cast<int*>(workspace));
+  slice_div_kernel<<<grid_for(count), 256, 0, s>>>(slices, (unsigned)count, reinterpret_cast<const int*>(workspace));
+  return check_launch("fsg_slice_gamma");
+}
+
+extern "C" int fsg_slice_rician(float* slices, int64_t count, float threshold, float sigma, const float* noise1, const float* noise2, fsg_rng rng, void* stream) {
+  FSG_REQUIRE(slices && count >= 1 && count < ((int64_t)1 << 32) && (!noise1 == !noise2), "fsg_slice_rician: bad arguments");
+  slice_rician_kernel<<<grid_for(count), 256, 0, as_stream(stream)>>>(slices, (unsigned)count, threshold, sigma, noise1, noise2, rng);
+  return check_launch("fsg_slice_rician");
+}
+
+extern "C" int fsg_slice_void(float* slices, int h, int w, const int32_t* idx, const float* params, int nvoid, void* stream) {
+  FSG_REQUIRE(slices && idx && params && h >= 1 && w >= 1 && nvoid >= 1 && nvoid <= 65535, "fsg_slice_void: bad arguments");
+  dim3 grid(grid_for((size_t)h * w) < 64 ? grid_for((size_t)h * w) : 64, nvoid);
+  slice_void_kernel<<<grid, 256, 0, as_stream(stream)>>>(slices, h, w, idx, params);
+  return check_launch("fsg_slice_void");
 }
 
 extern "C" int fsg_recon_merge(const float* rec, const float* gt, const float* weight_raw, const float* minmax, float increase, int smooth, int D, int H, int W, float* out,

@@ -292,8 +292,21 @@ int fsg_label_mask(const uint8_t* labels, int match, uint8_t* out, int64_t n, vo
  * slices: [n][h][w].  fsg_slice_acq_adjoint zero-fills vol / vol_weight itself. */
 int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
                           float res_slice, void* stream);
-int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices, float* vol,
-                          float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream);
+int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,
+                          const int32_t* slice_idx, float* vol, float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream);
+/* slice_idx (device, [n], may be NULL): slice in of the launch reads slices[slice_idx[in]] — the
+ * "stacks[kept_idx]" gather of PSFReconstructor (simulate_reco.py:766-767) without a copy.
+ *
+ * Slice-stack helpers of Scanner.scan (simulate_reco.py:300-466), all in place on [count] floats:
+ *   fsg_slice_sums    per-slice sums (:408), sums[n] on the device
+ *   fsg_slice_gamma   300 (s/300)^gamma, then / max (:225-236); workspace = 1 device float
+ *   fsg_slice_rician  sqrt((s + n1 sigma)^2 + (n2 sigma)^2) where s > threshold (:248-257);
+ *                     noise1/noise2 NULL: Philox draws (two per pixel), else injected arrays
+ *   fsg_slice_void    slice idx[k] *= 1 - A exp(...) (:273-297); params[k] = (yc, xc, theta, a, A, sx) */
+int fsg_slice_sums(const float* slices, int n, int hw, float* sums, void* stream);
+int fsg_slice_gamma(float* slices, int64_t count, float gamma, float* workspace, void* stream);
+int fsg_slice_rician(float* slices, int64_t count, float threshold, float sigma, const float* noise1, const float* noise2, fsg_rng rng, void* stream);
+int fsg_slice_void(float* slices, int h, int w, const int32_t* idx, const float* params, int nvoid, void* stream);
 /* Optional 3^3 mean (smooth_volume, simulate_reco.py:584-595) + merge with the clean volume
  * out = w*rec + (1-w)*gt (merge_volumes, :692-709); w = clamp((weight_raw + increase - min)/(max - min), 0, 1)
  * with minmax = [2] device floats (NULL: weight_raw is used as is); weight_raw NULL: no merge. */

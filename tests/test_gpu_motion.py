@@ -1,0 +1,207 @@
+"""SimulateMotion on the GPU: slice acquisition / PSF reconstruction kernels against (a) the
+reference's own CUDA extension built from its sources into oracle/_ref, (b) the numpy oracle,
+(c) golden vectors of the unmodified reference Scanner + PSFReconstructor.
+
+Float tolerance: max-abs <= 1e-4 x intensity range (TOL).  The reconstruction scatters with
+float atomics (summation order is not deterministic, in the reference either) and rounds tap
+positions to the nearest voxel, where a 1-ulp coordinate difference can move one tap to the
+neighbouring voxel: for it the bound is on the 99.9th percentile, with a loose cap on the max."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import np_motion as M
+from gpu_util import DEV, TOL
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def load(name):
+    with np.load(GOLDEN / f"{name}.npz") as z:
+        return {k: z[k] for k in z.files}
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    rng = float(b.max() - b.min()) or 1.0
+    return np.abs(a.astype(np.float64).reshape(b.shape) - b.astype(np.float64)) / rng
+
+
+def close(e, tol=TOL, cap=5e-2, q=99.9):
+    """Float parity up to rare in/out flips of single PSF taps at the volume faces (a tap whose
+    coordinate sits within an ulp of a bound is counted by one implementation and not the other)."""
+    p = float(np.percentile(e, q))
+    assert p <= tol and float(e.max()) <= cap, (p, float(e.max()), float((e > tol).mean()))
+
+
+def random_case(seed, D=40, n=10, hw=48):
+    rs = np.random.RandomState(seed)
+    vol = rs.rand(D, D + 4, D - 6).astype(np.float32)
+    ax = np.concatenate([rs.randn(n, 3) * 0.6, rs.randn(n, 2) * 3, np.linspace(-15, 15, n)[:, None]], 1).astype(np.float32)
+    mat = M.axisangle2mat(ax)
+    psf = M.get_psf(res_ratio=(1.3, 1.3, 4.2))
+    return vol, mat, psf, (hw, hw + 8), 1.3
+
+
+def ours_forward(mat, vol, psf, shape, res):
+    from fetalsyngen_b200.generator.artifacts.simulate_reco import slice_acquisition
+
+    return slice_acquisition(mat, torch.from_numpy(vol).to(DEV), psf, shape, res)[:, 0]
+
+
+def ours_adjoint(mat, psf, slices, vshape, res, idx=None):
+    from fetalsyngen_b200.generator.artifacts.simulate_reco import slice_acquisition_adjoint
+
+    s = slices if isinstance(slices, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(slices)).to(DEV)
+    v, w = slice_acquisition_adjoint(mat, psf, s, vshape, res, slice_idx=idx)
+    return v[0, 0], w[0, 0]
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_kernels_vs_numpy_oracle(seed):
+    vol, mat, psf, shape, res = random_case(seed)
+    want = M.slice_acq_forward(mat, vol, psf, shape, res)
+    got = ours_forward(mat, vol, psf, shape, res)
+    close(rel(got, want))
+    assert ((got.cpu().numpy() == 0) == (want == 0)).mean() > 0.999
+    wv, ww = M.slice_acq_adjoint(mat, psf, want, vol.shape, res, True)
+    gv, gw = ours_adjoint(mat, psf, want, vol.shape, res)
+    close(rel(gv, wv))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_kernels_and_oracle_vs_reference_extension(seed):
+    """The reference's slice_acq_cuda extension (built by oracle/build_ref.py from /root/reference)
+    is the ground truth for both our kernels and the numpy restatement."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+
+    ext = build_ref.load_built()
+    if ext is None:
+        pytest.skip("oracle/_ref/slice_acq_cuda.so not built")
+    vol, mat, psf, shape, res = random_case(seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    empty = torch.empty(0, device=DEV)
+    ref_s = ext.forward(t(mat), t(vol)[None, None], empty, empty, t(psf), list(shape), float(res), False, False)[0][:, 0]
+    ref_np = ref_s.cpu().numpy()
+    close(rel(M.slice_acq_forward(mat, vol, psf, shape, res), ref_np))
+    close(rel(ours_forward(mat, vol, psf, shape, res), ref_np))
+    ref_v = ext.adjoint_forward(t(mat), t(psf), ref_s[:, None].contiguous(), empty, empty, list(vol.shape), float(res), True, True)[0][0, 0].cpu().numpy()
+    for got in (M.slice_acq_adjoint(mat, psf, ref_np, vol.shape, res, True)[0], ours_adjoint(mat, psf, ref_np, vol.shape, res)[0]):
+        close(rel(got, ref_v))
+
+
+@pytest.mark.parametrize("name", ["motion_default", "motion_all_on"])
+def test_forward_and_adjoint_vs_reference_golden(name):
+    g = load(name)
+    for k in range(int(g["n_attempts"])):
+        got = ours_forward(g[f"fwd_mat_{k}"], g["image"], g["psf_acq"], g[f"fwd_img_{k}"].shape[1:], float(g["resolution_slice"]) / 0.5)
+        close(rel(got, g[f"fwd_img_{k}"]))
+    mask = (g["seg"] > 0).astype(np.float32)
+    got = ours_forward(g["fwd_mat_0"], mask, M.get_psf(0), g["fwd_mask_0"].shape[1:], float(g["resolution_slice"]) / 0.5)
+    close(rel(got, g["fwd_mask_0"]))
+    n = g["stacks"].shape[0]
+    kept = g["perm_kept"][int(n * float(g["rm_slices_ratio"])):] if bool(g["rm_slices_on"]) else np.arange(n)
+    assert len(kept) == int(g["adj_nslices"])
+    gv, _ = ours_adjoint(g["adj_mat"], g["psf_rec"], g["stacks"], g["image"].shape, float(g["res_slice"]), idx=kept)
+    close(rel(gv, g["recon"]))
+
+
+def _inject(g):
+    inj = {}
+    h, w = g["stacks"].shape[1:]
+    for k in range(int(g["n_stacks_logged"])):
+        n = g[f"noise_mask_{k}"].size * 8 // (h * w)
+        mask = np.unpackbits(g[f"noise_mask_{k}"])[: n * h * w].reshape(n, h, w).astype(bool)
+        for key in ("noise1", "noise2"):
+            full = np.zeros(mask.shape, np.float32)
+            full[mask] = g[f"{key}_{k}"]
+            inj[f"{key}_{k}"] = full
+        inj[f"void_{k}"] = {kk: g[f"void_{kk}_{k}"] for kk in ("idx", "yc", "xc", "theta", "a", "A", "sx") if f"void_{kk}_{k}" in g}
+    for key in ("perm_misreg", "perm_kept"):
+        if key in g:
+            inj[key] = g[key]
+    for o in range(int(g["octave"])):
+        inj[f"theta_{o}"], inj[f"phi_{o}"] = g[f"theta_{o}"], g[f"phi_{o}"]
+    return inj
+
+
+def _artifact(scanner_over=None, recon_over=None):
+    from fetalsyngen_b200.generator.artifacts.utils import ReconMergeParams, ReconParams, ScannerParams
+    from fetalsyngen_b200.generator.augmentation.artifacts import SimulateMotion
+
+    sp = dict(resolution_slice_fac_min=0.5, resolution_slice_fac_max=2, resolution_slice_max=1.5, slice_thickness_min=1.5, slice_thickness_max=3.5, gap_min=1.5, gap_max=5.5,
+              min_num_stack=2, max_num_stack=6, max_num_slices=250, noise_sigma_min=0, noise_sigma_max=0.1, TR_min=1, TR_max=2, prob_void=0.2, prob_gamma=0.1, gamma_std=0.05,
+              slice_size=None, restrict_transform=False, txy=3.0)
+    sp.update(scanner_over or {})
+    mp = ReconMergeParams(merge_type="perlin", perlin_res_list=[1, 2], perlin_octaves_list=[1, 2, 4], perlin_persistence=0.5, perlin_lacunarity=2,
+                          gauss_ngaussians_min=2, gauss_ngaussians_max=4, perlin_increase_size=0.25)
+    rp = dict(prob_misreg_slice=0.1, slices_misreg_ratio=0.1, prob_misreg_stack=0.1, txy=3.0, prob_merge=1.0, merge_params=mp, prob_smooth=0.2, prob_rm_slices=0.3,
+              rm_slices_min=0.1, rm_slices_max=0.4)
+    rp.update(recon_over or {})
+    return SimulateMotion(1.0, ScannerParams(**sp), ReconParams(**rp))
+
+
+CASES = {
+    "motion_default": ({"max_num_stack": 3}, None),
+    "motion_all_on": ({"prob_gamma": 1.0, "prob_void": 0.5, "min_num_stack": 3, "max_num_stack": 3},
+                      {"prob_misreg_slice": 1.0, "prob_misreg_stack": 1.0, "prob_smooth": 1.0, "prob_rm_slices": 1.0}),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_simulate_motion_vs_reference_golden(name):
+    """Whole artifact with the reference's numpy seed (same scalar draws in the same order) and
+    its torch draws injected: stacks, transforms and the merged output must match."""
+    from fetalsyngen_b200.generator.artifacts import simulate_reco as SR
+
+    g = load(name)
+    art = _artifact(*CASES[name])
+    img, seg = torch.from_numpy(g["image"]).to(DEV), torch.from_numpy(g["seg"].astype(np.float32)).to(DEV)
+    cap = {}
+    o_scan = SR.Scanner.scan
+
+    def scan(self, data, genparams={}, inject=None):
+        out = o_scan(self, data, genparams, inject)
+        cap.update({k: out[k] for k in ("stacks", "transforms", "transforms_gt", "positions")})
+        return out
+
+    SR.Scanner.scan = scan
+    try:
+        np.random.seed(int(g["seed"]))  # the golden run starts at Scanner.scan (after the gate draw of artifacts.py:388)
+        out, meta = SR.simulate_motion(art, img, seg, [0.5, 0.5, 0.5], inject=_inject(g))
+    finally:
+        SR.Scanner.scan = o_scan
+    assert cap["stacks"].shape[0] == g["stacks"].shape[0]
+    assert np.array_equal(cap["positions"], g["positions"])
+    assert np.abs(cap["transforms_gt"] - g["transforms_gt"]).max() <= 1e-4
+    assert np.abs(cap["transforms"] - g["transforms"]).max() <= 1e-4
+    close(rel(cap["stacks"][:, 0], g["stacks"]), 2 * TOL)
+    assert meta["nstacks"] == len(np.unique(g["positions"][:, 1]))
+    assert bool(meta["smooth_volume_on"]) == bool(g["smooth_volume_on"]) and int(meta["octave"]) == int(g["octave"])
+    close(rel(out, g["output"]), 2 * TOL)
+
+
+def test_simulate_motion_philox_mode_and_gate():
+    g = load("motion_default")
+    img, seg = torch.from_numpy(g["image"]).to(DEV), torch.from_numpy(g["seg"].astype(np.float32)).to(DEV)
+    art = _artifact()
+    art.prob = 0.0
+    out, meta = art(img, seg, DEV, {}, resolution=[0.5, 0.5, 0.5])
+    assert out is img and meta == {}
+    art.prob = 1.0
+    np.random.seed(5)
+    torch.manual_seed(5)
+    out, meta = art(img, seg, DEV, {}, resolution=[0.5, 0.5, 0.5])
+    assert out.shape == img.shape and torch.isfinite(out).all()
+    for key in ("resolution_recon", "resolution_slice", "slice_thickness", "gap", "nstacks", "smooth_volume_on", "rm_slices_on", "rm_slices_ratio", "misreg_stack_on", "misreg_slice_on",
+                "merge_volume_on", "merge_type", "res", "octave"):
+        assert key in meta
+    diff = (out - img).abs()
+    assert float(diff.max()) > 1e-3            # something was degraded ...
+    assert float(out.min()) >= -1e-6 and float(out.max()) <= float(img.max()) * 1.5 + 0.5
