@@ -9,7 +9,9 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libfsg.so"
+import os
+
+LIB_PATH = Path(os.environ.get("FSG_LIB", PKG / "libfsg.so"))  # FSG_LIB: A/B builds of the kernels (benchmarks only)
 MAX_JOBS = 16
 MAX_TAPS = 127
 
@@ -157,7 +159,7 @@ class LaunchStats:
 
     def __init__(self):
         self.calls: dict = {}
-        self.timing = False
+        self.timing = False     # True: every entry point; a set of names: only those
         self._events: list = []
 
     def reset(self):
@@ -185,7 +187,7 @@ stats = LaunchStats()
 def call(name: str, *args):
     lib = load()
     stats.calls[name] = stats.calls.get(name, 0) + 1
-    if stats.timing:
+    if stats.timing is True or (stats.timing and name in stats.timing):
         import torch
 
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

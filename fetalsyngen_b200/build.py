@@ -34,10 +34,11 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, defines: tuple = ()) -> Path:
+    """``out`` / ``defines``: variant builds for A/B kernel timing (``FSG_LIB`` selects one at load)."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, f"-I{ROOT / 'include'}", *[str(CSRC / s) for s in SOURCES], "-o", str(LIB)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], f"-I{ROOT / 'include'}", *[str(CSRC / s) for s in SOURCES], "-o", str(out or LIB)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -45,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

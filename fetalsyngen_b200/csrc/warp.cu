@@ -47,6 +47,44 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ float lerp_fma(float a, float b, float w) { return __fmaf_rn(w, __fsub_rn(b, a), a); }
 
+// Packed FP32x2 (sm_100: FADD2 / FMUL2 / FFMA2 take one issue slot for two lanes).  add/sub are
+// individually rounded like their scalar forms.  ptxas contracts mul.f32x2 feeding add.f32x2 into
+// FFMA2 even under --fmad=false, so the bit-exact coordinate chain keeps its products scalar
+// (FMUL writes straight into the halves of a register pair) and packs only the adds; mul2 / fma2
+// are used on the tolerance-checked image path.
+typedef unsigned long long P2;
+__device__ __forceinline__ P2 pk(float a, float b) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(P2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) {
+  P2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 add2_rz(P2 a, P2 b) {
+  P2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 sub2(P2 a, P2 b) {
+  P2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) {
+  P2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // Exact control-grid value at voxel (i,j,k): x-, y-, z-blend in myzoom_torch's order.  Used by
 // the edge pre-pass only (the main kernel stages the x/y blends in shared memory).
 __device__ __forceinline__ void field_at(const fsg_warp_job& job, int i, int j, int k, float& fx, float& fy, float& fz) {
@@ -376,6 +414,190 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------- fast path
+// Same arithmetic as warp_kernel<PASS_WARP> for the production case (deformation with a control
+// grid, image + segmentation, no second image, extents that are multiples of the tile), with the
+// per-voxel instruction count cut from ~200 to ~130 (r01d ncu: the generic kernel is issue-bound,
+// 72 % issue-slot utilisation at 15 % of DRAM bandwidth, 32 IMAD + 20 IADD3 + 9 MOV + 8 BRA per
+// voxel of pure overhead):
+//   * no per-voxel runtime flags: every job of the launch has the same feature set (the host
+//     partitions a batch) and EPI is a template parameter; the crop shift is subtracted
+//     unconditionally (x - 0 is exact);
+//   * ONE gather base index per voxel.  The floor indices are clamped to S-2 in the float domain
+//     (min with the largest float below S-1 before the magic add), so the +1 neighbours are always
+//     in bounds and become fixed pointer offsets (+1 element, +sz, +/-plane); where the reference
+//     clamps the ceil index instead (coordinate == S-1) the weight is exactly 1 and the lerp returns
+//     the same corner value to within an ulp of the image path's tolerance;
+//   * the 2^23 magic-number biases of the six float->int conversions fold into one per-thread
+//     constant; shared-memory and output addresses advance by constant strides;
+//   * gamma and bias share one exponential: v' = 2^(gamma*lg2 v + (1-gamma) lg2 300 + bf*lg2 e).
+// Coordinates (and therefore the nearest-neighbour segmentation) stay bit-exact: the chain of
+// separately rounded mul/add is unchanged.
+#ifndef FSG_WARP_MINBLOCKS
+#define FSG_WARP_MINBLOCKS 3  // <= 85 registers: 3 blocks of 256 threads per SM
+#endif
+template <bool EPI>
+__global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
+  const fsg_warp_job& job = batch.j[blockIdx.z];
+  const int tid = threadIdx.x;
+  extern __shared__ float4 s_dyn[];
+  float4* s_f = s_dyn;                    // [WY*WX][fz_n]: row = ry*WX + rx
+  __shared__ float s_b[WX * WY][MAX_BZ];  // bias rows, pre-scaled by log2(e)
+
+  const int fz_n = job.fs[2];
+  const bool has_bias = EPI && job.bf_low != nullptr;
+  const int ntile_y = sy / WY;
+  const int x0 = ((int)blockIdx.x / ntile_y) * WX, y0 = ((int)blockIdx.x % ntile_y) * WY;
+
+  // ---- phase A: x/y blends of the control grids for the tile's rows (exact, as in the generic kernel)
+  {
+    const int fy_n = job.fs[1];
+    const int per_row = fz_n * 3;
+    float* sf = reinterpret_cast<float*>(s_f);
+    for (int e = tid; e < WX * WY * per_row; e += WARP_THREADS) {
+      const int row = e / per_row, rem = e - row * per_row;
+      const int ry = row / WX, rx = row - ry * WX;
+      const Tab tx = load_tab(job.ftab[0], x0 + rx), ty = load_tab(job.ftab[1], y0 + ry);
+      const float* g = job.fsmall + rem;
+      const int sxs = fy_n * per_row;
+      const float t1f = blend(tx.wf, __ldg(g + tx.f * sxs + ty.f * per_row), tx.wc, __ldg(g + tx.c * sxs + ty.f * per_row));
+      const float t1c = blend(tx.wf, __ldg(g + tx.f * sxs + ty.c * per_row), tx.wc, __ldg(g + tx.c * sxs + ty.c * per_row));
+      const int zc = rem / 3, ch = rem - zc * 3;
+      sf[(row * fz_n + zc) * 4 + ch] = blend(ty.wf, t1f, ty.wc, t1c);
+    }
+  }
+  if (EPI) {
+    const int bz_n = has_bias ? job.bs[2] : 1;
+    for (int e = tid; e < WX * WY * bz_n; e += WARP_THREADS) {
+      const int row = e / bz_n, zc = e - row * bz_n;
+      float v = 0.f;
+      if (has_bias) {
+        const int ry = row / WX, rx = row - ry * WX;
+        const int by_n = job.bs[1];
+        const Tab tx = load_tab(job.btab[0], x0 + rx), ty = load_tab(job.btab[1], y0 + ry);
+        const float* g = job.bf_low + zc;
+        const int sxs = by_n * bz_n;
+        const float t1f = blend(tx.wf, __ldg(g + tx.f * sxs + ty.f * bz_n), tx.wc, __ldg(g + tx.c * sxs + ty.f * bz_n));
+        const float t1c = blend(tx.wf, __ldg(g + tx.f * sxs + ty.c * bz_n), tx.wc, __ldg(g + tx.c * sxs + ty.c * bz_n));
+        v = blend(ty.wf, t1f, ty.wc, t1c) * 1.4426950408889634f;
+      }
+      s_b[row][zc] = v;
+    }
+  }
+  __syncthreads();
+
+  const Affine aff(job);
+  const float cen_x = job.center[0], cen_y = job.center[1], cen_z = job.center[2];
+  const float mx = (float)(sx - 1), my = (float)(sy - 1), mz = (float)(sz - 1);
+  // largest floats below S-1: floor(min(c, that)) <= S-2
+  const float lx = __int_as_float(__float_as_int(mx) - 1), ly = __int_as_float(__float_as_int(my) - 1), lz = __int_as_float(__float_as_int(mz) - 1);
+  const int plane = sy * sz;
+  const int xs = job.flip ? -plane : plane;
+  // index = fx*xs + fy*sz + fz with all three taken as raw float bits of (value + 2^23)
+  const unsigned kbias = (unsigned)(job.flip ? (sx - 1) * plane : 0) - 0x4B000000u * (unsigned)(xs + sz + 1);
+  const float* __restrict__ const src_img = job.src_img;
+  const uint8_t* __restrict__ const src_seg = job.src_seg;
+  float* __restrict__ const dst_img = job.dst_img;
+  uint8_t* __restrict__ const dst_seg = job.dst_seg;
+  const float shx = job.shift[0], shy = job.shift[1], shz = job.shift[2];
+  const float gam = (EPI && job.has_gamma) ? job.gamma : 1.0f;
+  const float c0 = (EPI && job.has_gamma) ? 8.22881869049588f * (1.0f - job.gamma) : 0.f;  // lg2(300) (1 - gamma)
+
+  const P2 cen2 = pk(cen_x, cen_x), sh2x = pk(shx, shx), sh2y = pk(shy, shy), sh2z = pk(shz, shz), magic2 = pk(MAGIC, MAGIC);
+  const P2 c2x = pk(aff.c[0], aff.c[0]), c2y = pk(aff.c[1], aff.c[1]), c2z = pk(aff.c[2], aff.c[2]);
+  const char* const img_b = reinterpret_cast<const char*>(src_img);
+  const ptrdiff_t by_row = (ptrdiff_t)sz * 4, by_plane = (ptrdiff_t)xs * 4;
+
+  for (int k = tid; k < sz; k += WARP_THREADS) {
+    const Tab tf = load_tab(job.ftab[2], k);
+    Tab tb = {0, 0, 0.f, 1.f};
+    if (has_bias) tb = load_tab(job.btab[2], k);
+    const float zc = sub_rn((float)k, cen_z);
+    const P2 zc2 = pk(zc, zc), bwf2 = pk(tb.wf, tb.wf), bwc2 = pk(tb.wc, tb.wc), gam2 = pk(gam, gam), c02 = pk(c0, c0);
+    const float4* pf = s_f + tf.f;
+    const float4* pc = s_f + tf.c;
+    unsigned o_row = (unsigned)((x0 * sy + y0) * sz + k);
+    int row = 0;
+#pragma unroll 1
+    for (int ry = 0; ry < WY; ++ry, o_row += sz) {
+      const float yc = sub_rn((float)(y0 + ry), cen_y);
+      const P2 yc2 = pk(yc, yc);
+      P2 xi2 = pk((float)x0, (float)(x0 + 1));
+      unsigned o = o_row;
+#pragma unroll 1
+      for (int rx = 0; rx < WX; rx += 2, row += 2, o += 2 * plane, xi2 = add2(xi2, pk(2.0f, 2.0f))) {
+        // two voxels (i, j, k) and (i+1, j, k): products stay scalar FMULs (separately rounded, ptxas
+        // would contract a packed mul feeding a packed add), every add is one packed FADD2
+        const float4 f0a = pf[row * fz_n], f1a = pc[row * fz_n], f0b = pf[(row + 1) * fz_n], f1b = pc[(row + 1) * fz_n];
+        const P2 fx = add2(pk(mul_rn(tf.wf, f0a.x), mul_rn(tf.wf, f0b.x)), pk(mul_rn(tf.wc, f1a.x), mul_rn(tf.wc, f1b.x)));
+        const P2 fy = add2(pk(mul_rn(tf.wf, f0a.y), mul_rn(tf.wf, f0b.y)), pk(mul_rn(tf.wc, f1a.y), mul_rn(tf.wc, f1b.y)));
+        const P2 fz = add2(pk(mul_rn(tf.wf, f0a.z), mul_rn(tf.wf, f0b.z)), pk(mul_rn(tf.wc, f1a.z), mul_rn(tf.wc, f1b.z)));
+        float x1a, x1b, y1a, y1b, z1a, z1b;
+        upk(add2(sub2(xi2, cen2), fx), x1a, x1b);
+        upk(add2(yc2, fy), y1a, y1b);
+        upk(add2(zc2, fz), z1a, z1b);
+        float iia, iib, jja, jjb, kka, kkb;
+        upk(add2(add2(add2(pk(mul_rn(aff.a[0], x1a), mul_rn(aff.a[0], x1b)), pk(mul_rn(aff.a[1], y1a), mul_rn(aff.a[1], y1b))), pk(mul_rn(aff.a[2], z1a), mul_rn(aff.a[2], z1b))), c2x), iia, iib);
+        upk(add2(add2(add2(pk(mul_rn(aff.a[3], x1a), mul_rn(aff.a[3], x1b)), pk(mul_rn(aff.a[4], y1a), mul_rn(aff.a[4], y1b))), pk(mul_rn(aff.a[5], z1a), mul_rn(aff.a[5], z1b))), c2y), jja, jjb);
+        upk(add2(add2(add2(pk(mul_rn(aff.a[6], x1a), mul_rn(aff.a[6], x1b)), pk(mul_rn(aff.a[7], y1a), mul_rn(aff.a[7], y1b))), pk(mul_rn(aff.a[8], z1a), mul_rn(aff.a[8], z1b))), c2z), kka, kkb);
+        const P2 ii = sub2(pk(fminf(fmaxf(iia, 0.f), mx), fminf(fmaxf(iib, 0.f), mx)), sh2x);
+        const P2 jj = sub2(pk(fminf(fmaxf(jja, 0.f), my), fminf(fmaxf(jjb, 0.f), my)), sh2y);
+        const P2 kk = sub2(pk(fminf(fmaxf(kka, 0.f), mz), fminf(fmaxf(kkb, 0.f), mz)), sh2z);
+        upk(ii, iia, iib);
+        upk(jj, jja, jjb);
+        upk(kk, kka, kkb);
+        // ---- floor (clamped to S-2) and weights
+        const P2 tx2 = add2_rz(pk(fminf(iia, lx), fminf(iib, lx)), magic2), ty2 = add2_rz(pk(fminf(jja, ly), fminf(jjb, ly)), magic2), tz2 = add2_rz(pk(fminf(kka, lz), fminf(kkb, lz)), magic2);
+        float txa, txb, tya, tyb, tza, tzb;
+        upk(tx2, txa, txb);
+        upk(ty2, tya, tyb);
+        upk(tz2, tza, tzb);
+        const unsigned ba = (unsigned)__float_as_int(txa) * (unsigned)xs + (unsigned)__float_as_int(tya) * (unsigned)sz + (unsigned)__float_as_int(tza) + kbias;
+        const unsigned bb = (unsigned)__float_as_int(txb) * (unsigned)xs + (unsigned)__float_as_int(tyb) * (unsigned)sz + (unsigned)__float_as_int(tzb) + kbias;
+        const P2 wx2 = sub2(ii, sub2(tx2, magic2)), wy2 = sub2(jj, sub2(ty2, magic2)), wz2 = sub2(kk, sub2(tz2, magic2));
+        const char* a00 = img_b + (size_t)ba * 4;
+        const char* a01 = a00 + by_row;
+        const char* a10 = a00 + by_plane;
+        const char* a11 = a10 + by_row;
+        const char* b00 = img_b + (size_t)bb * 4;
+        const char* b01 = b00 + by_row;
+        const char* b10 = b00 + by_plane;
+        const char* b11 = b10 + by_row;
+#define LDF(p, off) __ldg(reinterpret_cast<const float*>(p) + (off))
+        const P2 c000 = pk(LDF(a00, 0), LDF(b00, 0)), c001 = pk(LDF(a00, 1), LDF(b00, 1)), c010 = pk(LDF(a01, 0), LDF(b01, 0)), c011 = pk(LDF(a01, 1), LDF(b01, 1));
+        const P2 c100 = pk(LDF(a10, 0), LDF(b10, 0)), c101 = pk(LDF(a10, 1), LDF(b10, 1)), c110 = pk(LDF(a11, 0), LDF(b11, 0)), c111 = pk(LDF(a11, 1), LDF(b11, 1));
+#undef LDF
+        // ---- nearest segmentation gather (round-half-even by the magic add)
+        float sxa, sxb, sya, syb, sza, szb;
+        upk(add2(ii, magic2), sxa, sxb);
+        upk(add2(jj, magic2), sya, syb);
+        upk(add2(kk, magic2), sza, szb);
+        const uint8_t laba = __ldg(src_seg + ((unsigned)__float_as_int(sxa) * (unsigned)xs + (unsigned)__float_as_int(sya) * (unsigned)sz + (unsigned)__float_as_int(sza) + kbias));
+        const uint8_t labb = __ldg(src_seg + ((unsigned)__float_as_int(sxb) * (unsigned)xs + (unsigned)__float_as_int(syb) * (unsigned)sz + (unsigned)__float_as_int(szb) + kbias));
+        // ---- trilinear blend (image path: fused, packed)
+        const P2 c00 = fma2(wx2, sub2(c100, c000), c000), c01 = fma2(wx2, sub2(c101, c001), c001);
+        const P2 c10 = fma2(wx2, sub2(c110, c010), c010), c11 = fma2(wx2, sub2(c111, c011), c011);
+        const P2 c0_ = fma2(wy2, sub2(c10, c00), c00), c1_ = fma2(wy2, sub2(c11, c01), c01);
+        float va, vb;
+        upk(fma2(wz2, sub2(c1_, c0_), c0_), va, vb);
+        va = fminf(fminf(iia, jja), kka) > 0.f ? va : 0.f;
+        vb = fminf(fminf(iib, jjb), kkb) > 0.f ? vb : 0.f;
+        if (EPI) {
+          const P2 bias = fma2(bwf2, pk(s_b[row][tb.f], s_b[row + 1][tb.f]), mul2(bwc2, pk(s_b[row][tb.c], s_b[row + 1][tb.c])));
+          float ea, eb;
+          upk(add2(fma2(gam2, pk(lg2_approx(va), lg2_approx(vb)), c02), bias), ea, eb);
+          va = ex2_approx(ea);
+          vb = ex2_approx(eb);
+        }
+        dst_img[o] = va;
+        dst_img[o + plane] = vb;
+        dst_seg[o] = laba;
+        dst_seg[o + plane] = labb;
+      }
+    }
+  }
+}
+
 __global__ void shift_init_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int njobs) {
   const int t = threadIdx.x;
   if (t < njobs * 3) const_cast<float*>(batch.j[t / 3].shift)[t % 3] = __int_as_float(0x7f800000);
@@ -444,16 +666,44 @@ extern "C" int fsg_warp_shift(const fsg_warp_job* jobs, int njobs, int sx, int s
   return check_launch("fsg_warp_shift");
 }
 
+// A job takes the fast kernel when it is the production case; `epi` = it has a gamma or bias epilogue.
+static bool fast_eligible(const fsg_warp_job& j, int sx, int sy, int sz) {
+  return j.mode == 1 && j.fsmall && j.src_img && j.dst_img && j.src_seg && j.dst_seg && !j.dst_img2 && sx % WX == 0 && sy % WY == 0 && sx >= 2 && sy >= 2 && sz >= 2 &&
+         (!j.bf_low || j.dst_img);
+}
+
 extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int sz, void* stream) {
-  Batch<fsg_warp_job> b;
-  if (int rc = fill_batch(b, jobs, njobs)) return rc;
+  FSG_REQUIRE(jobs != nullptr && njobs >= 1 && njobs <= FSG_MAX_JOBS, "fsg_warp: njobs=%d outside [1,%d]", njobs, FSG_MAX_JOBS);
   if (int rc = validate(jobs, njobs, sx, sy, sz, true, "fsg_warp")) return rc;
-  bool img2 = false;
-  for (int n = 0; n < njobs; ++n) img2 = img2 || jobs[n].dst_img2 != nullptr;
-  if (img2)
-    warp_kernel<PASS_WARP, true><<<warp_grid(njobs, sx, sy), WARP_THREADS, field_smem(jobs, njobs), as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
-  else
-    warp_kernel<PASS_WARP, false><<<warp_grid(njobs, sx, sy), WARP_THREADS, field_smem(jobs, njobs), as_stream(stream)>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  // partition the batch: fast kernel with / without epilogue, generic kernel for everything else
+  fsg_warp_job part[3][FSG_MAX_JOBS];
+  int cnt[3] = {0, 0, 0};
+  for (int n = 0; n < njobs; ++n) {
+    const fsg_warp_job& j = jobs[n];
+    const int g = !fast_eligible(j, sx, sy, sz) ? 2 : ((j.has_gamma || j.bf_low) ? 0 : 1);
+    part[g][cnt[g]++] = j;
+  }
+  cudaStream_t s = as_stream(stream);
+  Batch<fsg_warp_job> b;
+  for (int g = 0; g < 2; ++g) {
+    if (!cnt[g]) continue;
+    if (int rc = fill_batch(b, part[g], cnt[g])) return rc;
+    const dim3 grid((sy / WY) * (sx / WX), 1, cnt[g]);
+    const size_t smem = field_smem(part[g], cnt[g]);
+    if (g == 0)
+      warp_fast_kernel<true><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else
+      warp_fast_kernel<false><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+  }
+  if (cnt[2]) {
+    if (int rc = fill_batch(b, part[2], cnt[2])) return rc;
+    bool img2 = false;
+    for (int n = 0; n < cnt[2]; ++n) img2 = img2 || part[2][n].dst_img2 != nullptr;
+    if (img2)
+      warp_kernel<PASS_WARP, true><<<warp_grid(cnt[2], sx, sy), WARP_THREADS, field_smem(part[2], cnt[2]), s>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+    else
+      warp_kernel<PASS_WARP, false><<<warp_grid(cnt[2], sx, sy), WARP_THREADS, field_smem(part[2], cnt[2]), s>>>(b, sx, sy, sz, nullptr, nullptr, nullptr);
+  }
   return check_launch("fsg_warp");
 }
 

@@ -76,6 +76,7 @@ class SynthEngine:
         self.nvox = int(np.prod(self.shape))
         self.tables = DeviceTables(self.device)
         self._scratch: dict = {}
+        self._batch = None
 
     # ------------------------------------------------------------------ memory
     def scratch(self, name: str, batch: int, dtype=torch.float32, numel=None) -> torch.Tensor:
@@ -87,22 +88,71 @@ class SynthEngine:
             self._scratch[key] = t
         return t
 
-    RING_SLOTS, RING_FLOATS = 8, 1 << 18
+    RING_SLOTS, RING_FLOATS = 8, 1 << 19
+
+    # ------------------------------------------------------------------ launch batching
+    def begin(self):
+        """Open a launch batch: until ``flush`` the small-parameter uploads accumulate in ONE pinned
+        ring slot and the C-ABI calls are queued, so a whole pipeline step costs one H2D copy
+        followed by its launches (all job structs are built before the first kernel starts)."""
+        if self._batch is not None:
+            raise RuntimeError("SynthEngine.begin: a launch batch is already open")
+        self._ring_init()
+        hring, dring, events, pos = self._ring
+        slot = pos[0] % self.RING_SLOTS
+        pos[0] += 1
+        if events[slot] is not None:
+            events[slot].synchronize()
+        self._batch = {"slot": slot, "used": 0, "calls": [], "keep": []}
+
+    def flush(self):
+        b, self._batch = self._batch, None
+        hring, dring, events, _ = self._ring
+        if b["used"]:
+            dring[b["slot"], : b["used"]].copy_(hring[b["slot"], : b["used"]], non_blocking=True)
+            e = torch.cuda.Event()
+            e.record()
+            events[b["slot"]] = e
+        stream = _stream()
+        for name, args in b["calls"]:
+            _lib.call(name, *args, stream)
+        self._keep_batch = b["keep"]
+
+    def _call(self, name, *args):
+        """C-ABI call on the current stream (queued while a launch batch is open)."""
+        if self._batch is not None:
+            self._batch["calls"].append((name, args))
+        else:
+            _lib.call(name, *args, _stream())
+
+    def _ring_init(self):
+        if not hasattr(self, "_ring"):
+            self._ring = (torch.empty((self.RING_SLOTS, self.RING_FLOATS), dtype=torch.float32, pin_memory=True),
+                          torch.empty((self.RING_SLOTS, self.RING_FLOATS), dtype=torch.float32, device=self.device),
+                          [None] * self.RING_SLOTS, [0])
+            self._ring_np = self._ring[0].numpy()
 
     def upload(self, arrays: list[np.ndarray]) -> list[torch.Tensor]:
         """One H2D copy for a list of small float32 host arrays; returns device views.  Staged
         through a ring of pinned slots with a matching device ring (no allocation per call)."""
         sizes = [int(a.size) for a in arrays]
         total = sum((s + 3) // 4 * 4 for s in sizes) or 4
-        if total > self.RING_FLOATS:  # oversized request: one-off buffers
+        b = self._batch
+        if b is not None and b["used"] + total <= self.RING_FLOATS:
+            hv, dev = self._ring_np[b["slot"]], self._ring[1][b["slot"]]
+            o, views = b["used"], []
+            for a, s in zip(arrays, sizes):
+                hv[o : o + s] = np.asarray(a, dtype=np.float32).reshape(-1)
+                views.append(dev[o : o + s])
+                o += (s + 3) // 4 * 4
+            b["used"] = o
+            return views
+        if total > self.RING_FLOATS or b is not None:  # oversized request: one-off buffers
             host = torch.empty(total, dtype=torch.float32, pin_memory=True)
             dev = torch.empty(total, dtype=torch.float32, device=self.device)
             ev = None
         else:
-            if not hasattr(self, "_ring"):
-                self._ring = (torch.empty((self.RING_SLOTS, self.RING_FLOATS), dtype=torch.float32, pin_memory=True),
-                              torch.empty((self.RING_SLOTS, self.RING_FLOATS), dtype=torch.float32, device=self.device),
-                              [None] * self.RING_SLOTS, [0])
+            self._ring_init()
             hring, dring, events, pos = self._ring
             slot = pos[0] % self.RING_SLOTS
             pos[0] += 1
@@ -123,6 +173,8 @@ class SynthEngine:
             e = torch.cuda.Event()
             e.record()
             self._ring[2][ev] = e
+        elif self._batch is not None:
+            self._batch["keep"].append((host, dev))  # read by launches that are still queued
         else:
             self._oversize_keep = (host, dev)
         return views
@@ -149,7 +201,7 @@ class SynthEngine:
             j.out = out[b].data_ptr()
             j.labels_out = None if labels_out is None else labels_out[b].data_ptr()
             j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_GMM, 0)
-        _lib.call("fsg_gmm", jobs, B, int(out.shape[-1]), _stream())
+        self._call("fsg_gmm", jobs, B, int(out.shape[-1]))
         self._keep = (small,)
 
     # ------------------------------------------------------------------ K2
@@ -204,16 +256,16 @@ class SynthEngine:
         didx = [b for b, p in enumerate(plans) if p.deform]
         if didx:
             dj = (_lib.WarpJob * len(didx))(*[jobs[b] for b in didx])
-            _lib.call("fsg_warp_shift", dj, len(didx), sx, sy, sz, _stream())
-        _lib.call("fsg_warp", jobs, B, sx, sy, sz, _stream())
+            self._call("fsg_warp_shift", dj, len(didx), sx, sy, sz)
+        self._call("fsg_warp", jobs, B, sx, sy, sz)
         self._keep_warp = keep
 
     def warp_coords(self, plan):
         sx, sy, sz = self.shape
         jobs, keep = self._warp_jobs([plan], None, None, None, None, epilogue=False)
-        _lib.call("fsg_warp_shift", jobs, 1, sx, sy, sz, _stream())
+        self._call("fsg_warp_shift", jobs, 1, sx, sy, sz)
         out = torch.empty((3, sx, sy, sz), dtype=torch.float32, device=self.device)
-        _lib.call("fsg_warp_coords", jobs, sx, sy, sz, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream())
+        self._call("fsg_warp_coords", jobs, sx, sy, sz, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr())
         return out
 
     # ------------------------------------------------------------------ K4a
@@ -231,7 +283,7 @@ class SynthEngine:
                     t = self.tables.taps(float(stds[a]))
                     keep.append(t)
                     j.taps[a], j.ntaps[a] = t.data_ptr(), t.numel() // 4
-        _lib.call("fsg_blur3d", jobs, B, sx, sy, sz, _stream())
+        self._call("fsg_blur3d", jobs, B, sx, sy, sz)
 
     # ------------------------------------------------------------------ K4ab (fused)
     def sepconv(self, plans, src, dst, tmp1, tmp2, positions=True):
@@ -293,8 +345,8 @@ class SynthEngine:
                 j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
                 j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_NOISE, 0)
             info.append((tuple(n), np.asarray(factors, dtype=np.float64)))
-        _lib.call("fsg_sep_compose", cjobs, 3 * B, _stream())
-        _lib.call("fsg_sepconv", jobs, B, sx, sy, sz, _stream())
+        self._call("fsg_sep_compose", cjobs, 3 * B)
+        self._call("fsg_sepconv", jobs, B, sx, sy, sz)
         self._keep_sep = taps_dev
         return info
 
@@ -323,7 +375,7 @@ class SynthEngine:
                 j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
                 j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_NOISE, 0)
             info.append((n, np.asarray(factors, dtype=np.float64)))
-        _lib.call("fsg_resample", jobs, B, sx, sy, sz, _stream())
+        self._call("fsg_resample", jobs, B, sx, sy, sz)
         return info
 
     def add_noise(self, plans, src, dst, numel=None):
@@ -335,7 +387,7 @@ class SynthEngine:
             j.noise_std = float(np.float32(p.noise_std))
             j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
             j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_NOISE, 0)
-        _lib.call("fsg_add_noise", jobs, B, self.nvox if numel is None else numel, _stream())
+        self._call("fsg_add_noise", jobs, B, self.nvox if numel is None else numel)
 
     # ------------------------------------------------------------------ K4c
     def zoom(self, src_list, src_shapes, factors_list, dst, post=0, minmax=None):
@@ -353,16 +405,18 @@ class SynthEngine:
             j.src, j.dst = src_list[b].data_ptr(), dst[b].data_ptr()
             j.minmax, j.post = mm[b].data_ptr(), post
         if post > 0:
-            _lib.call("fsg_zoom_minmax", jobs, B, sx, sy, sz, _stream())
-        _lib.call("fsg_zoom", jobs, B, sx, sy, sz, _stream())
+            self._call("fsg_zoom_minmax", jobs, B, sx, sy, sz)
+        self._call("fsg_zoom", jobs, B, sx, sy, sz)
         return mm
 
     # ------------------------------------------------------------------ misc
     def scale_intensity(self, x: torch.Tensor, out: torch.Tensor | None = None):
         out = torch.empty_like(x) if out is None else out
         mm = torch.empty(2, dtype=torch.float32, device=self.device)
-        _lib.call("fsg_minmax", x.data_ptr(), x.numel(), mm.data_ptr(), _stream())
-        _lib.call("fsg_scale_intensity", x.data_ptr(), out.data_ptr(), x.numel(), mm.data_ptr(), _stream())
+        if self._batch is not None:
+            self._batch["keep"].append(mm)
+        self._call("fsg_minmax", x.data_ptr(), x.numel(), mm.data_ptr())
+        self._call("fsg_scale_intensity", x.data_ptr(), out.data_ptr(), x.numel(), mm.data_ptr())
         return out
 
     def to_u8(self, x: torch.Tensor) -> torch.Tensor:
@@ -372,7 +426,7 @@ class SynthEngine:
             x = x.float()
         x = x.contiguous()
         out = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
-        _lib.call("fsg_f32_to_u8", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        self._call("fsg_f32_to_u8", x.data_ptr(), out.data_ptr(), x.numel())
         return out
 
     def from_u8(self, x: torch.Tensor, dtype) -> torch.Tensor:
@@ -380,9 +434,9 @@ class SynthEngine:
             return x
         out = torch.empty(x.shape, dtype=dtype, device=self.device)
         if dtype == torch.float32:
-            _lib.call("fsg_u8_to_f32", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+            self._call("fsg_u8_to_f32", x.data_ptr(), out.data_ptr(), x.numel())
         elif dtype == torch.int64:
-            _lib.call("fsg_u8_to_i64", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+            self._call("fsg_u8_to_i64", x.data_ptr(), out.data_ptr(), x.numel())
         else:
             out = self.from_u8(x, torch.float32).to(dtype)
         return out
@@ -400,6 +454,17 @@ class SynthEngine:
         buf0 = self.scratch("buf0", B)
         buf1 = self.scratch("buf1", B)
         buf2 = self.scratch("buf2", B)
+        self.begin()
+        try:
+            self._run_base(plans, seeds, segs, out_img, out_seg, scale, buf0, buf1, buf2)
+        except BaseException:
+            self._batch = None
+            raise
+        self.flush()
+        return out_img, out_seg
+
+    def _run_base(self, plans, seeds, segs, out_img, out_seg, scale, buf0, buf1, buf2):
+        B = len(plans)
         self.gmm(plans, seeds, buf0)
         rs = [b for b, p in enumerate(plans) if p.spacing is not None]
         no_rs = [b for b, p in enumerate(plans) if p.spacing is None]

@@ -72,7 +72,15 @@ class FetalSynthGen:
         return {k: self._validated_genparams(v) for k, v in d.items() if v is not None}
 
     def engine(self, shape=None):
-        return engine_for(self.device, tuple(self.shape if shape is None else shape), self.resolution)
+        eng = engine_for(self.device, tuple(self.shape if shape is None else shape), self.resolution)
+        key = (float(getattr(self.resampled, "min_resolution", 0) or 0), float(getattr(self.resampled, "max_resolution", 0) or 0))
+        if key[1] > 0 and getattr(eng, "_prewarmed", None) != key:
+            # per-device workspace built once (the reference allocates nothing up front and rebuilds its
+            # sampling grids for every sample): all resolution-simulation tables of this generator
+            for a in sorted(set(eng.shape)):
+                eng.tables.prewarm_resample(a, float(eng.resolution[eng.shape.index(a)]), key[0], key[1])
+            eng._prewarmed = key
+        return eng
 
     def _new_plan(self) -> SamplePlan:
         self._sample_counter += 1
@@ -211,18 +219,30 @@ class FetalSynthGen:
         return out, seg_out, None if dst2 is None else dst2.view(shape), params
 
     # ------------------------------------------------------------------ batched fast path
-    def sample_batch(self, segmentations, seeds, scale: bool = False, out_img=None, out_seg=None, genparams: dict = {}):
+    def sample_batch(self, segmentations, seeds, scale: bool = False, out_img=None, out_seg=None, genparams: dict = {}, sample_ids=None, base_seed: int | None = None):
         """Generate ``len(segmentations)`` independent samples with batched launches.
 
         segmentations[b]: uint8 device volume; seeds[b]: the reference's seed-path dictionary
         ``{n_sub: {mlabel: path}}`` or a list of 1..4 int8 device volumes (already selected).
         Returns (images [B,*shape] float32, segmentations [B,*shape] uint8, [params]); both
-        tensors stay on the device.  SR artifacts are not applied on this path."""
+        tensors stay on the device.  SR artifacts are not applied on this path.
+
+        sample_ids + base_seed (multi-GPU streams, ``sharding.py``): every draw of sample b becomes
+        a function of (base_seed, sample_ids[b]) — numpy is reseeded per sample and the Philox key
+        is (base_seed, sample id) — so the output does not depend on how ids are spread over ranks."""
         shape = tuple(self.shape)
         eng = self.engine(shape)
         plans, params, vols = [], [], []
         for b in range(len(segmentations)):
-            plan = self._new_plan()
+            if sample_ids is not None:
+                from ..sharding import sample_seed
+
+                sd32 = sample_seed(base_seed or 0, sample_ids[b])
+                np.random.seed(sd32)
+                torch.default_generator.manual_seed(sd32)  # CPU generator only: the small tensors (mus, control grids)
+                plan = SamplePlan(rng_seed=int(base_seed or 0), sample_id=int(sample_ids[b]))
+            else:
+                plan = self._new_plan()
             sd = seeds[b]
             if isinstance(sd, dict):
                 pr = self._draw_generate(plan, sd, shape, genparams, None)

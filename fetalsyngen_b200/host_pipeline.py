@@ -1,53 +1,126 @@
 """Host-buffer front end of the batched generator: what a data-loading process calls when the
 inputs (segmentation + seed volumes) and the outputs (image + segmentation) live in host
 memory, as in the reference's ``FetalSynthDataset.sample`` (``fetalsyngen/data/datasets.py:
-256-327``: host tensors in, ``.cpu()`` tensors out).  Pinned staging buffers, one copy stream
-per direction, events instead of host synchronisation between the stages."""
+256-327``: host tensors in, ``.cpu()`` tensors out).
+
+Software pipeline over ``depth`` buffer slots: pinned host input -> H2D (copy stream) ->
+batched generation (compute stream) -> D2H (second copy stream) -> pinned host output.  The
+three stages of consecutive steps overlap (PCIe is full duplex and the copy engines run beside
+the SMs); ordering is by CUDA events only, the host blocks in ``collect`` alone.  Per step the
+link carries 80 MiB per volume in each direction (uint8 segmentation + four int8 seed volumes
+in, float32 image + uint8 segmentation out), so the pipeline is PCIe-bound, not kernel-bound.
+"""
 from __future__ import annotations
+
+from collections import deque
 
 import numpy as np
 import torch
 
 
+class _Slot:
+    def __init__(self, batch, shape, dev):
+        shp = (batch, *shape)
+        self.h_seg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
+        self.h_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, pin_memory=True)
+        self.h_img = torch.empty(shp, dtype=torch.float32, pin_memory=True)
+        self.h_oseg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
+        self.d_seg = torch.empty(shp, dtype=torch.uint8, device=dev)
+        self.d_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, device=dev)
+        self.d_img = torch.empty(shp, dtype=torch.float32, device=dev)
+        self.d_oseg = torch.empty(shp, dtype=torch.uint8, device=dev)
+        self.in_free = None    # compute of the previous use has consumed d_seg / d_seeds
+        self.out_done = None   # D2H of the previous use has landed in h_img / h_oseg
+        self.params = None
+
+
 class HostPipeline:
-    def __init__(self, generator, batch: int):
+    def __init__(self, generator, batch: int, depth: int = 2):
         self.gen = generator
         self.B = batch
         self.shape = tuple(generator.shape)
         self.eng = generator.engine(self.shape)
         dev = self.eng.device
-        shp = (batch, *self.shape)
-        self.h_seg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
-        self.h_seeds = torch.empty((batch, 4, *self.shape), dtype=torch.int8, pin_memory=True)
-        self.h_img = torch.empty(shp, dtype=torch.float32, pin_memory=True)
-        self.h_oseg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
-        self.d_seg = torch.empty(shp, dtype=torch.uint8, device=dev)
-        self.d_seeds = torch.empty((batch, 4, *self.shape), dtype=torch.int8, device=dev)
-        self.d_img = torch.empty(shp, dtype=torch.float32, device=dev)
-        self.d_oseg = torch.empty(shp, dtype=torch.uint8, device=dev)
+        self.slots = [_Slot(batch, self.shape, dev) for _ in range(max(1, depth))]
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
-        self.h2d_bytes = self.h_seg.numel() + self.h_seeds.numel()
-        self.d2h_bytes = self.h_img.numel() * 4 + self.h_oseg.numel()
+        self.h2d_bytes = self.slots[0].h_seg.numel() + self.slots[0].h_seeds.numel()
+        self.d2h_bytes = self.slots[0].h_img.numel() * 4 + self.slots[0].h_oseg.numel()
+        self._next = 0
+        self._inflight: deque = deque()
+
+    # ------------------------------------------------------------------ inputs
+    def input_buffers(self, slot: int | None = None):
+        """Pinned (segmentation [B,*shape] uint8, seeds [B,4,*shape] int8) of the slot the next
+        ``submit`` will use: the producer writes its decoded volumes straight into them."""
+        s = self.slots[self._next % len(self.slots) if slot is None else slot]
+        return s.h_seg, s.h_seeds
 
     def set_inputs(self, segs, seeds):
-        for b in range(self.B):
-            self.h_seg[b].copy_(torch.from_numpy(np.ascontiguousarray(segs[b])))
-            for m in range(4):
-                self.h_seeds[b, m].copy_(torch.from_numpy(np.ascontiguousarray(seeds[b][m])))
+        """Copy the same host volumes into every slot (benchmark / tests)."""
+        for s in self.slots:
+            for b in range(self.B):
+                s.h_seg[b].copy_(torch.from_numpy(np.ascontiguousarray(segs[b])))
+                for m in range(4):
+                    s.h_seeds[b, m].copy_(torch.from_numpy(np.ascontiguousarray(seeds[b][m])))
 
-    def step(self, scale: bool = True):
-        """H2D inputs -> generate -> D2H outputs; returns after the outputs are in host memory."""
+    # ------------------------------------------------------------------ pipeline
+    def submit(self, scale: bool = True, **kw):
+        """Enqueue H2D -> generate -> D2H for the next slot; returns immediately."""
+        if len(self._inflight) == len(self.slots):
+            raise RuntimeError("HostPipeline: every slot is in flight; call collect() first")
+        s = self.slots[self._next % len(self.slots)]
+        self._next += 1
         cur = torch.cuda.current_stream()
-        self.s_in.wait_stream(cur)
         with torch.cuda.stream(self.s_in):
-            self.d_seg.copy_(self.h_seg, non_blocking=True)
-            self.d_seeds.copy_(self.h_seeds, non_blocking=True)
-        cur.wait_stream(self.s_in)
-        _, _, params = self.gen.sample_batch([self.d_seg[b] for b in range(self.B)], [[self.d_seeds[b, m] for m in range(4)] for b in range(self.B)], scale=scale, out_img=self.d_img, out_seg=self.d_oseg)
-        self.s_out.wait_stream(cur)
+            if s.in_free is not None:
+                self.s_in.wait_event(s.in_free)
+            s.d_seg.copy_(s.h_seg, non_blocking=True)
+            s.d_seeds.copy_(s.h_seeds, non_blocking=True)
+            loaded = torch.cuda.Event()
+            loaded.record(self.s_in)
+        cur.wait_event(loaded)
+        if s.out_done is not None:
+            cur.wait_event(s.out_done)  # d_img / d_oseg of this slot are being read by the last D2H
+        _, _, s.params = self.gen.sample_batch([s.d_seg[b] for b in range(self.B)], [[s.d_seeds[b, m] for m in range(4)] for b in range(self.B)], scale=scale,
+                                               out_img=s.d_img, out_seg=s.d_oseg, **kw)
+        s.in_free = torch.cuda.Event()
+        s.in_free.record(cur)
         with torch.cuda.stream(self.s_out):
-            self.h_img.copy_(self.d_img, non_blocking=True)
-            self.h_oseg.copy_(self.d_oseg, non_blocking=True)
-        self.s_out.synchronize()
-        return self.h_img, self.h_oseg, params
+            self.s_out.wait_event(s.in_free)
+            s.h_img.copy_(s.d_img, non_blocking=True)
+            s.h_oseg.copy_(s.d_oseg, non_blocking=True)
+            s.out_done = torch.cuda.Event()
+            s.out_done.record(self.s_out)
+        self._inflight.append(s)
+
+    def collect(self):
+        """Block until the oldest submitted step is in host memory; returns (image, segmentation,
+        params) — views of that slot's pinned buffers, valid until the slot is submitted again."""
+        s = self._inflight.popleft()
+        s.out_done.synchronize()
+        return s.h_img, s.h_oseg, s.params
+
+    def drain(self):
+        out = None
+        while self._inflight:
+            out = self.collect()
+        return out
+
+    def step(self, scale: bool = True, **kw):
+        """Unpipelined convenience: one submit followed by its collect."""
+        self.submit(scale, **kw)
+        return self.collect()
+
+    def run(self, steps: int, scale: bool = True, on_result=None, **kw):
+        """``steps`` pipelined steps; every result is in host memory when this returns."""
+        for _ in range(steps):
+            if len(self._inflight) == len(self.slots):
+                r = self.collect()
+                if on_result is not None:
+                    on_result(*r)
+            self.submit(scale, **kw)
+        while self._inflight:
+            r = self.collect()
+            if on_result is not None:
+                on_result(*r)

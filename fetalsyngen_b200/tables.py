@@ -143,5 +143,38 @@ class DeviceTables:
             self._cache[key + ("factor",)] = factor
         return t, self._cache[key + ("factor",)]
 
+    def prewarm_resample(self, n_in: int, res_in: float, min_spacing: float, max_spacing: float) -> int:
+        """Build, in one upload, every table the resolution simulation can ask for along an axis of
+        extent ``n_in``: the down-sampling positions for each reachable coarse extent n_out and the
+        ``myzoom_torch`` table that brings n_out back to n_in.  The spacing is continuous but the
+        tables only depend on (n_in, n_out), so after this call the hot loop never builds a table."""
+        lo = max(1, resample_size(n_in, res_in, max_spacing))
+        hi = min(n_in, resample_size(n_in, res_in, min_spacing))
+        todo = []
+        for n_out in range(lo, hi + 1):
+            kr = ("resample", n_in, n_out)
+            if kr not in self._cache:
+                factor = n_out / n_in
+                delta = (1.0 - factor) / (2.0 * factor)
+                v = np.arange(delta, delta + n_out / factor, 1 / factor)[:n_out]
+                todo.append((kr, _pack(v, n_in, mark_outside=True), factor))
+            back = float(1 / np.float64(n_out / n_in))
+            kz = ("zoom", n_out, back, n_in)
+            if kz not in self._cache and zoom_size(n_out, back) == n_in:
+                todo.append((kz, zoom_table(n_out, back), None))
+        if not todo:
+            return 0
+        blobs = [np.ascontiguousarray(t).view(np.uint8).reshape(-1) for _, t, _ in todo]
+        offs = np.cumsum([0] + [(b.size + 15) // 16 * 16 for b in blobs])
+        stage = np.zeros(int(offs[-1]), dtype=np.uint8)
+        for b, o in zip(blobs, offs):
+            stage[o : o + b.size] = b
+        dev = torch.from_numpy(stage).to(self.device)
+        for (key, _, factor), b, o in zip(todo, blobs, offs):
+            self._cache[key] = dev[int(o) : int(o) + b.size]
+            if factor is not None:
+                self._cache[key + ("factor",)] = factor
+        return len(todo)
+
     def taps(self, sigma: float) -> torch.Tensor:
         return self._put(("taps", float(sigma)), lambda: gaussian_taps(sigma))

@@ -8,7 +8,11 @@ seg_h, seeds_h = label_phantom(shape)
 gen = bench.build_generator(shape, dev)
 seg_d = torch.from_numpy(seg_h).to(dev); seeds_d=[torch.from_numpy(s).to(dev) for s in seeds_h]
 out_img = torch.empty((B,*shape),dtype=torch.float32,device=dev); out_seg=torch.empty((B,*shape),dtype=torch.uint8,device=dev)
-def step(): gen.sample_batch([seg_d]*B,[seeds_d]*B,scale=True,out_img=out_img,out_seg=out_seg)
+from fetalsyngen_b200.sharding import step_ids
+cnt=[0]
+def step():
+    ids=step_ids(cnt[0],B,0,1); cnt[0]+=1
+    gen.sample_batch([seg_d]*B,[seeds_d]*B,scale=True,out_img=out_img,out_seg=out_seg,sample_ids=ids,base_seed=1234)
 for _ in range(3): step()
 torch.cuda.synchronize()
 t0=time.perf_counter()
@@ -18,4 +22,4 @@ print("host ms/step", (t1-t0)*100, "incl sync", (t2-t0)*100)
 pr=cProfile.Profile(); pr.enable()
 for _ in range(10): step()
 pr.disable(); torch.cuda.synchronize()
-s=io.StringIO(); pstats.Stats(pr,stream=s).sort_stats('cumulative').print_stats(45); print(s.getvalue()[:9000])
+s=io.StringIO(); pstats.Stats(pr,stream=s).sort_stats('cumulative').print_stats(60); print(s.getvalue()[:9000])

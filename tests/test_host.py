@@ -1,0 +1,234 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports what include/fsg.h declares, the
+product has no CPU fallback and never touches oracle/, host-side logic (config instantiation,
+NIfTI codec, dataset discovery, sample sharding) and the multi-process (gloo, world_size 2)
+layout of the benchmark."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+REF_CFG = Path("/root/reference/configs")
+
+
+# ----------------------------------------------------------------------------- boundary
+def _declared():
+    text = (ROOT / "include" / "fsg.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fsg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fetalsyngen_b200 import _lib
+
+    names = _declared()
+    assert len(names) >= 30
+    assert set(names) == set(_lib.SIGNATURES), (set(names) ^ set(_lib.SIGNATURES))
+    lib = _lib.load(build_if_missing=False)  # also checks struct sizes against fsg_sizeof
+    for n in names:
+        assert hasattr(lib, n)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (fsg_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert lib.fsg_version() >= 100
+    assert isinstance(lib.fsg_last_error(), bytes)
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    from fetalsyngen_b200 import _lib
+    from fetalsyngen_b200.engine import SynthEngine
+
+    with pytest.raises(_lib.FsgError):
+        SynthEngine((8, 8, 8), (1.0, 1.0, 1.0), "cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.FsgError):
+            SynthEngine((8, 8, 8), (1.0, 1.0, 1.0), "cuda:0")
+    for p in (ROOT / "fetalsyngen_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "np_oracle" not in src and "np_motion" not in src and "np_artifacts" not in src and "ref_import" not in src, p
+
+
+def test_c_abi_argument_checks_without_a_gpu():
+    """Argument validation happens before any CUDA call: bad arguments give rc != 0 + a message."""
+    from fetalsyngen_b200 import _lib
+
+    lib = _lib.load(build_if_missing=False)
+    assert lib.fsg_slice_sums(None, 0, 0, None, None) != 0
+    assert b"fsg_slice_sums" in lib.fsg_last_error()
+    assert lib.fsg_gmm(None, 0, 0, None) != 0
+    assert lib.fsg_sizeof(b"no_such_struct") <= 0
+
+
+# ----------------------------------------------------------------------------- config
+@pytest.mark.skipif(not REF_CFG.exists(), reason="reference configs not present")
+def test_reference_yaml_builds_our_classes():
+    from fetalsyngen_b200 import config
+    from fetalsyngen_b200.generator.augmentation.artifacts import BlurCortex, SimulatedBoundaries, SimulateMotion, StructNoise
+    from fetalsyngen_b200.generator.model import FetalSynthGen
+
+    cfg = config.load_yaml(REF_CFG / "dataset/generator/default.yaml")
+    cfg["device"] = "cuda:0"
+    gen = config.instantiate(cfg)
+    assert isinstance(gen, FetalSynthGen)
+    assert list(gen.shape) == [256, 256, 256] and gen.spatial_deform.device == "cuda:0"
+    assert isinstance(gen.artifacts["blur_cortex"], BlurCortex) and isinstance(gen.artifacts["struct_noise"], StructNoise)
+    assert isinstance(gen.artifacts["simulate_motion"], SimulateMotion) and isinstance(gen.artifacts["boundaries"], SimulatedBoundaries)
+    assert gen.artifacts["simulate_motion"].recon_args.merge_params.merge_type == "perlin"
+    assert gen.artifacts["simulate_motion"].scanner_args.max_num_slices == 250
+
+
+def test_instantiate_interpolation_and_errors(tmp_path):
+    from fetalsyngen_b200 import config
+
+    cfg = {"device": "cuda:1", "inner": {"_target_": "fetalsyngen.generator.augmentation.synthseg.RandGamma", "prob": 0.5, "gamma_std": 0.1}, "d2": "${.device}",
+           "nest": {"dev": "${..device}"}}
+    out = config.instantiate(cfg)
+    assert out["d2"] == "cuda:1" and out["nest"]["dev"] == "cuda:1"
+    assert type(out["inner"]).__module__.startswith("fetalsyngen_b200.")
+    with pytest.raises(ImportError):
+        config.instantiate({"_target_": "fetalsyngen.generator.model.NoSuchClass"})
+    (tmp_path / "generator").mkdir()
+    (tmp_path / "generator/default.yaml").write_text("shape: [4, 4, 4]\ndevice: cpu\n")
+    (tmp_path / "ds.yaml").write_text("defaults:\n  - generator/default\nname: x\ngenerator:\n  device: cuda\n")
+    merged = config.load_yaml(tmp_path / "ds.yaml")
+    assert merged["generator"] == {"shape": [4, 4, 4], "device": "cuda"} and merged["name"] == "x"
+
+
+# ----------------------------------------------------------------------------- NIfTI + dataset
+def test_nifti_round_trip_and_errors(tmp_path):
+    from fetalsyngen_b200.utils import nifti
+
+    rs = np.random.RandomState(0)
+    for dt in (np.float32, np.int8, np.uint8, np.int16):
+        a = (rs.rand(5, 6, 7) * 100).astype(dt)
+        aff = np.diag([0.5, 0.5, 0.5, 1.0])
+        nifti.write_nifti(tmp_path / "a.nii.gz", a, aff)
+        b, aff2 = nifti.read_nifti(tmp_path / "a.nii.gz", with_affine=True)
+        assert b.dtype == dt and np.array_equal(a, b) and np.allclose(aff, aff2)
+    (tmp_path / "bad.nii").write_bytes(b"\x00" * 100)
+    with pytest.raises(nifti.NiftiError):
+        nifti.read_nifti(tmp_path / "bad.nii")
+
+
+def _bids(tmp_path, subs=("sub-a", "sub-b"), with_img=True):
+    from fetalsyngen_b200.utils import nifti
+
+    for s in subs:
+        d = tmp_path / "bids" / s / "anat"
+        d.mkdir(parents=True)
+        seg = np.zeros((8, 8, 8), np.float32)
+        seg[2:6, 2:6, 2:6] = 3
+        nifti.write_nifti(d / f"{s}_rec-x_T2w_dseg.nii.gz", seg, np.diag([0.5, 0.5, 0.5, 1]))
+        if with_img:
+            nifti.write_nifti(d / f"{s}_rec-x_T2w.nii.gz", seg * 10, np.diag([0.5, 0.5, 0.5, 1]))
+        for n in range(1, 3):
+            for m in range(1, 5):
+                sd = tmp_path / "seeds" / f"subclasses_{n}" / s / "anat"
+                sd.mkdir(parents=True, exist_ok=True)
+                v = np.zeros((8, 8, 8), np.int8)
+                v[m : m + 1] = 10 * m
+                nifti.write_nifti(sd / f"{s}_rec-x_T2w_dseg_mlabel_{m}.nii.gz", v, np.diag([0.5, 0.5, 0.5, 1]))
+    return tmp_path / "bids", tmp_path / "seeds"
+
+
+def test_dataset_discovery_and_errors(tmp_path):
+    from fetalsyngen_b200.data.datasets import FetalSynthDataset, FetalTestDataset
+
+    bids, seeds = _bids(tmp_path)
+    ds = FetalTestDataset(str(bids), None)
+    assert len(ds) == 2 and ds.subjects == ["sub-a", "sub-b"]
+    ds1 = FetalTestDataset(str(bids), ["sub-b", "sub-zzz"])
+    assert ds1.subjects == ["sub-b"]
+    item = ds[0]
+    assert item["image"].shape == (1, 8, 8, 8) and item["label"].shape == (1, 8, 8, 8) and item["name"] == "sub-a"
+    assert float(item["image"].max()) == 30.0 and item["label"].dtype == torch.int64  # no transforms: raw intensities (datasets.py:150-176)
+
+    class G:  # the dataset only stores the generator at construction
+        shape, resolution, device = [8, 8, 8], [0.5] * 3, "cuda:0"
+
+    sd = FetalSynthDataset(str(bids), G(), str(seeds), None, load_image=False)
+    assert len(sd) == 2
+    assert sorted(sd.seed_paths["sub-a"].keys()) == [1, 2] and sorted(sd.seed_paths["sub-a"][1].keys()) == [1, 2, 3, 4]
+    with pytest.raises(Exception):
+        FetalSynthDataset(str(bids), G(), str(tmp_path / "nope"), None)
+
+
+# ----------------------------------------------------------------------------- sharding
+def test_shard_ids_cover_and_are_disjoint():
+    from fetalsyngen_b200 import sharding as S
+
+    for world in (1, 2, 3, 8):
+        got = sorted(i for r in range(world) for i in S.shard_ids(5, 64, r, world))
+        assert got == list(range(5, 69))
+        step = sorted(i for r in range(world) for i in S.step_ids(3, 8, r, world))
+        assert step == list(range(3 * 8 * world, 4 * 8 * world))
+    with pytest.raises(ValueError):
+        S.shard_ids(0, 4, 2, 2)
+    seeds = {S.sample_seed(1234, i) for i in range(10000)}
+    assert len(seeds) > 9990 and all(0 <= s < 2**32 for s in seeds)
+    assert S.sample_seed(1, 2) != S.sample_seed(2, 1)
+
+
+_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from fetalsyngen_b200 import sharding as S
+sys.path.insert(0, os.path.join(sys.argv[1]))
+import bench
+dist.init_process_group("gloo")
+rank, world, local = S.rank_info()
+ids = [i for st in range(2) for i in S.step_ids(st, 4, rank, world)]
+sig = {}
+for i in ids:                      # the host draws of a sample depend on (base_seed, id) only
+    np.random.seed(S.sample_seed(1234, i)); torch.default_generator.manual_seed(S.sample_seed(1234, i))
+    q = bench.draw_oracle_params(np.random, (16, 16, 16))
+    sig[i] = float(q["A"].sum() + q["mus"].sum() + q["noise_std"])
+allsig = [None] * world
+dist.all_gather_object(allsig, sig)
+S.barrier()
+t = S.max_over_ranks(10.0 + rank)  # slowest rank defines the step time
+if rank == 0:
+    merged = {}
+    for d in allsig: merged.update(d)
+    print(json.dumps({"n": len(merged), "ids": sorted(merged), "max": t, "sig": [merged[k] for k in sorted(merged)]}))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.timeout(300)
+def test_two_process_gloo_layout(tmp_path):
+    """world_size 2 over gloo: ranks own disjoint ids that cover the job, per-sample draws equal the
+    single-process ones (independent of the world size), timing is the max over ranks."""
+    import json
+
+    from fetalsyngen_b200 import sharding as S
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    w = tmp_path / "worker.py"
+    w.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29531", str(w), str(ROOT)]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=280)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["ids"] == list(range(16)) and line["max"] == 11.0
+    want = []
+    for i in range(16):
+        np.random.seed(S.sample_seed(1234, i))
+        q = bench.draw_oracle_params(np.random, (16, 16, 16))
+        want.append(float(q["A"].sum() + q["mus"].sum() + q["noise_std"]))
+    assert np.allclose(line["sig"], want, rtol=0, atol=0)
+
+
+def test_bench_reference_arm_nonzero_rank_exits_without_work():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert res.returncode == 0 and res.stdout.strip() == ""
