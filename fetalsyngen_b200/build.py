@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libfsg.so"
-SOURCES = ["core.cu", "gmm.cu", "warp.cu", "blur.cu", "resample.cu", "sepconv.cu", "zoom.cu", "artifacts.cu", "motion.cu"]
+SOURCES = ["core.cu", "gmm.cu", "warp.cu", "warp_tile.cu", "blur.cu", "resample.cu", "sepconv.cu", "zoom.cu", "artifacts.cu", "motion.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -30,7 +30,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", ROOT / "include" / "fsg.h"]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "warp_common.cuh", ROOT / "include" / "fsg.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -23,67 +23,14 @@
 //   * floor(min coordinate) (the reference's crop-shift quirk) is resolved by a pre-pass over
 //     the twelve edges of the volume; the full-volume pre-pass only runs for jobs whose edges do
 //     not already prove the shift to be 0.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "warp_common.cuh"
 
 namespace fsg {
 
-constexpr int WX = 8, WY = 4;
-constexpr int WARP_THREADS = 256;
-constexpr int MAX_FZ = 32;  // control-grid extent along z kept in smem (reference: <= 0.06*S)
-constexpr int MAX_BZ = 16;  // bias-grid extent along z (reference: <= 0.02*S)
-constexpr float MAGIC = 8388608.0f;  // 2^23: x + MAGIC has a unit ulp for 0 <= x < 2^23
-
-enum { PASS_SHIFT = 0, PASS_WARP = 1, PASS_COORDS = 2 };
-
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lerp_fma(float a, float b, float w) { return __fmaf_rn(w, __fsub_rn(b, a), a); }
-
-// Packed FP32x2 (sm_100: FADD2 / FMUL2 / FFMA2 take one issue slot for two lanes).  add/sub are
-// individually rounded like their scalar forms.  ptxas contracts mul.f32x2 feeding add.f32x2 into
-// FFMA2 even under --fmad=false, so the bit-exact coordinate chain keeps its products scalar
-// (FMUL writes straight into the halves of a register pair) and packs only the adds; mul2 / fma2
-// are used on the tolerance-checked image path.
-typedef unsigned long long P2;
-__device__ __forceinline__ P2 pk(float a, float b) {
-  P2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk(P2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ P2 add2(P2 a, P2 b) {
-  P2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ P2 add2_rz(P2 a, P2 b) {
-  P2 r;
-  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ P2 sub2(P2 a, P2 b) {
-  P2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ P2 mul2(P2 a, P2 b) {
-  P2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
-  P2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
+// warp_tile.cu: TMA-staged variant; returns 0 when it launched, -1 when the batch is not eligible
+int launch_warp_tile(const fsg_warp_job* jobs, int njobs, bool epi, int sx, int sy, int sz, cudaStream_t stream);
 
 // Exact control-grid value at voxel (i,j,k): x-, y-, z-blend in myzoom_torch's order.  Used by
 // the edge pre-pass only (the main kernel stages the x/y blends in shared memory).
@@ -106,26 +53,6 @@ __device__ __forceinline__ void field_at(const fsg_warp_job& job, int i, int j, 
   fx = out[0];
   fy = out[1];
   fz = out[2];
-}
-
-// Affine part of the deformation, copied out of the kernel-parameter space once per thread.
-struct Affine {
-  float a[9], c[3];
-  __device__ __forceinline__ explicit Affine(const fsg_warp_job& job) {
-#pragma unroll
-    for (int q = 0; q < 9; ++q) a[q] = job.A[q];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) c[q] = job.c2[q];
-  }
-};
-// Clamped (not yet shifted) sample coordinate of one voxel from its centred position + field.
-__device__ __forceinline__ void affine_clamp(const Affine& t, float x1, float y1, float z1, float mx, float my, float mz, float& ii, float& jj, float& kk) {
-  ii = add_rn(add_rn(add_rn(mul_rn(t.a[0], x1), mul_rn(t.a[1], y1)), mul_rn(t.a[2], z1)), t.c[0]);
-  jj = add_rn(add_rn(add_rn(mul_rn(t.a[3], x1), mul_rn(t.a[4], y1)), mul_rn(t.a[5], z1)), t.c[1]);
-  kk = add_rn(add_rn(add_rn(mul_rn(t.a[6], x1), mul_rn(t.a[7], y1)), mul_rn(t.a[8], z1)), t.c[2]);
-  ii = fminf(fmaxf(ii, 0.f), mx);
-  jj = fminf(fmaxf(jj, 0.f), my);
-  kk = fminf(fmaxf(kk, 0.f), mz);
 }
 
 // ---------------------------------------------------------------------------------- edge pre-pass
@@ -687,6 +614,19 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
   Batch<fsg_warp_job> b;
   for (int g = 0; g < 2; ++g) {
     if (!cnt[g]) continue;
+    // FSG_WARP_TILE=1 selects the TMA-staged cubic-tile variant (warp_tile.cu).  It is parity-green
+    // but measured 2.4x slower than the full-z kernel at 256^3 (r01e: 2.17 ms vs 0.90 ms per 8
+    // volumes; one 163 KB block per SM, no overlap of the box load with the gathers), so it is
+    // opt-in until it is double-buffered.
+    static const bool use_tile = [] {
+      const char* e = getenv("FSG_WARP_TILE");
+      return e && e[0] == '1';
+    }();
+    if (use_tile) {
+      const int rc = launch_warp_tile(part[g], cnt[g], g == 0, sx, sy, sz, s);
+      if (rc == 0) continue;
+      if (rc > 0) return rc;
+    }
     if (int rc = fill_batch(b, part[g], cnt[g])) return rc;
     const dim3 grid((sy / WY) * (sx / WX), 1, cnt[g]);
     const size_t smem = field_smem(part[g], cnt[g]);
