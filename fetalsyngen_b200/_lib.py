@@ -73,11 +73,15 @@ class PerlinOctave(C.Structure):
     _fields_ = [("grad", _vp), ("lin", _vp * 3), ("res", _i32 * 3), ("amp", _f32)]
 
 
+class GridJob(C.Structure):
+    _fields_ = [("out", _vp), ("rng", Rng), ("scale", _f32), ("n", _i32)]
+
+
 class SepComposeJob(C.Structure):
     _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32)]
 
 
-_STRUCTS = {"fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
+_STRUCTS = {"fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
@@ -121,6 +125,7 @@ SIGNATURES = {
     "fsg_slice_void": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
     "fsg_recon_merge": (C.c_int, [_vp, _vp, _vp, _vp, _f32, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
+    "fsg_draw_grids": (C.c_int, [C.POINTER(GridJob), C.c_int, _vp]),
 }
 
 _lib = None

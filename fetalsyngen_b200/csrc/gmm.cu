@@ -86,9 +86,34 @@ __global__ void __launch_bounds__(256) philox_fill_kernel(fsg_rng rng, float* ou
   }
 }
 
+// Control grids drawn on the device (batched generation): out[i] = scale * N(0,1), one Philox
+// stream per job.  Replaces torch.randn on the host + an upload per sample
+// (affine_nonrigid.py:312-316 Fsmall = nonlin_std * randn, synthseg.py:170-172 bf = bf_std * randn).
+__global__ void __launch_bounds__(256) grid_draw_kernel(const __grid_constant__ Batch<fsg_grid_job> batch) {
+  const fsg_grid_job& job = batch.j[blockIdx.y];
+  const int ngroups = (job.n + 3) / 4;
+  for (int g = blockIdx.x * 256 + threadIdx.x; g < ngroups; g += gridDim.x * 256) {
+    const float4 q = philox_normal4(job.rng, (uint32_t)g);
+    const float v[4] = {q.x, q.y, q.z, q.w};
+    for (int e = 0; e < 4 && g * 4 + e < job.n; ++e) job.out[g * 4 + e] = __fmul_rn(job.scale, v[e]);
+  }
+}
+
 }  // namespace fsg
 
 using namespace fsg;
+
+extern "C" int fsg_draw_grids(const fsg_grid_job* jobs, int njobs, void* stream) {
+  Batch<fsg_grid_job> b;
+  if (int rc = fill_batch(b, jobs, njobs)) return rc;
+  int nmax = 0;
+  for (int n = 0; n < njobs; ++n) {
+    FSG_REQUIRE(jobs[n].out && jobs[n].n >= 1, "fsg_draw_grids: job %d has no output", n);
+    nmax = jobs[n].n > nmax ? jobs[n].n : nmax;
+  }
+  grid_draw_kernel<<<dim3(((nmax + 3) / 4 + 255) / 256, njobs), 256, 0, as_stream(stream)>>>(b);
+  return check_launch("fsg_draw_grids");
+}
 
 template <bool INJECT>
 static void launch_gmm(const Batch<fsg_gmm_job>& b, int nseed, dim3 grid, int64_t nvox, cudaStream_t s) {

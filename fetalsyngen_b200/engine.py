@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from .tables import DeviceTables, gaussian_taps_np, resample_size, zoom_size
 
-STAGE_GMM, STAGE_NOISE = 1, 2
+STAGE_GMM, STAGE_NOISE, STAGE_FIELD, STAGE_BIAS = 1, 2, 3, 4
 
 
 @dataclass
@@ -34,6 +34,8 @@ class SamplePlan:
     c2: np.ndarray | None = None          # float64 [3]
     center: np.ndarray | None = None      # float32 [3] = (size-1)/2
     fsmall: np.ndarray | None = None      # float32 [s0,s1,s2,3] (already scaled by nonlin_std)
+    fsmall_dev: tuple | None = None       # ((s0,s1,s2), nonlin_std): draw the control grid on the device instead
+    bf_dev: tuple | None = None           # ((b0,b1,b2), bf_std): same for the bias control grid
     gamma: float | None = None
     bf_low: np.ndarray | None = None      # float32 [b0,b1,b2] (already scaled by bf_std)
     spacing: np.ndarray | None = None     # float64 [3]
@@ -208,17 +210,36 @@ class SynthEngine:
     def _warp_jobs(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True):
         B = len(plans)
         sx, sy, sz = self.shape
-        arrays, slots = [], []
-        for p in plans:
+        arrays, slots, gjobs = [], [], []
+        for b, p in enumerate(plans):
             slot = {}
             if p.deform and p.fsmall is not None:
                 slot["f"] = len(arrays)
                 arrays.append(p.fsmall)
+            elif p.deform and p.fsmall_dev is not None:
+                gjobs.append((b, "f", p.fsmall_dev[0], 3 * int(np.prod(p.fsmall_dev[0])), p.fsmall_dev[1], STAGE_FIELD))
             if epilogue and p.bf_low is not None:
                 slot["b"] = len(arrays)
                 arrays.append(p.bf_low)
+            elif epilogue and p.bf_dev is not None:
+                gjobs.append((b, "b", p.bf_dev[0], int(np.prod(p.bf_dev[0])), p.bf_dev[1], STAGE_BIAS))
             slots.append(slot)
         small = self.upload(arrays) if arrays else []
+        dev_grid = {}
+        if gjobs:
+            # control grids drawn on the device: one launch for the whole batch, no upload
+            nf = (max([g[3] for g in gjobs if g[1] == "f"], default=0) + 3) // 4 * 4
+            nb = (max([g[3] for g in gjobs if g[1] == "b"], default=0) + 3) // 4 * 4
+            gbuf = self.scratch("grids", B, torch.float32, max(nf + nb, 4))
+            gj = (_lib.GridJob * len(gjobs))()
+            for q, (b, kind, shp, n, std, stage) in enumerate(gjobs):
+                ptr = gbuf[b].data_ptr() + (0 if kind == "f" else 4 * nf)
+                gj[q].out, gj[q].n, gj[q].scale = ptr, n, float(std)
+                gj[q].rng = _lib.Rng(plans[b].rng_seed & (2**64 - 1), plans[b].sample_id, stage, 0)
+                dev_grid[(b, kind)] = (ptr, shp)
+            for q0 in range(0, len(gjobs), _lib.MAX_JOBS):
+                chunk = (_lib.GridJob * min(_lib.MAX_JOBS, len(gjobs) - q0))(*gj[q0 : q0 + _lib.MAX_JOBS])
+                self._call("fsg_draw_grids", chunk, len(chunk))
         shift = self.scratch("shift", B, torch.float32, 4)
         jobs = (_lib.WarpJob * B)()
         keep = [small, shift]
@@ -233,17 +254,23 @@ class SynthEngine:
                 j.A = (C.c_float * 9)(*np.asarray(p.A, dtype=np.float32).reshape(-1))
                 j.c2 = (C.c_float * 3)(*np.asarray(p.c2, dtype=np.float64).astype(np.float32))
                 j.center = (C.c_float * 3)(*np.asarray(p.center, dtype=np.float32))
-                if "f" in slots[b]:
-                    fs = p.fsmall.shape[:3]
-                    j.fsmall = small[slots[b]["f"]].data_ptr()
+                if "f" in slots[b] or (b, "f") in dev_grid:
+                    if "f" in slots[b]:
+                        fs = p.fsmall.shape[:3]
+                        j.fsmall = small[slots[b]["f"]].data_ptr()
+                    else:
+                        j.fsmall, fs = dev_grid[(b, "f")]
                     j.fs = (C.c_int32 * 3)(*fs)
                     for a in range(3):
                         j.ftab[a] = self.tables.zoom(fs[a], self.shape[a] / fs[a], self.shape[a]).data_ptr()
             if epilogue and p.gamma is not None:
                 j.has_gamma, j.gamma = 1, float(np.float32(p.gamma))
-            if "b" in slots[b]:
-                bs = p.bf_low.shape
-                j.bf_low = small[slots[b]["b"]].data_ptr()
+            if "b" in slots[b] or (b, "b") in dev_grid:
+                if "b" in slots[b]:
+                    bs = p.bf_low.shape
+                    j.bf_low = small[slots[b]["b"]].data_ptr()
+                else:
+                    j.bf_low, bs = dev_grid[(b, "b")]
                 j.bs = (C.c_int32 * 3)(*bs)
                 for a in range(3):
                     j.btab[a] = self.tables.zoom(bs[a], self.shape[a] / bs[a], self.shape[a]).data_ptr()

@@ -92,14 +92,17 @@ class RandBiasField(RandTransform):
         self.std_min = std_min
         self.std_max = std_max
 
-    def draw(self, image_size, genparams: dict = {}, inject: dict | None = None):
-        """Returns (bf_low float32 grid | None, params dict)   (synthseg.py:157-176)."""
+    def draw(self, image_size, genparams: dict = {}, inject: dict | None = None, device_grids: bool = False):
+        """Returns (bf_low float32 grid | None, params dict)   (synthseg.py:157-176).  device_grids: return
+        ((size, std), params) instead; the grid is then drawn on the device (fsg_draw_grids)."""
         if not (np.random.rand() < self.prob or len(genparams.keys()) > 0):
             return None, {"bf_scale": None, "bf_std": None, "bf_size": None}
         bf_scale = self.scale_min + np.random.rand(1) * (self.scale_max - self.scale_min) if "bf_scale" not in genparams.keys() else genparams["bf_scale"]
         bf_size = np.round(bf_scale * np.array(image_size)).astype(int)
         bf_size = np.maximum(bf_size, 1).tolist()
         bf_std = self.std_min + (self.std_max - self.std_min) * np.random.rand(1) if "bf_std" not in genparams.keys() else genparams["bf_std"]
+        if device_grids and not (inject and "bf_n" in inject):
+            return (tuple(int(v) for v in bf_size), float(np.asarray(bf_std, dtype=np.float32).reshape(-1)[0])), {"bf_scale": bf_scale, "bf_std": bf_std, "bf_size": bf_size}
         if inject and "bf_n" in inject:
             n = np.asarray(inject["bf_n"], dtype=np.float32)
         else:

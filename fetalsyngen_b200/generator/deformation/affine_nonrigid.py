@@ -42,7 +42,7 @@ class SpatialDeformation:
         self.device = device
 
     # ------------------------------------------------------------------ host draws
-    def draw(self, image_shape, genparams: dict = {}, inject: dict | None = None, random_shift: bool = True):
+    def draw(self, image_shape, genparams: dict = {}, inject: dict | None = None, random_shift: bool = True, device_grids: bool = False):
         """Draw gate, flip, affine and control grid in the reference's RNG order
         (affine_nonrigid.py:140-145, 249-324).  Returns (plan_fields dict, deform_params dict)."""
         inject = inject or {}
@@ -77,11 +77,15 @@ class SpatialDeformation:
             nonlin_scale = (self.nonlin_scale_min + np.random.rand(1) * (self.nonlin_scale_max - self.nonlin_scale_min)) if "nonlin_scale" not in nr.keys() else nr["nonlin_scale"]
             size_F_small = np.round(nonlin_scale * np.array(image_shape)).astype(int).tolist() if "size_F_small" not in nr.keys() else nr["size_F_small"]
             nonlin_std = self.nonlin_std_max * np.random.rand() if "nonlin_std" not in nr.keys() else nr["nonlin_std"]
-            if "Fsmall_n" in inject:
-                n = np.asarray(inject["Fsmall_n"], dtype=np.float32)
+            if device_grids and "Fsmall_n" not in inject:
+                # batched generator: the control grid is drawn on the device (fsg_draw_grids)
+                fields["fsmall_dev"] = (tuple(int(v) for v in size_F_small), float(np.float32(nonlin_std)))
             else:
-                n = torch.randn([*size_F_small, 3], dtype=torch.float).numpy()
-            fields["fsmall"] = (np.float32(nonlin_std) * n).astype(np.float32)
+                if "Fsmall_n" in inject:
+                    n = np.asarray(inject["Fsmall_n"], dtype=np.float32)
+                else:
+                    n = torch.randn([*size_F_small, 3], dtype=torch.float).numpy()
+                fields["fsmall"] = (np.float32(nonlin_std) * n).astype(np.float32)
             non_rigid_params = {"nonlin_scale": nonlin_scale, "nonlin_std": nonlin_std, "size_F_small": size_F_small}
         params = {
             "affine": {"rotations": rotations, "shears": shears, "scalings": scalings},

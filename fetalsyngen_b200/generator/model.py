@@ -87,7 +87,7 @@ class FetalSynthGen:
         return SamplePlan(rng_seed=int(torch.randint(0, 2**62, (1,)).item()), sample_id=self._sample_counter)
 
     # ------------------------------------------------------------------ draws
-    def _draw_generate(self, plan, seeds, shape, genparams, inject):
+    def _draw_generate(self, plan, seeds, shape, genparams, inject, device_grids: bool = False):
         ig = self.intensity_generator
         params = {}
         if seeds is not None:
@@ -98,15 +98,19 @@ class FetalSynthGen:
         else:
             params["selected_seeds"] = {}
             params["seed_intensities"] = {}
-        fields, deform_params = self.spatial_deform.draw(shape, genparams.get("deform_params", {}), inject)
+        fields, deform_params = self.spatial_deform.draw(shape, genparams.get("deform_params", {}), inject, device_grids=device_grids)
         for k, v in fields.items():
             setattr(plan, k, v)
         params["deform_params"] = deform_params
         return params
 
-    def _draw_augment(self, plan, shape, genparams, inject):
+    def _draw_augment(self, plan, shape, genparams, inject, device_grids: bool = False):
         plan.gamma = self.gamma.draw(genparams.get("gamma_params", {}))
-        plan.bf_low, bf_params = self.biasfield.draw(shape, genparams.get("bf_params", {}), inject)
+        bf, bf_params = self.biasfield.draw(shape, genparams.get("bf_params", {}), inject, device_grids=device_grids)
+        if isinstance(bf, tuple):
+            plan.bf_dev = bf
+        else:
+            plan.bf_low = bf
         plan.spacing, plan.stds = self.resampled.draw(np.array(self.resolution), genparams.get("resample_params", {}), inject)
         plan.noise_std = self.noise.draw(genparams.get("noise_params", {}))
         return {
@@ -245,13 +249,13 @@ class FetalSynthGen:
                 plan = self._new_plan()
             sd = seeds[b]
             if isinstance(sd, dict):
-                pr = self._draw_generate(plan, sd, shape, genparams, None)
+                pr = self._draw_generate(plan, sd, shape, genparams, None, device_grids=True)
                 vols.append([v.view(-1) for v in plan.meta["seed_vols"]])
             else:
-                pr = self._draw_generate(plan, None, shape, genparams, None)
+                pr = self._draw_generate(plan, None, shape, genparams, None, device_grids=True)
                 plan.mus, plan.sigmas = self.intensity_generator.draw_gmm(genparams.get("seed_intensities", {}))
                 vols.append([v.view(-1) for v in sd])
-            pr.update(self._draw_augment(plan, shape, genparams, None))
+            pr.update(self._draw_augment(plan, shape, genparams, None, device_grids=True))
             plans.append(plan)
             params.append(pr)
         img, seg = eng.run_base(plans, vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)

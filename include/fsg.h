@@ -312,6 +312,18 @@ int fsg_slice_void(float* slices, int h, int w, const int32_t* idx, const float*
  * with minmax = [2] device floats (NULL: weight_raw is used as is); weight_raw NULL: no merge. */
 int fsg_recon_merge(const float* rec, const float* gt, const float* weight_raw, const float* minmax, float increase, int smooth, int D, int H, int W, float* out, void* stream);
 
+/* Control grids of a batch drawn on the device: out[i] = scale * N(0,1) from the job's Philox
+ * stream.  Used by the batched generator for the deformation control grid (Fsmall = nonlin_std *
+ * randn, affine_nonrigid.py:312-316) and the bias control grid (synthseg.py:170-172) instead of a
+ * host draw + upload per sample.  At most FSG_MAX_JOBS jobs per call. */
+typedef struct fsg_grid_job {
+  float* out;
+  fsg_rng rng;
+  float scale;
+  int32_t n;
+} fsg_grid_job;
+int fsg_draw_grids(const fsg_grid_job* jobs_host, int njobs, void* stream);
+
 /* RNG self-test: fills out[n] with Philox standard normals exactly as the kernels draw them;
  * raw != 0 writes the raw 32-bit words instead (for the Random123 known-answer test). */
 int fsg_philox_fill(fsg_rng rng, float* out, int64_t n, int raw, void* stream);

@@ -317,3 +317,41 @@ def test_warp_kernel_variants_agree(monkeypatch):
     assert "tile (" not in res.stdout  # no box-bound violations reported by the debug check
     err = float(res.stdout.split("ERR")[1])
     assert err <= TOL
+
+
+def test_sample_batch_streams_do_not_depend_on_the_sharding():
+    """sample ids generated as one batch or split over two 'ranks' give bit-identical volumes:
+    every draw is a function of (base_seed, sample id) (sharding.py), including the control grids
+    drawn on the device."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+    from fetalsyngen_b200.sharding import shard_ids
+    from fetalsyngen_b200.utils.phantom import label_phantom
+
+    shape = (64, 64, 64)
+    seg_h, seeds_h = label_phantom(shape)
+    gen = bench.build_generator(shape, DEV)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+
+    def run(ids):
+        img, seg, params = gen.sample_batch([seg_d] * len(ids), [seeds_d] * len(ids), scale=True, sample_ids=ids, base_seed=77)
+        return {i: (img[n].clone(), seg[n].clone(), params[n]) for n, i in enumerate(ids)}
+
+    whole = run([0, 1, 2, 3])
+    parts = {}
+    for r in range(2):
+        parts.update(run(shard_ids(0, 4, r, 2)))
+    for i in range(4):
+        assert torch.equal(whole[i][0], parts[i][0]) and torch.equal(whole[i][1], parts[i][1])
+        assert whole[i][2]["gamma_params"] == parts[i][2]["gamma_params"]
+    assert not torch.equal(whole[0][0], whole[1][0])
+    again = run([3])
+    assert torch.equal(again[3][0], whole[3][0])
+    for i in range(4):  # sanity of the generated data
+        v = whole[i][0]
+        assert torch.isfinite(v).all() and float(v.min()) == 0.0 and float(v.max()) == 1.0
+        assert set(torch.unique(whole[i][1]).tolist()) <= set(range(8))
