@@ -279,7 +279,7 @@ def run_ours(args, shape):
     from fetalsyngen_b200.host_pipeline import HostPipeline
 
     e2e_steps = 0 if args.no_e2e else args.steps  # --no-e2e: profiling runs only
-    hp = HostPipeline(gen, B, depth=2 if e2e_steps else 1)
+    hp = HostPipeline(gen, B, depth=args.depth if e2e_steps else 1)
     hp.set_inputs([seg_h] * B, [seeds_h] * B)
     sink = [0.0]
 
@@ -287,7 +287,7 @@ def run_ours(args, shape):
         sink[0] += float(h_img[0, 0, 0, 0]) + float(h_seg[-1, -1, -1, -1])  # the host reads the step's result
 
     if e2e_steps:
-        hp.run(2, on_result=consume)
+        hp.run(args.depth, on_result=consume)
     barrier()
     t0 = time.perf_counter()
     hp.run(e2e_steps, on_result=consume)  # returns when every step's image + segmentation is in host memory
@@ -347,6 +347,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=3, help="buffer slots of the host pipeline (e2e leg)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
     shape = (args.shape,) * 3

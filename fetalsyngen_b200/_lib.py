@@ -126,6 +126,7 @@ SIGNATURES = {
     "fsg_recon_merge": (C.c_int, [_vp, _vp, _vp, _vp, _f32, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
     "fsg_draw_grids": (C.c_int, [C.POINTER(GridJob), C.c_int, _vp]),
+    "fsg_fetch_params": (C.c_int, [_vp, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -120,6 +120,23 @@ int fsg_sizeof(const char* name) {
   return -1;
 }
 
+// Small-parameter fetch: an SM copy from (mapped, pinned) host memory into the device ring.  A
+// cudaMemcpyAsync would queue on the H2D copy engine behind the bulk input transfers of the next
+// pipeline steps (FIFO across streams) and stall this step's kernels for tens of milliseconds.
+__global__ void __launch_bounds__(256) fetch_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int n4) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) dst[i] = src[i];
+}
+
+int fsg_fetch_params(const float* src_host_mapped, float* dst, int64_t nfloats, void* stream) {
+  FSG_REQUIRE(src_host_mapped && dst && nfloats >= 0 && nfloats < ((int64_t)1 << 30), "fsg_fetch_params: bad arguments");
+  FSG_REQUIRE(((reinterpret_cast<uintptr_t>(src_host_mapped) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "fsg_fetch_params: buffers must be 16-byte aligned");
+  if (nfloats == 0) return 0;
+  const int n4 = (int)((nfloats + 3) / 4);
+  const int want = (n4 + 255) / 256;
+  fetch_kernel<<<want < 148 ? want : 148, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src_host_mapped), reinterpret_cast<float4*>(dst), n4);
+  return check_launch("fsg_fetch_params");
+}
+
 int fsg_f32_to_u8(const float* x, uint8_t* out, int64_t n, void* stream) { return convert(x, out, n, stream, "fsg_f32_to_u8"); }
 int fsg_u8_to_f32(const uint8_t* x, float* out, int64_t n, void* stream) { return convert(x, out, n, stream, "fsg_u8_to_f32"); }
 int fsg_u8_to_i64(const uint8_t* x, int64_t* out, int64_t n, void* stream) { return convert(x, out, n, stream, "fsg_u8_to_i64"); }

@@ -110,12 +110,13 @@ class SynthEngine:
     def flush(self):
         b, self._batch = self._batch, None
         hring, dring, events, _ = self._ring
+        stream = _stream()
         if b["used"]:
-            dring[b["slot"], : b["used"]].copy_(hring[b["slot"], : b["used"]], non_blocking=True)
+            # SM fetch from the pinned (device-mapped) ring, not a copy-engine transfer: see fsg_fetch_params
+            _lib.call("fsg_fetch_params", hring[b["slot"]].data_ptr(), dring[b["slot"]].data_ptr(), b["used"], stream)
             e = torch.cuda.Event()
             e.record()
             events[b["slot"]] = e
-        stream = _stream()
         for name, args in b["calls"]:
             _lib.call(name, *args, stream)
         self._keep_batch = b["keep"]
@@ -168,7 +169,7 @@ class SynthEngine:
             hv[o : o + s] = np.asarray(a, dtype=np.float32).reshape(-1)
             views.append(dev[o : o + s])
             o += (s + 3) // 4 * 4
-        dev.copy_(host, non_blocking=True)
+        _lib.call("fsg_fetch_params", host.data_ptr(), dev.data_ptr(), total, _stream())
         if ev is not None:
             # host slot: reusable once this copy has run; device slot: later copies into it are
             # stream-ordered after the kernels that read it (everything runs on the current stream)

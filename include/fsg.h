@@ -312,6 +312,11 @@ int fsg_slice_void(float* slices, int h, int w, const int32_t* idx, const float*
  * with minmax = [2] device floats (NULL: weight_raw is used as is); weight_raw NULL: no merge. */
 int fsg_recon_merge(const float* rec, const float* gt, const float* weight_raw, const float* minmax, float increase, int smooth, int D, int H, int W, float* out, void* stream);
 
+/* Copies nfloats (rounded up to 4) from pinned, device-mapped host memory into device memory with
+ * an SM kernel instead of the copy engine: the per-step parameter block must not queue behind the
+ * bulk H2D transfers of later pipeline steps.  Both pointers 16-byte aligned. */
+int fsg_fetch_params(const float* src_host_mapped, float* dst, int64_t nfloats, void* stream);
+
 /* Control grids of a batch drawn on the device: out[i] = scale * N(0,1) from the job's Philox
  * stream.  Used by the batched generator for the deformation control grid (Fsmall = nonlin_std *
  * randn, affine_nonrigid.py:312-316) and the bias control grid (synthseg.py:170-172) instead of a
