@@ -168,7 +168,30 @@ def run_reference(args, shape):
 
 
 # ---------------------------------------------------------------------------------- our arm
-def build_generator(shape, device):
+def default_artifacts(prob=1.0):
+    """The four SR-artifact stages with the reference's default parameters
+    (configs/dataset/generator/default.yaml:58-142), probabilities forced to `prob`."""
+    from fetalsyngen_b200.generator.artifacts.utils import ReconMergeParams, ReconParams, ScannerParams, StructNoiseMergeParams
+    from fetalsyngen_b200.generator.augmentation.artifacts import BlurCortex, SimulatedBoundaries, SimulateMotion, StructNoise
+
+    smp = StructNoiseMergeParams(merge_type="perlin", gauss_nloc_min=5, gauss_nloc_max=15, gauss_sigma_mu=25, gauss_sigma_std=5, perlin_res_list=[1, 2],
+                                 perlin_octaves_list=[1, 2, 4], perlin_persistence=0.5, perlin_lacunarity=2, perlin_increase_size=0.1)
+    sp = ScannerParams(resolution_slice_fac_min=0.5, resolution_slice_fac_max=2, resolution_slice_max=1.5, slice_thickness_min=1.5, slice_thickness_max=3.5, gap_min=1.5,
+                       gap_max=5.5, min_num_stack=2, max_num_stack=6, max_num_slices=250, noise_sigma_min=0, noise_sigma_max=0.1, TR_min=1, TR_max=2, prob_void=0.2,
+                       prob_gamma=0.1, gamma_std=0.05, slice_size=None, restrict_transform=False, txy=3.0)
+    rmp = ReconMergeParams(merge_type="perlin", perlin_res_list=[1, 2], perlin_octaves_list=[1, 2, 4], perlin_persistence=0.5, perlin_lacunarity=2, gauss_ngaussians_min=2,
+                           gauss_ngaussians_max=4, perlin_increase_size=0.25)
+    rp = ReconParams(prob_misreg_slice=0.1, slices_misreg_ratio=0.1, prob_misreg_stack=0.1, txy=3.0, prob_merge=1.0, merge_params=rmp, prob_smooth=0.2, prob_rm_slices=0.3,
+                     rm_slices_min=0.1, rm_slices_max=0.4)
+    return dict(
+        blur_cortex=BlurCortex(prob, 2, 50, 200, 3, 1, 2, 1),
+        struct_noise=StructNoise(prob, 3, 0.2, 0.4, smp, 1, 5),
+        simulate_motion=SimulateMotion(prob, sp, rp),
+        boundaries=SimulatedBoundaries(1.0 - prob, 1.0 if prob >= 1 else 0.5, 1.0 if prob >= 1 else 0.5),
+    )
+
+
+def build_generator(shape, device, artifacts=None):
     from fetalsyngen_b200.generator.augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
     from fetalsyngen_b200.generator.deformation.affine_nonrigid import SpatialDeformation
     from fetalsyngen_b200.generator.intensity.rand_gmm import ImageFromSeeds
@@ -181,7 +204,7 @@ def build_generator(shape, device):
         intensity_generator=ImageFromSeeds(1, 6, labels, classes),
         spatial_deform=SpatialDeformation(20, 0.02, 0.1, list(shape), 1.0, True, 0.03, 0.06, 4, 0.5, device),
         resampler=RandResample(1.0, 0.5, 1.5), bias_field=RandBiasField(1.0, 0.004, 0.02, 0.01, 0.3),
-        noise=RandNoise(1.0, 5, 15), gamma=RandGamma(1.0, 0.1),
+        noise=RandNoise(1.0, 5, 15), gamma=RandGamma(1.0, 0.1), **(artifacts or {}),
     )
 
 

@@ -1,0 +1,182 @@
+#!/usr/bin/env python
+"""Secondary measurements of BASELINE.json (one JSON line each, CUDA-event timed):
+
+  --config artifacts   configs[2]: full pipeline with the four SR artifacts forced on at 256^3,
+                       per-artifact milliseconds through the reference-shaped call
+                       (artifact(output, seg, device, genparams, resolution=...)).
+  --config sweep       configs[3]: 128^3 / 256^3 / 384^3 with the fixed mid-range parameters of
+                       SURVEY.md section 8(d) C4; the warp, the fused blur+down-sample and the
+                       up-sample kernels alone, batch 1 and 8, GB/s of algorithmic bytes against the
+                       measured HBM peak.
+
+    python tools/bench_configs.py --config sweep > profiles/r01_sweep.jsonl
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import bench  # noqa: E402
+from fetalsyngen_b200 import _lib  # noqa: E402
+from fetalsyngen_b200.engine import SamplePlan, engine_for  # noqa: E402
+from fetalsyngen_b200.tables import make_affine_matrix, resample_size, resample_stds  # noqa: E402
+from fetalsyngen_b200.utils.phantom import label_phantom  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timed(fn, reps=5, warm=2):
+    """Wall-to-wall device time of fn (CUDA events around the whole call sequence, host gaps included)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def timed_kernels(fn, reps=5, warm=2, before=None):
+    """Device time of the C-ABI calls fn makes (CUDA events bracket each call: the host-side job
+    building between launches is not counted).  Returns (ms per fn, {entry point: ms per fn})."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    _lib.stats.reset()
+    for _ in range(reps):
+        if before is not None:
+            before()
+        torch.cuda.synchronize()
+        _lib.stats.timing = True
+        fn()
+        _lib.stats.timing = False
+    per = {k: v[1] / reps for k, v in _lib.stats.elapsed_ms().items()}
+    _lib.stats.reset()
+    return sum(per.values()), per
+
+
+def flush_l2(buf=[None]):
+    if buf[0] is None:
+        buf[0] = torch.empty(256 * 2**20, dtype=torch.uint8, device=DEV)
+    buf[0].fill_(1)
+
+
+def run_artifacts(args):
+    shape = (args.shape,) * 3
+    seg_h, seeds_h = label_phantom(shape)
+    arts = bench.default_artifacts(1.0)
+    gen = bench.build_generator(shape, DEV)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    np.random.seed(0)
+    torch.manual_seed(0)
+    img, seg, _ = gen.sample_batch([seg_d], [seeds_d], scale=False, sample_ids=[0], base_seed=1)
+    out, segf = img[0], seg[0].float()
+    res = {}
+    for name, art in arts.items():
+        times = []
+        for rep in range(args.reps + 1):
+            np.random.seed(10 + rep)
+            torch.manual_seed(10 + rep)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            y, meta = art(out, segf, DEV, {}, resolution=[0.5, 0.5, 0.5])
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+            assert y.shape == out.shape and bool(torch.isfinite(y).all())
+        res[name] = {"ms_mean": float(np.mean(times[1:])), "ms_min": float(np.min(times[1:])), "ms_max": float(np.max(times[1:])), "first_call_ms": times[0]}
+    base = timed(lambda: gen.sample_batch([seg_d], [seeds_d], scale=False, sample_ids=[0], base_seed=1), reps=5)
+    total = base + sum(v["ms_mean"] for v in res.values())
+    print(json.dumps({"config": "configs[2]: full pipeline + 4 SR artifacts forced on", "shape": list(shape), "base_pipeline_ms": base, "artifacts_ms": res,
+                      "volumes_per_s_single_stream": 1000.0 / total, "reps": args.reps, "note": "device time of the reference-shaped per-sample calls (batch 1); host draws included"}))
+
+
+def sweep_plan(S, rs):
+    """Fixed mid-range parameters of SURVEY.md 8(d) C4."""
+    shape = (S, S, S)
+    res = 0.5 * 256 / S
+    p = SamplePlan(mus=(25 + 200 * rs.rand(50)).astype(np.float32), sigmas=(5 + 20 * rs.rand(50)).astype(np.float32), rng_seed=1, sample_id=int(rs.randint(1 << 30)))
+    rot = np.array([10.0, -7.0, 5.0]) / 180 * np.pi
+    p.deform, p.flip = True, False
+    p.A = make_affine_matrix(rot, np.array([0.01, -0.01, 0.005]), np.array([1.05, 0.95, 1.0])).astype(np.float32)
+    p.c2 = (np.array(shape) - 1) / 2
+    p.center = ((np.array(shape) - 1) / 2).astype(np.float32)
+    s = int(round(0.045 * S))
+    p.fsmall = (2.0 * rs.randn(s, s, s, 3)).astype(np.float32)
+    p.gamma = 1.05
+    p.bf_low = (0.15 * rs.randn(3, 3, 3)).astype(np.float32)
+    p.spacing = np.array([2 * res] * 3)
+    p.stds = resample_stds(p.spacing, [res] * 3, 0.5)  # (0.85 + 0.3 * 0.5) = 1.0 -> sigma = 2 ln5 / pi voxels
+    p.noise_std = 10.0
+    return p, res
+
+
+def run_sweep(args):
+    peak, _ = bench.peaks()
+    for S in args.sizes:
+        shape = (S, S, S)
+        N = S**3
+        seg_h, seeds_h = label_phantom(shape)
+        seg_d = torch.from_numpy(seg_h).to(DEV).view(-1)
+        seeds_d = [torch.from_numpy(s).to(DEV).view(-1) for s in seeds_h]
+        for B in args.batches:
+            rs = np.random.RandomState(S + B)
+            plans, res = [], None
+            for _ in range(B):
+                p, res = sweep_plan(S, rs)
+                plans.append(p)
+            eng = engine_for(DEV, shape, (res,) * 3)
+            buf = [torch.empty((B, N), dtype=torch.float32, device=DEV) for _ in range(4)]
+            oseg = torch.empty((B, N), dtype=torch.uint8, device=DEV)
+            eng.gmm(plans, [seeds_d] * B, buf[0])
+            n = resample_size(S, res, 2 * res)
+            f3 = (n / S) ** 3
+            cases = {
+                "fsg_gmm (seed sum + GMM + Philox)": (lambda: eng.gmm(plans, [seeds_d] * B, buf[0]), 8),
+                "fsg_warp (deform + trilinear + nearest + gamma + bias)": (lambda: eng.warp(plans, buf[0], [seg_d] * B, buf[1], oseg), 10),
+                "fsg_sepconv (blur o down-sample + noise)": (lambda: eng.sepconv(plans, buf[1], buf[2], buf[2], buf[3]), 4 * (1 + f3)),
+            }
+            info = eng.sepconv(plans, buf[1], buf[2], buf[2], buf[3])
+            cases["fsg_zoom_minmax + fsg_zoom (up-sample, /max, ScaleIntensity)"] = (
+                lambda: eng.zoom([buf[2][b] for b in range(B)], [i[0] for i in info], [1 / i[1] for i in info], [buf[3][b] for b in range(B)], post=2), 4 * (1 + f3))
+            cases["whole base pipeline (run_base)"] = (lambda: eng.run_base(plans, [seeds_d] * B, [seg_d] * B, scale=True), 8 + 10 + 4 * (1 + f3) * 2)
+            for name, (fn, bytes_per_voxel) in cases.items():
+                small = B * N * 4 < 200 * 2**20  # working set below L2: flush between iterations
+                ms, per = timed_kernels(fn, reps=args.reps, before=flush_l2 if small else None)
+                algo = bytes_per_voxel * N * B
+                print(json.dumps({"config": "configs[3] sweep", "shape": S, "batch": B, "kernel": name, "ms": round(ms, 4), "algorithmic_bytes": int(algo),
+                                  "GBps": round(algo / ms / 1e6, 1), "frac_of_measured_hbm_peak": round(algo / ms / 1e6 / peak, 4), "volumes_per_s": round(B * 1000 / ms, 1),
+                                  "coarse_grid": n, "l2": "flushed between iterations" if small else "working set > L2", "per_entry_ms": {k: round(v, 4) for k, v in per.items()}}))
+            del buf, oseg
+            torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", choices=["artifacts", "sweep"], required=True)
+    ap.add_argument("--shape", type=int, default=256)
+    ap.add_argument("--sizes", type=int, nargs="+", default=[128, 256, 384])
+    ap.add_argument("--batches", type=int, nargs="+", default=[1, 8])
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("needs a CUDA device")
+    _lib.load()
+    (run_artifacts if args.config == "artifacts" else run_sweep)(args)
+
+
+if __name__ == "__main__":
+    main()
