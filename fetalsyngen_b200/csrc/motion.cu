@@ -17,6 +17,8 @@
 // adjoint : two passes over the taps per pixel (normalisation weight, then scatter of
 //           psf/weight * s to the nearest voxel with red.global.add) + equalisation vol /= weight.
 //           Summation order of the atomics is not deterministic (same as the reference).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fsg {
@@ -105,13 +107,93 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const flo
   if (weight > 0.f) slices[((size_t)in * h + iy) * w + ix] = __fdiv_rn(val, weight);
 }
 
+// Warp-per-pixel acquisition for large PSFs: the lanes split the taps of one pixel (consecutive taps
+// sample neighbouring voxels: coalesced gathers), partial sums are reduced with shuffles.  Summation
+// order differs from the sequential tap loop (float tolerance).
+__global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_warp_kernel(const float* __restrict__ transforms, const float* __restrict__ vol, const float4* __restrict__ taps, int ntaps,
+                                                                             float radius, float* __restrict__ slices, int h, int w, int D, int H, int W, float res) {
+  extern __shared__ float4 s_tap[];
+  const int in = blockIdx.z;
+  const float* t = transforms + in * 12;
+  const int tid = threadIdx.y * ACQ_TILE + threadIdx.x;
+  for (int p = tid; p < ntaps; p += ACQ_TILE * ACQ_TILE) {
+    const float4 q = taps[p];
+    float x = t[0] * q.x;
+    x = x + t[1] * q.y;
+    x = x + t[2] * q.z;
+    float y = t[4] * q.x;
+    y = y + t[5] * q.y;
+    y = y + t[6] * q.z;
+    float z = t[8] * q.x;
+    z = z + t[9] * q.y;
+    z = z + t[10] * q.z;
+    s_tap[p] = make_float4(x, y, z, q.w);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int Sy = W, Sz = H * W;
+  const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
+  const int my_ix = blockIdx.x * ACQ_TILE + (lane & 15), my_iy = blockIdx.y * ACQ_TILE + 2 * warp + (lane >> 4);
+  const bool inside = my_ix < w && my_iy < h;
+  const SliceGeom mine = slice_geom(t, inside ? my_ix : 0, inside ? my_iy : 0, h, w, D, H, W, res);
+  const bool keep = inside && !(mine.xc + radius < 0.f || mine.yc + radius < 0.f || mine.zc + radius < 0.f || mine.xc - radius >= mx || mine.yc - radius >= my || mine.zc - radius >= mz);
+  unsigned todo = __ballot_sync(0xffffffffu, keep);
+  float my_out = 0.f;
+  bool my_set = false;
+  while (todo) {
+    const int q = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const float xc = __shfl_sync(0xffffffffu, mine.xc, q), yc = __shfl_sync(0xffffffffu, mine.yc, q), zc = __shfl_sync(0xffffffffu, mine.zc, q);
+    float val = 0.f, weight = 0.f;
+    for (int p = lane; p < ntaps; p += 32) {
+      const float4 o = s_tap[p];
+      const float x = xc + o.x, y = yc + o.y, z = zc + o.z;
+      if (x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz) continue;
+      const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+      const float wx = x - fx, wy = y - fy, wz = z - fz;
+      const float* v = vol + ((int)fz * Sz + (int)fy * Sy + (int)fx);
+      const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
+      const float p000 = ux * uy * uz * o.w, p100 = wx * uy * uz * o.w, p010 = ux * wy * uz * o.w, p001 = ux * uy * wz * o.w;
+      const float p110 = wx * wy * uz * o.w, p101 = wx * uy * wz * o.w, p011 = ux * wy * wz * o.w, p111 = wx * wy * wz * o.w;
+      val += p000 * __ldg(v);
+      weight += p000;
+      val += p100 * __ldg(v + 1);
+      weight += p100;
+      val += p010 * __ldg(v + Sy);
+      weight += p010;
+      val += p001 * __ldg(v + Sz);
+      weight += p001;
+      val += p110 * __ldg(v + 1 + Sy);
+      weight += p110;
+      val += p101 * __ldg(v + 1 + Sz);
+      weight += p101;
+      val += p011 * __ldg(v + Sy + Sz);
+      weight += p011;
+      val += p111 * __ldg(v + Sy + Sz + 1);
+      weight += p111;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      val += __shfl_xor_sync(0xffffffffu, val, o);
+      weight += __shfl_xor_sync(0xffffffffu, weight, o);
+    }
+    if (lane == q && weight > 0.f) {
+      my_out = __fdiv_rn(val, weight);
+      my_set = true;
+    }
+  }
+  if (my_set) slices[((size_t)in * h + my_iy) * w + my_ix] = my_out;  // one coalesced store per warp
+}
+
 // ---------------------------------------------------------------------------------- adjoint
 // interpolated PSF value at the voxel nearest to (x, y, z), or -1 when it falls off the PSF grid
 __device__ __forceinline__ float psf_at_voxel(const SliceGeom& g, const float* __restrict__ psf, int dp, int hp, int wp, float xr, float yr, float zr) {
   const float dx = xr - g.xc, dy = yr - g.yc, dz = zr - g.zc;
-  const float xp = (float)((double)(g.r11 * dx + g.r21 * dy + g.r31 * dz) + (wp - 1) / 2.);
-  const float yp = (float)((double)(g.r12 * dx + g.r22 * dy + g.r32 * dz) + (hp - 1) / 2.);
-  const float zp = (float)((double)(g.r13 * dx + g.r23 * dy + g.r33 * dz) + (dp - 1) / 2.);
+  // the reference adds the double constant (w_p-1)/2.; it is an integer or a half, exactly
+  // representable in float, so the float add rounds to the same value without FP64 conversions
+  const float xp = (g.r11 * dx + g.r21 * dy + g.r31 * dz) + 0.5f * (float)(wp - 1);
+  const float yp = (g.r12 * dx + g.r22 * dy + g.r32 * dz) + 0.5f * (float)(hp - 1);
+  const float zp = (g.r13 * dx + g.r23 * dy + g.r33 * dz) + 0.5f * (float)(dp - 1);
   if (xp < 0.f || yp < 0.f || zp < 0.f || xp >= (float)(wp - 1) || yp >= (float)(hp - 1) || zp >= (float)(dp - 1)) return -1.f;
   const float fx = floorf(xp), fy = floorf(yp), fz = floorf(zp);
   const float wx = xp - fx, wy = yp - fy, wz = zp - fz;
@@ -130,8 +212,7 @@ __device__ __forceinline__ float psf_at_voxel(const SliceGeom& g, const float* _
 
 __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const float* __restrict__ transforms, const float* __restrict__ psf, int dp, int hp, int wp,
                                                                         const float4* __restrict__ taps, int ntaps, float radius, const float* __restrict__ slices,
-                                                                        const int* __restrict__ slice_idx, float* __restrict__ vol, float* __restrict__ vol_weight, int h, int w,
-                                                                        int D, int H, int W, float res) {
+                                                                        const int* __restrict__ slice_idx, float2* __restrict__ acc, int h, int w, int D, int H, int W, float res) {
   extern __shared__ float4 s_tap[];
   const int in = blockIdx.z;
   const float* t = transforms + in * 12;  // transforms are already gathered: [n][3][4]
@@ -174,15 +255,98 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const flo
     if (pv < 0.f) continue;
     pv = __fdiv_rn(pv, weight);
     const int iv = (int)zr * Sz + (int)yr * Sy + (int)xr;
-    atomicAdd(vol + iv, pv * s);
-    if (vol_weight) atomicAdd(vol_weight + iv, pv);
+    // value and weight of a voxel are interleaved: ONE 64-bit reduction per tap instead of two 32-bit
+    // ones (the kernel is bound by the L2 reduction rate, ~2.6 G taps per reconstruction)
+    atomicAdd(acc + iv, make_float2(pv * s, pv));
   }
 }
 
-__global__ void __launch_bounds__(256) equalize_kernel(float* __restrict__ vol, const float* __restrict__ wgt, unsigned n) {
+// Warp-per-pixel reconstruction: the 32 lanes of a warp split the PSF taps of ONE slice pixel, keep
+// their interpolated PSF values and target voxels in registers, reduce the normalisation weight with
+// shuffles and scatter straight away — every tap is evaluated once (the thread-per-pixel kernel above,
+// like the reference, evaluates every tap twice), lanes of a warp never diverge on the pixel cull and
+// consecutive taps land on neighbouring voxels.  A block still owns a 16x16 pixel tile of one slice
+// (rotated tap offsets staged once); each warp walks 32 of its pixels.  TPL = taps per lane.
+template <int TPL>
+__global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_warp_kernel(const float* __restrict__ transforms, const float* __restrict__ psf, int dp, int hp, int wp,
+                                                                             const float4* __restrict__ taps, int ntaps, float radius, const float* __restrict__ slices,
+                                                                             const int* __restrict__ slice_idx, float2* __restrict__ acc, int h, int w, int D, int H, int W, float res) {
+  extern __shared__ float4 s_tap[];
+  const int in = blockIdx.z;
+  const float* t = transforms + in * 12;
+  const int tid = threadIdx.y * ACQ_TILE + threadIdx.x;
+  for (int p = tid; p < ntaps; p += ACQ_TILE * ACQ_TILE) {
+    const float4 q = taps[p];
+    float x = t[0] * q.x;
+    x = x + t[1] * q.y;
+    x = x + t[2] * q.z;
+    float y = t[4] * q.x;
+    y = y + t[5] * q.y;
+    y = y + t[6] * q.z;
+    float z = t[8] * q.x;
+    z = z + t[9] * q.y;
+    z = z + t[10] * q.z;
+    s_tap[p] = make_float4(x, y, z, q.w);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int Sy = W, Sz = H * W;
+  const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
+  const float* __restrict__ srow = slices + (size_t)(slice_idx ? slice_idx[in] : in) * h * w;
+  // warp `warp` owns tile rows 2*warp and 2*warp+1 (32 pixels).  Lane q first evaluates the geometry and
+  // the cull of pixel q; the warp then walks the surviving pixels, broadcasting their geometry.
+  const int my_ix = blockIdx.x * ACQ_TILE + (lane & 15), my_iy = blockIdx.y * ACQ_TILE + 2 * warp + (lane >> 4);
+  const bool inside = my_ix < w && my_iy < h;
+  const SliceGeom mine = slice_geom(t, inside ? my_ix : 0, inside ? my_iy : 0, h, w, D, H, W, res);
+  const bool keep = inside && !(mine.xc + radius < 0.f || mine.yc + radius < 0.f || mine.zc + radius < 0.f || mine.xc - radius >= mx || mine.yc - radius >= my || mine.zc - radius >= mz);
+  const float my_s = keep ? srow[my_iy * w + my_ix] : 0.f;
+  unsigned todo = __ballot_sync(0xffffffffu, keep);
+  while (todo) {
+    const int q = __ffs(todo) - 1;
+    todo &= todo - 1;
+    SliceGeom g = mine;  // the rotation is the slice's: identical in every lane
+    g.xc = __shfl_sync(0xffffffffu, mine.xc, q);
+    g.yc = __shfl_sync(0xffffffffu, mine.yc, q);
+    g.zc = __shfl_sync(0xffffffffu, mine.zc, q);
+    const float s = __shfl_sync(0xffffffffu, my_s, q);
+    float pv[TPL];
+    int iv[TPL];
+    float weight = 0.f;
+#pragma unroll
+    for (int u = 0; u < TPL; ++u) {
+      const int p = lane + 32 * u;
+      pv[u] = -1.f;
+      iv[u] = 0;
+      if (p < ntaps) {
+        const float4 o = s_tap[p];
+        const float x = g.xc + o.x, y = g.yc + o.y, z = g.zc + o.z;
+        if (!(x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz)) {
+          const float xr = roundf(x), yr = roundf(y), zr = roundf(z);
+          pv[u] = psf_at_voxel(g, psf, dp, hp, wp, xr, yr, zr);
+          iv[u] = (int)zr * Sz + (int)yr * Sy + (int)xr;
+          if (pv[u] >= 0.f) weight += pv[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) weight += __shfl_xor_sync(0xffffffffu, weight, o);
+    if (weight < 0.5f) continue;  // border
+#pragma unroll
+    for (int u = 0; u < TPL; ++u) {
+      if (pv[u] >= 0.f) {
+        const float v = __fdiv_rn(pv[u], weight);
+        atomicAdd(acc + iv[u], make_float2(v * s, v));
+      }
+    }
+  }
+}
+
+// de-interleave the accumulator; equalize: vol /= weight where the weight is positive (kernel :672-693)
+__global__ void __launch_bounds__(256) equalize_kernel(const float2* __restrict__ acc, float* __restrict__ vol, float* __restrict__ wgt, unsigned n, int equalize) {
   for (unsigned v = blockIdx.x * 256 + threadIdx.x; v < n; v += gridDim.x * 256) {
-    const float wv = wgt[v];
-    if (wv > 0.f) vol[v] = __fdiv_rn(vol[v], wv);
+    const float2 a = acc[v];
+    vol[v] = (equalize && a.y > 0.f) ? __fdiv_rn(a.x, a.y) : a.x;
+    if (wgt) wgt[v] = a.y;
   }
 }
 
@@ -312,30 +476,68 @@ extern "C" int fsg_slice_acq_forward(const float* transforms, const float* vol, 
   cudaMemsetAsync(slices, 0, sizeof(float) * (size_t)n * h * w, s);
   dim3 grid((w + ACQ_TILE - 1) / ACQ_TILE, (h + ACQ_TILE - 1) / ACQ_TILE, n);
   const size_t smem = sizeof(float4) * ntaps;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(slice_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  slice_fwd_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, vol, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, h, w, D, H, W, res_slice);
+  // large PSFs: lanes over taps (coalesced gathers); small ones (the 1-tap mask acquisition): thread per pixel
+  static const int warp_min_taps = [] {
+    const char* e = getenv("FSG_FWD_WARP_MIN_TAPS");
+    return e ? atoi(e) : 400;  // r01: 215 taps 2.5 ms (thread) vs 3.9 ms (warp); 729 taps 12.7 vs 9.3 ms
+  }();
+  if (ntaps >= warp_min_taps) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(slice_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    slice_fwd_warp_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, vol, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, h, w, D, H, W, res_slice);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(slice_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    slice_fwd_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, vol, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, h, w, D, H, W, res_slice);
+  }
   return check_launch("fsg_slice_acq_forward");
 }
 
 extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,
-                                     const int32_t* slice_idx, float* vol, float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream) {
+                                     const int32_t* slice_idx, float* vol, float* vol_weight, float* workspace, int n, int h, int w, int D, int H, int W, float res_slice,
+                                     int equalize, void* stream) {
   if (int rc = check_acq("fsg_slice_acq_adjoint", ntaps, n, h, w, D, H, W)) return rc;
-  FSG_REQUIRE(transforms && psf && taps && slices && vol, "fsg_slice_acq_adjoint: NULL pointer");
-  FSG_REQUIRE(!equalize || vol_weight, "fsg_slice_acq_adjoint: equalize needs vol_weight");
+  FSG_REQUIRE(transforms && psf && taps && slices && vol && workspace, "fsg_slice_acq_adjoint: NULL pointer");
+  FSG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "fsg_slice_acq_adjoint: workspace must be 8-byte aligned");
   FSG_REQUIRE(dp >= 2 && hp >= 2 && wp >= 2, "fsg_slice_acq_adjoint: PSF must be at least 2 voxels wide per axis");
   FSG_REQUIRE((reinterpret_cast<uintptr_t>(taps) & 15) == 0, "fsg_slice_acq_adjoint: taps must be 16-byte aligned");
   cudaStream_t s = as_stream(stream);
   const size_t nv = (size_t)D * H * W;
-  cudaMemsetAsync(vol, 0, sizeof(float) * nv, s);
-  if (vol_weight) cudaMemsetAsync(vol_weight, 0, sizeof(float) * nv, s);
+  float2* acc = reinterpret_cast<float2*>(workspace);
+  cudaMemsetAsync(acc, 0, sizeof(float2) * nv, s);
   dim3 grid((w + ACQ_TILE - 1) / ACQ_TILE, (h + ACQ_TILE - 1) / ACQ_TILE, n);
   const size_t smem = sizeof(float4) * ntaps;
   if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  slice_adj_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, slice_idx, vol, vol_weight, h, w,
-                                                               D, H, W, res_slice);
-  if (equalize) {
+  const float4* taps4 = reinterpret_cast<const float4*>(taps);
+#define FSG_ADJ_WARP(TPL)                                                                                                                                           \
+  do {                                                                                                                                                              \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_warp_kernel<TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                 \
+    slice_adj_warp_kernel<TPL><<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, taps4, ntaps, radius, slices, slice_idx, acc, h, w, D, H, W, \
+                                                                           res_slice);                                                                             \
+  } while (0)
+  const int tpl = (ntaps + 31) / 32;
+  static const bool per_thread = [] {
+    const char* e = getenv("FSG_ADJ_THREAD");  // A/B: the thread-per-pixel kernel
+    return e && e[0] == '1';
+  }();
+  if (per_thread || tpl > 32)
+    slice_adj_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, taps4, ntaps, radius, slices, slice_idx, acc, h, w, D, H, W, res_slice);
+  else if (tpl <= 2)
+    FSG_ADJ_WARP(2);
+  else if (tpl <= 4)
+    FSG_ADJ_WARP(4);
+  else if (tpl <= 8)
+    FSG_ADJ_WARP(8);
+  else if (tpl <= 12)
+    FSG_ADJ_WARP(12);
+  else if (tpl <= 16)
+    FSG_ADJ_WARP(16);
+  else if (tpl <= 24)
+    FSG_ADJ_WARP(24);
+  else
+    FSG_ADJ_WARP(32);
+#undef FSG_ADJ_WARP
+  {
     const size_t want = (nv + 255) / 256;
-    equalize_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(vol, vol_weight, (unsigned)nv);
+    equalize_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(acc, vol, vol_weight, (unsigned)nv, equalize);
   }
   return check_launch("fsg_slice_acq_adjoint");
 }

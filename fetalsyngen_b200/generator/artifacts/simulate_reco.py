@@ -64,11 +64,12 @@ def slice_acquisition_adjoint(mat, psf, slices, vol_shape, res_slice, slice_idx=
     D, H, W = (int(s) for s in vol_shape)
     vol = torch.empty((1, 1, D, H, W), dtype=torch.float32, device=dev)
     wgt = torch.empty((1, 1, D, H, W), dtype=torch.float32, device=dev)
+    acc = torch.empty((D * H * W, 2), dtype=torch.float32, device=dev)  # interleaved (value, weight) accumulator
     t_d, taps_d, psf_d = _dev_f32(mat, dev), _dev_f32(taps, dev), _dev_f32(psf, dev)
     idx_d = None if slice_idx is None else _dev_i32(slice_idx, dev)
     dp, hp, wp = psf.shape
     _lib.call("fsg_slice_acq_adjoint", t_d.data_ptr(), psf_d.data_ptr(), dp, hp, wp, taps_d.data_ptr(), int(taps.shape[0]), float(radius), slices.data_ptr(),
-              None if idx_d is None else idx_d.data_ptr(), vol.data_ptr(), wgt.data_ptr(), n, h, w, D, H, W, float(F32(res_slice)), int(bool(equalize)), _stream())
+              None if idx_d is None else idx_d.data_ptr(), vol.data_ptr(), wgt.data_ptr(), acc.data_ptr(), n, h, w, D, H, W, float(F32(res_slice)), int(bool(equalize)), _stream())
     return vol, wgt
 
 

@@ -289,11 +289,14 @@ int fsg_label_mask(const uint8_t* labels, int match, uint8_t* out, int64_t n, vo
  * transforms: [n][3][4] row-major device floats.  vol: [D][H][W] (W fastest).  taps: [ntaps][4]
  * device floats = the NON-ZERO PSF entries in the reference's loop order as (ix_p, iy_p, iz_p, value),
  * 16-byte aligned; radius >= max |tap offset| (pixels farther than that from the volume are skipped).
- * slices: [n][h][w].  fsg_slice_acq_adjoint zero-fills vol / vol_weight itself. */
+ * slices: [n][h][w].  fsg_slice_acq_adjoint zero-fills its accumulator itself. */
 int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
                           float res_slice, void* stream);
 int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,
-                          const int32_t* slice_idx, float* vol, float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice, int equalize, void* stream);
+                          const int32_t* slice_idx, float* vol, float* vol_weight, float* workspace, int n, int h, int w, int D, int H, int W, float res_slice, int equalize,
+                          void* stream);
+/* workspace: 2*D*H*W device floats, 8-byte aligned (interleaved value/weight accumulator: one 64-bit
+ * reduction per tap); vol_weight may be NULL. */
 /* slice_idx (device, [n], may be NULL): slice in of the launch reads slices[slice_idx[in]] — the
  * "stacks[kept_idx]" gather of PSFReconstructor (simulate_reco.py:766-767) without a copy.
  *

@@ -164,9 +164,48 @@ def run_sweep(args):
             torch.cuda.empty_cache()
 
 
+def run_motion(args):
+    """Slice-acquisition forward / PSF-reconstruction adjoint at the default config's sizes: libfsg vs
+    the reference's own extension (oracle/_ref, built from the reference's sources for sm_100a)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+    import np_motion as M
+    from fetalsyngen_b200.generator.artifacts import simulate_reco as SR
+    from fetalsyngen_b200.generator.artifacts import svort
+
+    ext = build_ref.load_built()
+    S = args.shape
+    seg_h, _ = label_phantom((S, S, S))
+    rs = np.random.RandomState(0)
+    vol = torch.from_numpy((seg_h > 0).astype(np.float32) * (0.3 + 0.7 * rs.rand(S, S, S).astype(np.float32))).to(DEV)
+    for res_s, thick, gap in ((0.6, 2.5, 3.5), (1.0, 3.5, 1.6), (0.3, 1.5, 5.0)):
+        np.random.seed(1)
+        psf = svort.get_PSF(res_ratio=(res_s / 0.5, res_s / 0.5, thick / 0.5))
+        ss = int(np.ceil(int(np.sqrt(3 * S * S / 2.0) * 0.5 / res_s) / 32.0) * 32)
+        ns = int(S * 0.5 / gap) + 2
+        init = svort.random_init_stack_transforms(ns, gap, False, 3.0)
+        motion = svort.sample_motion(np.arange(ns) * 1.5, True)
+        mat = svort.mat_update_resolution(motion.compose(init).matrix(), 0.5, 0.5)
+        nstack = max(1, min(6, 250 // ns))
+        mats = np.concatenate([mat] * nstack)[:250]
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+        empty = torch.empty(0, device=DEV)
+        ours_f = timed(lambda: SR.slice_acquisition(mat, vol, psf, (ss, ss), res_s / 0.5), reps=args.reps)
+        sl = SR.slice_acquisition(mats, vol, psf, (ss, ss), res_s / 0.5)
+        ours_a = timed(lambda: SR.slice_acquisition_adjoint(mats, psf, sl, (S, S, S), res_s / 0.5), reps=args.reps)
+        line = {"config": "motion kernels", "shape": S, "res_slice": res_s, "slice_thickness": thick, "gap": gap, "slice_size": ss, "slices_per_stack": ns, "psf_shape": list(psf.shape),
+                "psf_taps": int((psf != 0).sum()), "forward_ms_ours": ours_f, "adjoint_slices": int(mats.shape[0]), "adjoint_ms_ours": ours_a}
+        if ext is not None:
+            tm, tp, tms = t(mat), t(psf), t(mats)
+            ref_f = timed(lambda: ext.forward(tm, vol[None, None], empty, empty, tp, [ss, ss], float(res_s / 0.5), False, False), reps=args.reps)
+            ref_a = timed(lambda: ext.adjoint_forward(tms, tp, sl, empty, empty, [S, S, S], float(res_s / 0.5), True, True), reps=args.reps)
+            line.update({"forward_ms_reference_ext": ref_f, "adjoint_ms_reference_ext": ref_a, "forward_speedup": ref_f / ours_f, "adjoint_speedup": ref_a / ours_a})
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["artifacts", "sweep"], required=True)
+    ap.add_argument("--config", choices=["artifacts", "sweep", "motion"], required=True)
     ap.add_argument("--shape", type=int, default=256)
     ap.add_argument("--sizes", type=int, nargs="+", default=[128, 256, 384])
     ap.add_argument("--batches", type=int, nargs="+", default=[1, 8])
@@ -175,7 +214,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device")
     _lib.load()
-    (run_artifacts if args.config == "artifacts" else run_sweep)(args)
+    {"artifacts": run_artifacts, "sweep": run_sweep, "motion": run_motion}[args.config](args)
 
 
 if __name__ == "__main__":
