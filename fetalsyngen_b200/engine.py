@@ -476,7 +476,18 @@ class SynthEngine:
         B = len(plans)
         if B < 1 or B > _lib.MAX_JOBS:
             raise ValueError(f"batch must be 1..{_lib.MAX_JOBS}")
+        if len(seeds) != B or len(segs) != B:
+            raise ValueError("run_base: plans, seeds and segmentations must have the same length")
+        for b, sg in enumerate(segs):
+            if sg.numel() != self.nvox:
+                raise ValueError(f"segmentation {b} has {sg.numel()} voxels, the engine shape {self.shape} has {self.nvox}")
+            _check(sg, torch.uint8, self.device, f"segmentation {b}")
         shp = (B, *self.shape)
+        for name, t, dt in (("out_img", out_img, torch.float32), ("out_seg", out_seg, torch.uint8)):
+            if t is not None:
+                if tuple(t.shape) != shp:
+                    raise ValueError(f"{name} must have shape {shp}, got {tuple(t.shape)}")
+                _check(t, dt, self.device, name)
         out_img = torch.empty(shp, dtype=torch.float32, device=self.device) if out_img is None else out_img
         out_seg = torch.empty(shp, dtype=torch.uint8, device=self.device) if out_seg is None else out_seg
         buf0 = self.scratch("buf0", B)

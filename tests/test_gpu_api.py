@@ -1,0 +1,170 @@
+"""Reference-shaped API on the GPU: error behaviour, gates, default probabilities, dtype and
+ownership contracts (model.py:94-276, datasets.py:256-349), host pipeline, larger volumes."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import bench  # noqa: E402
+from fetalsyngen_b200 import _lib  # noqa: E402
+from fetalsyngen_b200.utils.phantom import label_phantom  # noqa: E402
+from gpu_util import DEV  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(shape, probs=1.0, artifacts=None):
+    from fetalsyngen_b200.generator.augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
+    from fetalsyngen_b200.generator.deformation.affine_nonrigid import SpatialDeformation
+    from fetalsyngen_b200.generator.intensity.rand_gmm import ImageFromSeeds
+    from fetalsyngen_b200.generator.model import FetalSynthGen
+
+    labels = [0] + list(range(10, 50))
+    classes = [0] + [10] * 10 + [20] * 10 + [30] * 10 + list(range(40, 50))
+    return FetalSynthGen(shape=list(shape), resolution=[0.5] * 3, device=DEV, intensity_generator=ImageFromSeeds(1, 6, labels, classes),
+                         spatial_deform=SpatialDeformation(20, 0.02, 0.1, list(shape), probs, True, 0.03, 0.06, 4, 0.5, DEV), resampler=RandResample(probs, 0.5, 1.5),
+                         bias_field=RandBiasField(probs, 0.004, 0.02, 0.01, 0.3), noise=RandNoise(probs, 5, 15), gamma=RandGamma(probs, 0.1), **(artifacts or {}))
+
+
+def test_errors_match_the_reference_contract():
+    shape = (32, 32, 32)
+    gen = _gen(shape)
+    seg = torch.zeros(shape, dtype=torch.float32, device=DEV)
+    with pytest.raises(ValueError):  # model.py:132-135: no seeds and no image
+        gen.sample(image=None, segmentation=seg, seeds=None)
+    with pytest.raises(_lib.FsgError):
+        from fetalsyngen_b200.engine import SynthEngine
+
+        SynthEngine(shape, (0.5,) * 3, "cpu")
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    with pytest.raises(ValueError):  # more volumes than FSG_MAX_JOBS in one launch
+        gen.sample_batch([seg_d] * 17, [seeds_d] * 17)
+    with pytest.raises((TypeError, ValueError)):  # seed volumes must be int8/uint8 label maps
+        gen.sample_batch([seg_d], [[s.float() for s in seeds_d]])
+    with pytest.raises((TypeError, ValueError, _lib.FsgError)):  # segmentation of another shape
+        gen.sample_batch([seg_d[:16]], [seeds_d])
+
+
+def test_all_gates_off_is_identity_on_the_segmentation_and_pure_gmm_on_the_image():
+    shape = (32, 32, 32)
+    gen = _gen(shape, probs=0.0)
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    np.random.seed(3)
+    torch.manual_seed(3)
+    img, seg, params = gen.sample_batch([seg_d], [seeds_d], scale=False)
+    assert torch.equal(seg[0], seg_d)
+    p = params[0]
+    assert p["deform_params"]["affine"] is None and p["gamma_params"]["gamma"] is None and p["resample_params"]["spacing"] is None and p["noise_params"]["noise_std"] is None
+    lab = sum(s.astype(np.int64) for s in seeds_h)
+    x = img[0].cpu().numpy()
+    assert x.min() >= 0 and np.isfinite(x).all()
+    # per-label moments of the Philox GMM draw (the reference's sigma per label is in the drawn table)
+    mus, sigmas = gen.intensity_generator.draw_gmm({})  # shapes only: the actual tables are not returned on this path
+    assert mus.shape == (50,) and sigmas.shape == (50,)
+    for lbl in np.unique(lab)[:6]:
+        v = x[lab == lbl]
+        if v.size > 500:
+            assert 0 < v.std() < 40 and 0 <= v.mean() < 330
+
+
+def test_default_probabilities_give_mixed_batches():
+    """prob 0.9 / flip 0.5 as in the reference's default YAML: some samples skip stages; every volume
+    stays finite, in [0,1] after ScaleIntensity, labels stay in the input label set."""
+    shape = (64, 64, 64)
+    gen = _gen(shape, probs=0.6)
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    seen = {"deform_off": 0, "resample_off": 0, "bias_off": 0}
+    for it in range(3):
+        ids = list(range(8 * it, 8 * it + 8))
+        img, seg, params = gen.sample_batch([seg_d] * 8, [seeds_d] * 8, scale=True, sample_ids=ids, base_seed=5)
+        assert torch.isfinite(img).all() and float(img.min()) >= 0 and float(img.max()) <= 1
+        assert set(torch.unique(seg).tolist()) <= set(np.unique(seg_h).tolist())
+        for p in params:
+            seen["deform_off"] += p["deform_params"]["affine"] is None
+            seen["resample_off"] += p["resample_params"]["spacing"] is None
+            seen["bias_off"] += p["bf_params"]["bf_size"] is None
+    assert all(v > 0 for v in seen.values()), seen
+
+
+def test_sample_keeps_dtypes_and_parameter_keys():
+    shape = (32, 32, 32)
+    gen = _gen(shape)
+    seg_h, seeds_h = label_phantom(shape)
+    for dt in (torch.float32, torch.int64, torch.uint8):
+        seg = torch.from_numpy(seg_h).to(DEV).to(dt)
+        plan_seeds = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+        img, sg, params = gen.sample_batch([seg.to(torch.uint8)], [plan_seeds])
+        assert sg.dtype == torch.uint8 and img.dtype == torch.float32
+    for key in ("selected_seeds", "seed_intensities", "deform_params", "gamma_params", "bf_params", "resample_params", "noise_params"):
+        assert key in params[0]
+    assert set(params[0]["deform_params"]) == {"affine", "non_rigid", "flip"}
+    assert set(params[0]["deform_params"]["affine"]) == {"rotations", "shears", "scalings"}
+
+
+def test_host_pipeline_matches_device_path_and_keeps_order():
+    from fetalsyngen_b200.host_pipeline import HostPipeline
+
+    shape = (64, 64, 64)
+    gen = _gen(shape)
+    seg_h, seeds_h = label_phantom(shape)
+    B = 2
+    hp = HostPipeline(gen, B, depth=2)
+    hp.set_inputs([seg_h] * B, [seeds_h] * B)
+    got = []
+    steps = 5
+    for it in range(steps):
+        if it >= 2:
+            img, seg, _ = hp.collect()
+            got.append((img.clone(), seg.clone()))
+        hp.submit(sample_ids=[2 * it, 2 * it + 1], base_seed=9)
+    while len(got) < steps:
+        img, seg, _ = hp.collect()
+        got.append((img.clone(), seg.clone()))
+    with pytest.raises(IndexError):
+        hp.collect()
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    for it in range(steps):
+        img, seg, _ = gen.sample_batch([seg_d] * B, [seeds_d] * B, scale=True, sample_ids=[2 * it, 2 * it + 1], base_seed=9)
+        assert torch.equal(img.cpu(), got[it][0]) and torch.equal(seg.cpu(), got[it][1])
+    assert hp.h2d_bytes == B * 5 * 64**3 and hp.d2h_bytes == B * 5 * 64**3
+
+
+def test_full_sample_with_all_artifacts_runs_at_96():
+    shape = (96, 96, 96)
+    gen = _gen(shape, artifacts=bench.default_artifacts(1.0))
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV).float()
+    gen.intensity_generator._cache = {}
+    np.random.seed(1)
+    torch.manual_seed(1)
+    # sample() takes the reference's seed-path dictionary; feed decoded volumes through the cache
+    seeds = {n: {m: f"mem://{n}/{m}" for m in range(1, 5)} for n in range(1, 7)}
+    for n in range(1, 7):
+        for m in range(1, 5):
+            gen.intensity_generator._cache[(f"mem://{n}/{m}", str(torch.device(DEV)))] = torch.from_numpy(seeds_h[m - 1]).to(DEV)
+    out, seg, image, params = gen.sample(image=None, segmentation=seg_d, seeds=seeds)
+    assert out.shape == shape and seg.dtype == torch.float32 and image is None and torch.isfinite(out).all()
+    assert set(params["artifacts"]) == {"blur_cortex", "struct_noise", "simulate_motion", "boundaries"}
+    assert params["artifacts"]["simulate_motion"]["nstacks"] >= 2
+    assert float((out == 0).float().mean()) > 0.05  # boundaries masked the background
+
+
+def test_volume_384_single_sample():
+    shape = (384, 384, 384)
+    gen = _gen(shape)
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    img, seg, _ = gen.sample_batch([seg_d], [seeds_d], scale=True, sample_ids=[0], base_seed=1)
+    assert img.shape == (1, *shape) and torch.isfinite(img).all() and float(img.max()) == 1.0
+    assert set(torch.unique(seg).tolist()) <= set(np.unique(seg_h).tolist())
