@@ -10,5 +10,5 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_$TAG.log 2>&1
 echo "launches rc=$?"
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'gmm_kernel|warp_kernel|sep_|zoom' -s ${NCU_SKIP:-30} -c ${NCU_COUNT:-12} -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gmm_kernel|warp_fast|warp_kernel|sep_|zoom_rows" -s ${NCU_SKIP:-27} -c ${NCU_COUNT:-9} -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"

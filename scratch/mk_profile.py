@@ -13,7 +13,7 @@ rows = [r for r in csv.DictReader(l for l in open(f"gpurun_out/launches_{tag}.cs
 t = defaultdict(lambda: [0, 0.0])
 for r in rows:
     if r["Metric Name"] == "gpu__time_duration.sum":
-        k = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
+        k = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("fsg::", "")
         t[k][0] += 1; t[k][1] += float(r["Metric Value"]) / 1e6
 tot = sum(v[1] for v in t.values())
 with open(f"profiles/{out}_launch_shares.txt", "w") as f:
@@ -21,7 +21,7 @@ with open(f"profiles/{out}_launch_shares.txt", "w") as f:
     for k, v in sorted(t.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:60s} {v[0]:4d} {v[1]:9.3f} ms {100*v[1]/tot:5.1f} %\n")
 # traffic per entry point (dominant device kernel of each)
-ENTRY = {"warp_kernel<1": "fsg_warp", "gmm_kernel": "fsg_gmm", "zoom_rows_kernel<0": "fsg_zoom", "zoom_rows_kernel<1": "fsg_zoom_minmax", "sep_": "fsg_sepconv"}
+ENTRY = {"warp_fast_kernel": "fsg_warp", "warp_kernel<1": "fsg_warp", "gmm_kernel": "fsg_gmm", "zoom_rows_kernel<0": "fsg_zoom", "zoom_rows_kernel<1": "fsg_zoom_minmax", "sep_": "fsg_sepconv"}
 per_kernel = defaultdict(lambda: [0.0, 0]); cur = None
 for line in summ.splitlines():
     if line.startswith("---"):
