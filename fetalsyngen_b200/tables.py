@@ -87,19 +87,22 @@ def resample_stds(spacing, res_in, blur_u: float) -> np.ndarray:
 
 def make_affine_matrix(rot, sh, s) -> np.ndarray:
     """3x3 float64 affine of the spatial deformation: shear_x . shear_y . shear_z . Rx . Ry . Rz,
-    rows scaled (utils/generation.py:39-71)."""
-    c, si = np.cos(np.asarray(rot, dtype=np.float64)), np.sin(np.asarray(rot, dtype=np.float64))
-    mats = [
-        np.array([[1, 0, 0], [sh[1], 1, 0], [sh[2], 0, 1]], dtype=np.float64),
-        np.array([[1, sh[0], 0], [0, 1, 0], [0, sh[2], 1]], dtype=np.float64),
-        np.array([[1, 0, sh[0]], [0, 1, sh[1]], [0, 0, 1]], dtype=np.float64),
-        np.array([[1, 0, 0], [0, c[0], -si[0]], [0, si[0], c[0]]], dtype=np.float64),
-        np.array([[c[1], 0, si[1]], [0, 1, 0], [-si[1], 0, c[1]]], dtype=np.float64),
-        np.array([[c[2], -si[2], 0], [si[2], c[2], 0], [0, 0, 1]], dtype=np.float64),
-    ]
-    a = mats[0]
-    for m in mats[1:]:
-        a = a @ m
+    rows scaled (utils/generation.py:39-71).  Same six float64 matrices and the same left-to-right
+    numpy products as the reference (bit-identical), built by index assignment into one array."""
+    c0, c1, c2 = (float(v) for v in np.cos(np.asarray(rot, dtype=np.float64)))
+    s0, s1, s2 = (float(v) for v in np.sin(np.asarray(rot, dtype=np.float64)))
+    h0, h1, h2 = float(sh[0]), float(sh[1]), float(sh[2])
+    m = np.zeros((6, 3, 3), dtype=np.float64)
+    m[:, 0, 0] = m[:, 1, 1] = m[:, 2, 2] = 1.0
+    m[0, 1, 0], m[0, 2, 0] = h1, h2
+    m[1, 0, 1], m[1, 2, 1] = h0, h2
+    m[2, 0, 2], m[2, 1, 2] = h0, h1
+    m[3, 1, 1], m[3, 1, 2], m[3, 2, 1], m[3, 2, 2] = c0, -s0, s0, c0
+    m[4, 0, 0], m[4, 0, 2], m[4, 2, 0], m[4, 2, 2] = c1, s1, -s1, c1
+    m[5, 0, 0], m[5, 0, 1], m[5, 1, 0], m[5, 1, 1] = c2, -s2, s2, c2
+    a = m[0]
+    for k in range(1, 6):
+        a = a @ m[k]
     return a * np.asarray(s, dtype=np.float64)[:, None]
 
 

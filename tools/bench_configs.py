@@ -203,9 +203,64 @@ def run_motion(args):
         print(json.dumps(line))
 
 
+def run_sample_api(args):
+    """The reference's own published figure is `generation_time` of one `FetalSynthDataset.sample`
+    call (docs/datasets.md:76,131: 0.5616 s / 0.6192 s on an unspecified GPU; wall clock around
+    generator.sample + ScaleIntensity + .cpu(), datasets.py:303-320).  Same call here, on a BIDS tree
+    written to a temporary directory from the label phantom."""
+    import tempfile
+    import time
+
+    from fetalsyngen_b200.data.datasets import FetalSynthDataset
+    from fetalsyngen_b200.utils import nifti
+
+    S = args.shape
+    shape = (S, S, S)
+    seg_h, seeds_h = label_phantom(shape)
+    aff = np.diag([0.5, 0.5, 0.5, 1.0])
+    with tempfile.TemporaryDirectory() as tmp:
+        root = Path(tmp)
+        d = root / "bids" / "sub-phantom" / "anat"
+        d.mkdir(parents=True)
+        nifti.write_nifti(d / "sub-phantom_rec-x_T2w_dseg.nii.gz", seg_h.astype(np.float32), aff)
+        for n in range(1, 7):
+            sd = root / "seeds" / f"subclasses_{n}" / "sub-phantom" / "anat"
+            sd.mkdir(parents=True)
+            for m in range(1, 5):
+                nifti.write_nifti(sd / f"sub-phantom_rec-x_T2w_dseg_mlabel_{m}.nii.gz", seeds_h[m - 1], aff)
+        res = {}
+        for name, arts in (("base stages (default probabilities)", None), ("with the four SR artifacts (default probabilities)", bench.default_artifacts(0.4))):
+            gen = bench.build_generator(shape, DEV, artifacts=arts)
+            for st in (gen.spatial_deform, gen.resampled, gen.biasfield, gen.noise, gen.gamma):
+                st.prob = 0.9  # configs/dataset/generator/default.yaml
+            gen.spatial_deform.flip_prb = 0.5
+            ds = FetalSynthDataset(str(root / "bids"), gen, str(root / "seeds"), None)
+            np.random.seed(0)
+            torch.manual_seed(0)
+            t0 = time.perf_counter()
+            ds.sample(0)
+            first = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            nwarm = 0
+            while len(gen.intensity_generator._cache) < 24 and nwarm < 200:  # all 24 seed volumes decoded once (the reference re-reads 4 per sample)
+                ds.sample(0)
+                nwarm += 1
+            warm = time.perf_counter() - t0
+            times = []
+            for _ in range(args.reps * 4):
+                t0 = time.perf_counter()
+                out, params = ds.sample(0)
+                times.append(time.perf_counter() - t0)
+            assert out["image"].shape == (1, *shape) and out["label"].dtype == torch.int64 and out["image"].device.type == "cpu"
+            res[name] = {"first_call_s": first, "seed_cache_warmup_calls": nwarm, "seed_cache_warmup_s": warm, "mean_s": float(np.mean(times)), "median_s": float(np.median(times)), "min_s": float(np.min(times)), "max_s": float(np.max(times)),
+                         "generation_time_last": params["generation_time"]}
+    print(json.dumps({"config": "FetalSynthDataset.sample wall clock (reference: generation_time 0.5616 s / 0.6192 s, docs/datasets.md:76,131)", "shape": list(shape), "calls": args.reps * 4,
+                      "results": res, "note": "host tensors out: float32 image (1,S,S,S) + int64 label on the CPU, as the reference returns them; seeds / segmentation decoded once and cached on the device"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["artifacts", "sweep", "motion"], required=True)
+    ap.add_argument("--config", choices=["artifacts", "sweep", "motion", "sample_api"], required=True)
     ap.add_argument("--shape", type=int, default=256)
     ap.add_argument("--sizes", type=int, nargs="+", default=[128, 256, 384])
     ap.add_argument("--batches", type=int, nargs="+", default=[1, 8])
@@ -214,7 +269,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device")
     _lib.load()
-    {"artifacts": run_artifacts, "sweep": run_sweep, "motion": run_motion}[args.config](args)
+    {"artifacts": run_artifacts, "sweep": run_sweep, "motion": run_motion, "sample_api": run_sample_api}[args.config](args)
 
 
 if __name__ == "__main__":
