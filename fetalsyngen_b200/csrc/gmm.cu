@@ -20,16 +20,24 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
     s_ms[i] = make_float2(in ? job.mus[i] : 0.f, in ? job.sigmas[i] : 0.f);
   }
   __syncthreads();
+  __shared__ float s_first[2][GMM_THREADS];  // first value of every thread's group (pairs output), double-buffered
 
   const int8_t* __restrict__ sp[4] = {job.seed[0], job.seed[1], job.seed[2], job.seed[3]};
   const float* __restrict__ noise = job.noise;
   float* __restrict__ out = job.out;
   uint8_t* __restrict__ lab_out = job.labels_out;
   const fsg_rng rng = job.rng;
+  uint32_t* __restrict__ pairs = job.out_pairs;
+  const int row_len = job.row_len;
 
   const int64_t ngroups = nvox >> 2;  // whole groups of 4 voxels; the tail is handled below
   const int64_t stride = (int64_t)gridDim.x * GMM_THREADS;
-  for (int64_t g = (int64_t)blockIdx.x * GMM_THREADS + threadIdx.x; g < ngroups; g += stride) {
+  int it = 0;
+  for (int64_t gbase = (int64_t)blockIdx.x * GMM_THREADS; gbase < ngroups; gbase += stride, it ^= 1) {
+    const int64_t g = gbase + threadIdx.x;
+    const bool active = g < ngroups;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
     const int64_t v0 = g * 4;
     // labels of the seed volumes are disjoint small non-negative codes: one byte-wise SIMD add sums 4 voxels
     uint32_t lab4 = 0;
@@ -41,13 +49,44 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
     else
       n = philox_normal4(rng, (uint32_t)g);
     const float2 m0 = s_ms[lab4 & 0xff], m1 = s_ms[(lab4 >> 8) & 0xff], m2 = s_ms[(lab4 >> 16) & 0xff], m3 = s_ms[lab4 >> 24];
-    float4 o;
     o.x = fmaxf(add_rn(m0.x, mul_rn(m0.y, n.x)), 0.f);
     o.y = fmaxf(add_rn(m1.x, mul_rn(m1.y, n.y)), 0.f);
     o.z = fmaxf(add_rn(m2.x, mul_rn(m2.y, n.z)), 0.f);
     o.w = fmaxf(add_rn(m3.x, mul_rn(m3.y, n.w)), 0.f);
-    *reinterpret_cast<float4*>(out + v0) = o;
+    if (out) *reinterpret_cast<float4*>(out + v0) = o;
     if (lab_out) *reinterpret_cast<uint32_t*>(lab_out + v0) = lab4;
+    }
+    if (pairs) {  // block-uniform
+      // the pair of voxel v needs I[v+1]: the next thread's first value (shared memory), or — for the
+      // block's last thread when its group does not end a row — one extra evaluation
+      // (one barrier per iteration: the buffer written now is next written two iterations later)
+      s_first[it][threadIdx.x] = o.x;
+      __syncthreads();
+      if (active) {
+        const int64_t v0 = g * 4;
+        float nxt = 0.f;
+        const int64_t v4 = v0 + 4;
+        if (v4 < nvox && (v4 % row_len) != 0) {
+          if (threadIdx.x + 1 < GMM_THREADS) {
+            nxt = s_first[it][threadIdx.x + 1];
+          } else {
+            int l = 0;
+            for (int m = 0; m < NSEED; ++m) l += sp[m][v4];
+            const float nz = INJECT ? noise[v4] : philox_normal4(rng, (uint32_t)(g + 1)).x;
+            const float2 ms = s_ms[l & (GMM_MAX_LABELS - 1)];
+            nxt = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
+          }
+        }
+        // round(I * 128) by the 2^23 magic add (round-to-nearest-even in the FMA); the low 16 bits of the
+        // float's mantissa are the fixed-point value (I <= 511.99 after the clamp)
+        const float cap = 511.9921875f;
+        const uint32_t q0 = __float_as_uint(__fmaf_rn(fminf(o.x, cap), 128.0f, 8388608.0f)), q1 = __float_as_uint(__fmaf_rn(fminf(o.y, cap), 128.0f, 8388608.0f));
+        const uint32_t q2 = __float_as_uint(__fmaf_rn(fminf(o.z, cap), 128.0f, 8388608.0f)), q3 = __float_as_uint(__fmaf_rn(fminf(o.w, cap), 128.0f, 8388608.0f));
+        const uint32_t q4 = __float_as_uint(__fmaf_rn(fminf(nxt, cap), 128.0f, 8388608.0f));
+        // pair = low halves of (q_k, q_{k+1})
+        *reinterpret_cast<uint4*>(pairs + v0) = make_uint4(__byte_perm(q0, q1, 0x5410), __byte_perm(q1, q2, 0x5410), __byte_perm(q2, q3, 0x5410), __byte_perm(q3, q4, 0x5410));
+      }
+    }
   }
   // tail (nvox % 4 voxels): one thread, scalar
   if (blockIdx.x == 0 && threadIdx.x == 0 && (nvox & 3)) {
@@ -62,7 +101,7 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
       for (int m = 0; m < NSEED; ++m) l += sp[m][v0 + e];
       const float nz = INJECT ? noise[v0 + e] : nn[e];
       const float2 ms = s_ms[l & (GMM_MAX_LABELS - 1)];
-      out[v0 + e] = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
+      if (out) out[v0 + e] = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
       if (lab_out) lab_out[v0 + e] = (uint8_t)l;
     }
   }
@@ -134,7 +173,10 @@ extern "C" int fsg_gmm(const fsg_gmm_job* jobs, int njobs, int64_t nvox, void* s
   int nseed = -1;
   for (int i = 0; i < njobs; ++i) {
     const fsg_gmm_job& j = jobs[i];
-    FSG_REQUIRE(j.out && j.mus && j.sigmas, "fsg_gmm: job %d has a NULL out/mus/sigmas", i);
+    FSG_REQUIRE((j.out || j.out_pairs) && j.mus && j.sigmas, "fsg_gmm: job %d has a NULL out/mus/sigmas", i);
+    if (j.out_pairs)
+      FSG_REQUIRE(j.row_len >= 1 && nvox % j.row_len == 0 && nvox % 4 == 0 && (reinterpret_cast<uintptr_t>(j.out_pairs) & 15) == 0,
+                  "fsg_gmm: job %d: out_pairs needs row_len dividing nvox, nvox %% 4 == 0 and a 16-byte aligned buffer", i);
     FSG_REQUIRE(j.nlabels >= 1 && j.nlabels <= GMM_MAX_LABELS, "fsg_gmm: nlabels=%d outside [1,%d]", j.nlabels, GMM_MAX_LABELS);
     FSG_REQUIRE((j.noise != nullptr) == inject, "fsg_gmm: jobs mix injected and Philox noise");
     // compact the seed pointers of the launch copy to the front

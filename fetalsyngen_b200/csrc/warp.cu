@@ -363,7 +363,10 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
 #ifndef FSG_WARP_MINBLOCKS
 #define FSG_WARP_MINBLOCKS 3  // <= 85 registers: 3 blocks of 256 threads per SM
 #endif
-template <bool EPI>
+// PAIRS: the source image is fsg_gmm's out_pairs volume — 16-bit fixed point (I[z] | I[z+1] << 16), so
+// ONE 32-bit gather brings both z corners of an (x, y) row: four gather instructions per voxel instead
+// of eight (the kernel is bound by L1 wavefronts per gather, not by bytes).
+template <bool EPI, bool PAIRS>
 __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
   const fsg_warp_job& job = batch.j[blockIdx.z];
   const int tid = threadIdx.x;
@@ -422,13 +425,14 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
   const int xs = job.flip ? -plane : plane;
   // index = fx*xs + fy*sz + fz with all three taken as raw float bits of (value + 2^23)
   const unsigned kbias = (unsigned)(job.flip ? (sx - 1) * plane : 0) - 0x4B000000u * (unsigned)(xs + sz + 1);
-  const float* __restrict__ const src_img = job.src_img;
+  const float* __restrict__ const src_img = PAIRS ? reinterpret_cast<const float*>(job.src_pairs) : job.src_img;
   const uint8_t* __restrict__ const src_seg = job.src_seg;
   float* __restrict__ const dst_img = job.dst_img;
   uint8_t* __restrict__ const dst_seg = job.dst_seg;
   const float shx = job.shift[0], shy = job.shift[1], shz = job.shift[2];
   const float gam = (EPI && job.has_gamma) ? job.gamma : 1.0f;
-  const float c0 = (EPI && job.has_gamma) ? 8.22881869049588f * (1.0f - job.gamma) : 0.f;  // lg2(300) (1 - gamma)
+  // lg2(300) (1 - gamma); the fixed-point scale 2^-7 of the pairs format folds in as -7 gamma
+  const float c0 = ((EPI && job.has_gamma) ? 8.22881869049588f * (1.0f - job.gamma) : 0.f) - (PAIRS ? 7.0f * gam : 0.f);
 
   const P2 cen2 = pk(cen_x, cen_x), sh2x = pk(shx, shx), sh2y = pk(shy, shy), sh2z = pk(shz, shz), magic2 = pk(MAGIC, MAGIC);
   const P2 c2x = pk(aff.c[0], aff.c[0]), c2y = pk(aff.c[1], aff.c[1]), c2z = pk(aff.c[2], aff.c[2]);
@@ -490,10 +494,37 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
         const char* b01 = b00 + by_row;
         const char* b10 = b00 + by_plane;
         const char* b11 = b10 + by_row;
+        P2 c000, c001, c010, c011, c100, c101, c110, c111;
+        if (PAIRS) {
+#define LDU(p) __ldg(reinterpret_cast<const unsigned*>(p))
+          const unsigned ua00 = LDU(a00), ua01 = LDU(a01), ua10 = LDU(a10), ua11 = LDU(a11);
+          const unsigned ub00 = LDU(b00), ub01 = LDU(b01), ub10 = LDU(b10), ub11 = LDU(b11);
+#undef LDU
+          // 16-bit field -> float: (0x4B000000 | field) is 2^23 + field exactly; one packed subtract per corner pair
+#define LO(u) __uint_as_float(__byte_perm((u), 0x4B000000u, 0x7610))
+#define HI(u) __uint_as_float(__byte_perm((u), 0x4B000000u, 0x7632))
+          c000 = sub2(pk(LO(ua00), LO(ub00)), magic2);
+          c001 = sub2(pk(HI(ua00), HI(ub00)), magic2);
+          c010 = sub2(pk(LO(ua01), LO(ub01)), magic2);
+          c011 = sub2(pk(HI(ua01), HI(ub01)), magic2);
+          c100 = sub2(pk(LO(ua10), LO(ub10)), magic2);
+          c101 = sub2(pk(HI(ua10), HI(ub10)), magic2);
+          c110 = sub2(pk(LO(ua11), LO(ub11)), magic2);
+          c111 = sub2(pk(HI(ua11), HI(ub11)), magic2);
+#undef LO
+#undef HI
+        } else {
 #define LDF(p, off) __ldg(reinterpret_cast<const float*>(p) + (off))
-        const P2 c000 = pk(LDF(a00, 0), LDF(b00, 0)), c001 = pk(LDF(a00, 1), LDF(b00, 1)), c010 = pk(LDF(a01, 0), LDF(b01, 0)), c011 = pk(LDF(a01, 1), LDF(b01, 1));
-        const P2 c100 = pk(LDF(a10, 0), LDF(b10, 0)), c101 = pk(LDF(a10, 1), LDF(b10, 1)), c110 = pk(LDF(a11, 0), LDF(b11, 0)), c111 = pk(LDF(a11, 1), LDF(b11, 1));
+          c000 = pk(LDF(a00, 0), LDF(b00, 0));
+          c001 = pk(LDF(a00, 1), LDF(b00, 1));
+          c010 = pk(LDF(a01, 0), LDF(b01, 0));
+          c011 = pk(LDF(a01, 1), LDF(b01, 1));
+          c100 = pk(LDF(a10, 0), LDF(b10, 0));
+          c101 = pk(LDF(a10, 1), LDF(b10, 1));
+          c110 = pk(LDF(a11, 0), LDF(b11, 0));
+          c111 = pk(LDF(a11, 1), LDF(b11, 1));
 #undef LDF
+        }
         // ---- nearest segmentation gather (round-half-even by the magic add)
         float sxa, sxb, sya, syb, sza, szb;
         upk(add2(ii, magic2), sxa, sxb);
@@ -509,6 +540,10 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
         upk(fma2(wz2, sub2(c1_, c0_), c0_), va, vb);
         va = fminf(fminf(iia, jja), kka) > 0.f ? va : 0.f;
         vb = fminf(fminf(iib, jjb), kkb) > 0.f ? vb : 0.f;
+        if (PAIRS && !EPI) {
+          va *= 0.0078125f;
+          vb *= 0.0078125f;
+        }
         if (EPI) {
           const P2 bias = fma2(bwf2, pk(s_b[row][tb.f], s_b[row + 1][tb.f]), mul2(bwc2, pk(s_b[row][tb.c], s_b[row + 1][tb.c])));
           float ea, eb;
@@ -554,10 +589,11 @@ static int validate(const fsg_warp_job* jobs, int njobs, int sx, int sy, int sz,
     }
     if (need_io) {
       FSG_REQUIRE(j.dst_img || j.dst_seg || j.dst_img2, "%s: job %d has no output", who, n);
-      FSG_REQUIRE(!j.dst_img || j.src_img, "%s: job %d dst_img without src_img", who, n);
+      FSG_REQUIRE(!j.dst_img || j.src_img || j.src_pairs, "%s: job %d dst_img without src_img", who, n);
       FSG_REQUIRE(!j.dst_seg || j.src_seg, "%s: job %d dst_seg without src_seg", who, n);
       FSG_REQUIRE(!j.dst_img2 || j.src_img2, "%s: job %d dst_img2 without src_img2", who, n);
       FSG_REQUIRE(j.dst_img != j.src_img || !j.dst_img || (j.mode == 0 && !j.flip), "%s: job %d in-place warp is not allowed", who, n);
+      FSG_REQUIRE(!j.src_pairs || static_cast<const void*>(j.src_pairs) != static_cast<const void*>(j.dst_img), "%s: job %d in-place warp is not allowed", who, n);
     }
   }
   return 0;
@@ -595,25 +631,29 @@ extern "C" int fsg_warp_shift(const fsg_warp_job* jobs, int njobs, int sx, int s
 
 // A job takes the fast kernel when it is the production case; `epi` = it has a gamma or bias epilogue.
 static bool fast_eligible(const fsg_warp_job& j, int sx, int sy, int sz) {
-  return j.mode == 1 && j.fsmall && j.src_img && j.dst_img && j.src_seg && j.dst_seg && !j.dst_img2 && sx % WX == 0 && sy % WY == 0 && sx >= 2 && sy >= 2 && sz >= 2 &&
-         (!j.bf_low || j.dst_img);
+  return j.mode == 1 && j.fsmall && (j.src_img || j.src_pairs) && j.dst_img && j.src_seg && j.dst_seg && !j.dst_img2 && sx % WX == 0 && sy % WY == 0 && sx >= 2 && sy >= 2 &&
+         sz >= 2 && (!j.bf_low || j.dst_img);
 }
 
 extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int sz, void* stream) {
   FSG_REQUIRE(jobs != nullptr && njobs >= 1 && njobs <= FSG_MAX_JOBS, "fsg_warp: njobs=%d outside [1,%d]", njobs, FSG_MAX_JOBS);
   if (int rc = validate(jobs, njobs, sx, sy, sz, true, "fsg_warp")) return rc;
   // partition the batch: fast kernel with / without epilogue, generic kernel for everything else
-  fsg_warp_job part[3][FSG_MAX_JOBS];
-  int cnt[3] = {0, 0, 0};
+  // groups: 0/1 = fast kernel on a float source with / without epilogue, 2 = generic, 3/4 = fast kernel on
+  // the fixed-point pairs source with / without epilogue
+  fsg_warp_job part[5][FSG_MAX_JOBS];
+  int cnt[5] = {0, 0, 0, 0, 0};
   for (int n = 0; n < njobs; ++n) {
     const fsg_warp_job& j = jobs[n];
-    const int g = !fast_eligible(j, sx, sy, sz) ? 2 : ((j.has_gamma || j.bf_low) ? 0 : 1);
+    const bool fast = fast_eligible(j, sx, sy, sz);
+    FSG_REQUIRE(!j.src_pairs || (fast && (reinterpret_cast<uintptr_t>(j.src_pairs) & 3) == 0), "fsg_warp: job %d: src_pairs is only read by the fast path", n);
+    const int g = !fast ? 2 : ((j.src_pairs ? 3 : 0) + ((j.has_gamma || j.bf_low) ? 0 : 1));
     part[g][cnt[g]++] = j;
   }
   cudaStream_t s = as_stream(stream);
   Batch<fsg_warp_job> b;
-  for (int g = 0; g < 2; ++g) {
-    if (!cnt[g]) continue;
+  for (int g = 0; g < 5; ++g) {
+    if (!cnt[g] || g == 2) continue;
     // FSG_WARP_TILE=1 selects the TMA-staged cubic-tile variant (warp_tile.cu).  It is parity-green
     // but measured 2.4x slower than the full-z kernel at 256^3 (r01e: 2.17 ms vs 0.90 ms per 8
     // volumes; one 163 KB block per SM, no overlap of the box load with the gathers), so it is
@@ -622,7 +662,7 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
       const char* e = getenv("FSG_WARP_TILE");
       return e && e[0] == '1';
     }();
-    if (use_tile) {
+    if (use_tile && g < 2) {
       const int rc = launch_warp_tile(part[g], cnt[g], g == 0, sx, sy, sz, s);
       if (rc == 0) continue;
       if (rc > 0) return rc;
@@ -631,9 +671,13 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
     const dim3 grid((sy / WY) * (sx / WX), 1, cnt[g]);
     const size_t smem = field_smem(part[g], cnt[g]);
     if (g == 0)
-      warp_fast_kernel<true><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+      warp_fast_kernel<true, false><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else if (g == 1)
+      warp_fast_kernel<false, false><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else if (g == 3)
+      warp_fast_kernel<true, true><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
     else
-      warp_fast_kernel<false><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+      warp_fast_kernel<false, true><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
   }
   if (cnt[2]) {
     if (int rc = fill_batch(b, part[2], cnt[2])) return rc;

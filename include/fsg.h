@@ -57,11 +57,14 @@ typedef struct fsg_gmm_job {
   const float* mus;      /* [nlabels] */
   const float* sigmas;   /* [nlabels] */
   const float* noise;    /* [nvox] standard normal draws to inject, or NULL -> Philox */
-  float* out;            /* [nvox] */
+  float* out;            /* [nvox], or NULL when out_pairs is used */
   uint8_t* labels_out;   /* optional [nvox] summed labels, or NULL */
   fsg_rng rng;
   int32_t nlabels;
-  int32_t _pad;
+  int32_t row_len;       /* z extent of a row (out_pairs only): pairs do not cross row ends */
+  uint32_t* out_pairs;   /* optional [nvox]: 16.7 fixed point pairs (I[v] | I[v+1] << 16), I * 128 rounded;
+                          * the gather format of fsg_warp's fast path (one 32-bit load brings both z corners;
+                          * quantisation <= 1/256 intensity unit, ~1e-5 of the intensity range) */
 } fsg_gmm_job;
 int fsg_gmm(const fsg_gmm_job* jobs_host, int njobs, int64_t nvox, void* stream);
 
@@ -74,6 +77,7 @@ int fsg_gmm(const fsg_gmm_job* jobs_host, int njobs, int64_t nvox, void* stream)
  * mode 1: coordinates = A*(grid - center + F) + c2, clamped to [0,S-1], minus shift. */
 typedef struct fsg_warp_job {
   const float* src_img;   /* [S] or NULL */
+  const uint32_t* src_pairs; /* fsg_gmm's out_pairs volume instead of src_img (fast path only), or NULL */
   const uint8_t* src_seg; /* [S] or NULL */
   const float* src_img2;  /* optional second image (load_image=True), or NULL */
   float* dst_img;

@@ -355,3 +355,30 @@ def test_sample_batch_streams_do_not_depend_on_the_sharding():
         v = whole[i][0]
         assert torch.isfinite(v).all() and float(v.min()) == 0.0 and float(v.max()) == 1.0
         assert set(torch.unique(whole[i][1]).tolist()) <= set(range(8))
+
+
+def test_fixed_point_pairs_handover_stays_within_tolerance():
+    """FSG_GMM_PAIRS=1 (opt-in): the GMM -> warp hand-over as 16-bit fixed-point z-pairs keeps the
+    segmentation bit-exact and the image within the float tolerance of the reference golden."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path[:0]=['.','oracle','tests']\n"
+        "import numpy as np, torch\n"
+        "from golden_util import load_case\n"
+        "from gpu_util import plan_from_golden, seeds_from_golden, engine_from_golden, rel_err\n"
+        "for name in ('c64_default','c32_all'):\n"
+        "    d=load_case(name); eng=engine_from_golden(d); plan=plan_from_golden(d)\n"
+        "    assert eng.pairs_eligible(plan)\n"
+        "    seg=torch.from_numpy(d['seg_in']).cuda().contiguous().view(-1)\n"
+        "    img,sg=eng.run_base([plan],[seeds_from_golden(d)],[seg],scale=False)\n"
+        "    assert np.array_equal(sg[0].cpu().numpy(), d['seg_out'])\n"
+        "    print('ERR', rel_err(img[0], d['final']))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, FSG_GMM_PAIRS="1"))
+    assert res.returncode == 0, res.stderr[-1500:]
+    errs = [float(l.split()[1]) for l in res.stdout.splitlines() if l.startswith("ERR")]
+    assert len(errs) == 2 and max(errs) <= TOL, errs
