@@ -160,7 +160,7 @@ def run_reference(args, shape):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"base pipeline, all stage probs=1, {shape[0]}^3 @0.5mm phantom; one step = {workers} volumes (1 per host process)", "shape": list(shape)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": f"{args.steps} x {workers} volumes, numpy port of the reference path (oracle/np_oracle.py), one process per volume"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": f"{args.steps} x {workers} volumes, numpy port of the reference path (oracle/np_oracle.py), one process per volume; host has {os.cpu_count()} logical CPUs (workers capped by min(cpus, 32, RAM / 6 GB))"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -284,7 +284,7 @@ def run_ours(args, shape):
     ms = e0.elapsed_time(e1)
     _lib.stats.timing = False
     dominant = _lib.stats.elapsed_ms()
-    launches = _lib.stats.total_calls()
+    launches = _lib.stats.total_kernels()  # kernels of libfsg launched inside the timed region
     clocks = sampler.stop() if rank == 0 else {}
     _lib.stats.reset()
     _lib.stats.timing = True

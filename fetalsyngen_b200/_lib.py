@@ -129,6 +129,10 @@ SIGNATURES = {
     "fsg_fetch_params": (C.c_int, [_vp, _vp, _i64, _vp]),
 }
 
+# kernels one call of an entry point launches on the fused base path (profiles/r01g_launches.csv);
+# entry points not listed launch one
+KERNELS_PER_CALL = {"fsg_warp_shift": 4, "fsg_sepconv": 3, "fsg_zoom_minmax": 3, "fsg_minmax": 3, "fsg_slice_acq_adjoint": 2, "fsg_slice_gamma": 2}
+
 _lib = None
 
 
@@ -174,6 +178,10 @@ class LaunchStats:
 
     def total_calls(self) -> int:
         return sum(self.calls.values())
+
+    def total_kernels(self) -> int:
+        """Kernel launches behind the counted calls (memsets and copies not counted)."""
+        return sum(n * KERNELS_PER_CALL.get(name, 1) for name, n in self.calls.items())
 
     def elapsed_ms(self) -> dict:
         """Per entry point: (number of calls, total device milliseconds). Synchronises."""
