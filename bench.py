@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, help="buffer slots of the host pipeline (e2e leg)")
+    ap.add_argument("--depth", type=int, default=2, help="buffer slots of the host pipeline (e2e leg); 2 slots = 2.5 GiB of pinned host memory per rank at 256^3 / batch 8")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
     shape = (args.shape,) * 3
