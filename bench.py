@@ -41,25 +41,66 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs: NVML polled every
+    2 ms from a thread (a 25 ms timed region still yields ~10 samples); `nvidia-smi -lms` as a fallback."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, False
+        self.sm, self.mask, self.max_mhz = [], 0, None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the PCI bus id
+            import torch
+
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (pynvml, h)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self._stop:
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop = True
+            time.sleep(0.005)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm), "source": "nvml, 2 ms poll"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -72,7 +113,43 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
+
+
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host memory is allocated:
+    the pipeline's staging buffers then live next to the GPU's PCIe root (8 ranks move ~130 GB/s)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        import torch
+
+        props = torch.cuda.get_device_properties(local)
+        h = None
+        for i in range(pynvml.nvmlDeviceGetCount()):
+            hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+            if hasattr(props, "pci_bus_id") and int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(props.pci_bus_id):
+                h = hi
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        node = int(Path(f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node").read_text())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node}, {len(cpus)} cpus"
+        return f"numa node {node}: no allowed cpu there"
+    except Exception as e:  # affinity is an optimisation only
+        return f"numa: not bound ({type(e).__name__})"
 
 
 # ---------------------------------------------------------------------------------- synthetic inputs
@@ -233,6 +310,7 @@ def run_ours(args, shape):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     B = args.batch
@@ -348,7 +426,7 @@ def run_ours(args, shape):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: batch of {B} volumes/GPU/step, {shape[0]}^3 @0.5mm phantom, deformation+GMM+gamma+bias+blur+resample+noise, all stage probs=1, Philox noise, ScaleIntensity fused", "shape": list(shape), "batch_per_gpu": B, "l2": f"inputs larger than L2 ({B * nvox * 4 / 2**20:.0f} MiB per buffer per step)"},
+        "config": {"workload": f"configs[1]: batch of {B} volumes/GPU/step, {shape[0]}^3 @0.5mm phantom, deformation+GMM+gamma+bias+blur+resample+noise, all stage probs=1, Philox noise, ScaleIntensity fused", "shape": list(shape), "batch_per_gpu": B, "l2": f"inputs larger than L2 ({B * nvox * 4 / 2**20:.0f} MiB per buffer per step)", "host_affinity": numa},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes},
         "gpu_launches": launches,
