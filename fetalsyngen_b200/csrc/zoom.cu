@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
   // post 1: v / max (exactly 1 at the maximum).  post 2: ((v / max) - min / max) / (1 - min / max)
   // folded into one FMA, clamped to [0, 1] (float path: tolerance, not bit parity).
   float vmax = 1.f, rmax = 1.f, pa = 1.f, pb = 0.f;
+  float vmax_eq = __int_as_float(0x7fc00000);  // value that maps to exactly 1 under post 2 (NaN: none, for a constant image)
   const int post = job.post;
   if (!REDUCE && post > 0) {
     vmax = job.minmax[1];
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
     const bool flat = den == 0.f;  // constant image: ScaleIntensity returns x * minv = 0
     pa = flat ? 0.f : __fdiv_rn(rmax, den);
     pb = flat ? 0.f : -__fdiv_rn(qmin, den);
+    if (!flat) vmax_eq = vmax;
   }
   const int nrows = sx * sy;
   for (int row = blockIdx.x * ZM_WARPS + warp; row < nrows; row += gridDim.x * ZM_WARPS) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (post == 1) v[e] = div_nr(v[e], vmax, rmax);
-            if (post == 2) v[e] = fminf(fmaxf(__fmaf_rn(v[e], pa, pb), 0.f), 1.f);
+            if (post == 2) v[e] = v[e] == vmax_eq ? 1.f : fminf(fmaxf(__fmaf_rn(v[e], pa, pb), 0.f), 1.f);  // the maximum maps to exactly 1 (ScaleIntensity)
           }
           __stcs(reinterpret_cast<float4*>(job.dst + (size_t)row * sz + 128 * m + 4 * lane), make_float4(v[0], v[1], v[2], v[3]));
         }
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
           hi = fmaxf(hi, val);
         } else {
           if (post == 1) val = div_nr(val, vmax, rmax);
-          if (post == 2) val = fminf(fmaxf(__fmaf_rn(val, pa, pb), 0.f), 1.f);
+          if (post == 2) val = val == vmax_eq ? 1.f : fminf(fmaxf(__fmaf_rn(val, pa, pb), 0.f), 1.f);
           out[k] = val;
         }
       }
