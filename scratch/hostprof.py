@@ -22,4 +22,4 @@ print("host ms/step", (t1-t0)*100, "incl sync", (t2-t0)*100)
 pr=cProfile.Profile(); pr.enable()
 for _ in range(10): step()
 pr.disable(); torch.cuda.synchronize()
-s=io.StringIO(); pstats.Stats(pr,stream=s).sort_stats('cumulative').print_stats(60); print(s.getvalue()[:9000])
+s=io.StringIO(); pstats.Stats(pr,stream=s).sort_stats("tottime").print_stats(45); print(s.getvalue()[:9000])
