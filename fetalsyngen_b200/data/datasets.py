@@ -221,3 +221,80 @@ class FetalSynthDataset(FetalDataset):
         names = [self._sub_ses_string(*self.sub_ses[i]) for i in indices]
         img, seg, params = self.generator.sample_batch(segs, [self.seed_paths[n] for n in names], scale=scale)
         return {"image": img.unsqueeze(1), "label": seg.unsqueeze(1), "name": names}, params
+
+
+class DeviceBatchLoader:
+    """GPU-resident replacement of ``DataLoader(FetalSynthDataset, num_workers=k)`` for an on-the-fly
+    training loop on the same device (the reference hands CPU tensors from spawned workers to the
+    trainer, ``fetalsyngen/test_dl.py:17-23``, because "GPU memory cannot be easily shared between
+    processes", ``docs/datasets.md:4-6``).
+
+    Iterating yields ``{"image": (B,1,H,W,D) float32 in [0,1], "label": (B,1,H,W,D) uint8 or int64,
+    "name": [...], "params": [...]}`` on the generator's device.  Batches are produced on a private
+    CUDA stream one step ahead of the consumer into ``depth`` rotating buffer sets; the consumer's
+    stream waits on the producing event only, nothing is copied to the host.  A yielded batch stays
+    valid until ``depth - 1`` further batches have been requested.
+    """
+
+    def __init__(self, dataset: "FetalSynthDataset", batch_size: int, num_batches: int | None = None, shuffle: bool = True, labels_int64: bool = False,
+                 depth: int = 2, base_seed: int | None = None, rank: int = 0, world: int = 1):
+        if dataset.image_as_intensity or dataset.seed_path is None:
+            raise ValueError("DeviceBatchLoader needs seed-based intensity generation")
+        if depth < 2:
+            raise ValueError("depth must be >= 2 (one batch in use, one in flight)")
+        self.ds, self.B, self.depth = dataset, int(batch_size), int(depth)
+        self.num_batches = num_batches if num_batches is not None else max(1, len(dataset) // self.B)
+        self.shuffle, self.labels_int64 = shuffle, labels_int64
+        self.base_seed, self.rank, self.world = base_seed, rank, world
+        gen = dataset.generator
+        self.shape = tuple(gen.shape)
+        self.eng = gen.engine(self.shape)
+        dev = self.eng.device
+        self.stream = torch.cuda.Stream(device=dev)
+        shp = (self.B, *self.shape)
+        self._img = [torch.empty(shp, dtype=torch.float32, device=dev) for _ in range(self.depth)]
+        self._seg = [torch.empty(shp, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+        self._lab = [torch.empty(shp, dtype=torch.int64, device=dev) for _ in range(self.depth)] if labels_int64 else None
+        self._released = [None] * self.depth  # event: the consumer is done with this slot
+
+    def __len__(self):
+        return self.num_batches
+
+    def _indices(self, step, rs):
+        n = len(self.ds)
+        return [int(v) for v in (rs.randint(0, n, self.B) if self.shuffle else [(step * self.B + k) % n for k in range(self.B)])]
+
+    def _produce(self, step, slot, rs):
+        from ..sharding import step_ids
+
+        idx = self._indices(step, rs)
+        segs = [self.ds._segmentation(i) for i in idx]
+        names = [self.ds._sub_ses_string(*self.ds.sub_ses[i]) for i in idx]
+        kw = {}
+        if self.base_seed is not None:  # reproducible, sharding-independent sample streams
+            kw = {"sample_ids": step_ids(step, self.B, self.rank, self.world), "base_seed": self.base_seed}
+        with torch.cuda.stream(self.stream):
+            if self._released[slot] is not None:
+                self.stream.wait_event(self._released[slot])
+            _, _, params = self.ds.generator.sample_batch(segs, [self.ds.seed_paths[n] for n in names], scale=True, out_img=self._img[slot], out_seg=self._seg[slot], **kw)
+            if self._lab is not None:
+                self.eng._call("fsg_u8_to_i64", self._seg[slot].data_ptr(), self._lab[slot].data_ptr(), self._seg[slot].numel())
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return done, names, params
+
+    def __iter__(self):
+        rs = np.random.RandomState(None if self.base_seed is None else self.base_seed + 7919 * self.rank)
+        pending = self._produce(0, 0, rs)
+        for step in range(self.num_batches):
+            slot = step % self.depth
+            done, names, params = pending
+            if step + 1 < self.num_batches:
+                pending = self._produce(step + 1, (step + 1) % self.depth, rs)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(done)
+            label = self._lab[slot] if self._lab is not None else self._seg[slot]
+            yield {"image": self._img[slot].unsqueeze(1), "label": label.unsqueeze(1), "name": names, "params": params}
+            rel = torch.cuda.Event()
+            rel.record(cur)  # everything the consumer queued on its stream so far has read this slot
+            self._released[slot] = rel

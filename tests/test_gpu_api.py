@@ -168,3 +168,48 @@ def test_volume_384_single_sample():
     img, seg, _ = gen.sample_batch([seg_d], [seeds_d], scale=True, sample_ids=[0], base_seed=1)
     assert img.shape == (1, *shape) and torch.isfinite(img).all() and float(img.max()) == 1.0
     assert set(torch.unique(seg).tolist()) <= set(np.unique(seg_h).tolist())
+
+
+def test_device_batch_loader_matches_sample_batch_and_keeps_batches_valid(tmp_path):
+    """DeviceBatchLoader (the GPU-resident DataLoader replacement): batches equal the ones
+    `generator.sample_batch` produces for the same sample ids, stay on the device, and a yielded batch
+    is still intact after the next one has been requested (depth 3: valid for depth - 1 further requests)."""
+    from fetalsyngen_b200.data.datasets import DeviceBatchLoader, FetalSynthDataset
+    from fetalsyngen_b200.sharding import step_ids
+    from fetalsyngen_b200.utils import nifti
+
+    shape = (64, 64, 64)
+    seg_h, seeds_h = label_phantom(shape)
+    aff = np.diag([0.5, 0.5, 0.5, 1.0])
+    for sub in ("sub-a", "sub-b"):
+        d = tmp_path / "bids" / sub / "anat"
+        d.mkdir(parents=True)
+        nifti.write_nifti(d / f"{sub}_rec-x_T2w_dseg.nii.gz", seg_h.astype(np.float32), aff)
+        for n in range(1, 3):
+            sd = tmp_path / "seeds" / f"subclasses_{n}" / sub / "anat"
+            sd.mkdir(parents=True)
+            for m in range(1, 5):
+                nifti.write_nifti(sd / f"{sub}_rec-x_T2w_dseg_mlabel_{m}.nii.gz", seeds_h[m - 1], aff)
+    gen = _gen(shape)
+    gen.intensity_generator.min_subclusters, gen.intensity_generator.max_subclusters = 1, 2
+    ds = FetalSynthDataset(str(tmp_path / "bids"), gen, str(tmp_path / "seeds"), None)
+    loader = DeviceBatchLoader(ds, batch_size=2, num_batches=4, shuffle=False, labels_int64=True, base_seed=21, depth=3)
+    assert len(loader) == 4
+    kept = []
+    for step, batch in enumerate(loader):
+        assert batch["image"].shape == (2, 1, *shape) and batch["image"].device.type == "cuda" and batch["label"].dtype == torch.int64
+        assert len(batch["name"]) == 2 and len(batch["params"]) == 2
+        kept.append((batch["image"], batch["label"], batch["image"].clone(), batch["label"].clone()))
+        if step >= 1:  # the previous batch (other slot) must not have been overwritten yet
+            torch.cuda.synchronize()
+            assert torch.equal(kept[step - 1][0], kept[step - 1][2]) and torch.equal(kept[step - 1][1], kept[step - 1][3])
+    torch.cuda.synchronize()
+    # same ids through the plain batched call
+    for step in range(4):
+        idx = [(step * 2 + k) % len(ds) for k in range(2)]
+        segs = [ds._segmentation(i) for i in idx]
+        names = [ds._sub_ses_string(*ds.sub_ses[i]) for i in idx]
+        img, seg, _ = gen.sample_batch(segs, [ds.seed_paths[n] for n in names], scale=True, sample_ids=step_ids(step, 2, 0, 1), base_seed=21)
+        assert torch.equal(img.unsqueeze(1), kept[step][2]) and torch.equal(seg.unsqueeze(1).long(), kept[step][3])
+    with pytest.raises(ValueError):
+        DeviceBatchLoader(ds, batch_size=2, depth=1)
