@@ -50,6 +50,44 @@ __device__ __forceinline__ float lerp2(float a, float wf, float b, float wc) {
   return __fadd_rn(__fmul_rn(a, wf), __fmul_rn(b, wc));
 }
 
+// Packed FP32x2 (sm_100: FADD2 / FMUL2 / FFMA2 take one issue slot for two lanes).  add/sub are
+// individually rounded like their scalar forms.  ptxas contracts mul.f32x2 feeding add.f32x2 into
+// FFMA2 even under --fmad=false, so the bit-exact coordinate chain keeps its products scalar
+// (FMUL writes straight into the halves of a register pair) and packs only the adds; mul2 / fma2
+// are used on the tolerance-checked image path.
+typedef unsigned long long P2;
+__device__ __forceinline__ P2 pk(float a, float b) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(P2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) {
+  P2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 add2_rz(P2 a, P2 b) {
+  P2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 sub2(P2 a, P2 b) {
+  P2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) {
+  P2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // ------------------------------------------------------------------ ordered float atomics
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);

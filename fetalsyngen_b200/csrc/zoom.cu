@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
 
   const float* __restrict__ src = job.src;
   const float inf = __int_as_float(0x7f800000);
-  float lo = inf, hi = -inf;
+  float lo_ = inf, hi_ = -inf;
   // post 1: v / max (exactly 1 at the maximum).  post 2: ((v / max) - min / max) / (1 - min / max)
   // folded into one FMA, clamped to [0, 1] (float path: tolerance, not bit parity).
   float vmax = 1.f, rmax = 1.f, pa = 1.f, pb = 0.f;
@@ -94,12 +94,17 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
         vfc[u] = in ? __ldg(pfc + K) : 0.f;
         vcc[u] = in ? __ldg(pcc + K) : 0.f;
       }
+      // image path (tolerance, not bit parity): the x / y blends run as packed FP32x2 FMAs on two K
+      // positions at a time
+      const P2 wfx = pk(tx.wf, tx.wf), wcx = pk(tx.wc, tx.wc), wfy = pk(ty.wf, ty.wf), wcy = pk(ty.wc, ty.wc);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int K = K0 + 32 * u;
-        const float a_f = blend(tx.wf, vff[u], tx.wc, vcf[u]);  // tmp1[y=f]
-        const float a_c = blend(tx.wf, vfc[u], tx.wc, vcc[u]);  // tmp1[y=c]
-        if (K < n2) s_row[K] = blend(ty.wf, a_f, ty.wc, a_c);   // tmp2
+      for (int u = 0; u < 4; u += 2) {
+        const P2 a_f = fma2(wfx, pk(vff[u], vff[u + 1]), mul2(wcx, pk(vcf[u], vcf[u + 1])));  // tmp1[y=f]
+        const P2 a_c = fma2(wfx, pk(vfc[u], vfc[u + 1]), mul2(wcx, pk(vcc[u], vcc[u + 1])));  // tmp1[y=c]
+        float r0, r1;
+        upk(fma2(wfy, a_f, mul2(wcy, a_c)), r0, r1);                                           // tmp2
+        if (K0 + 32 * u < n2) s_row[K0 + 32 * u] = r0;
+        if (K0 + 32 * (u + 1) < n2) s_row[K0 + 32 * (u + 1)] = r1;
       }
     }
     __syncwarp();
@@ -108,18 +113,28 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
       for (int m = 0; m < (KG > 0 ? KG : 1); ++m) {
         float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 4; e += 2) {
           const int q = 4 * m + e;
-          v[e] = blend(twf[q], s_row[tfc[q] & 0xffff], twc[q], s_row[tfc[q] >> 16]);
+          const P2 lo = pk(s_row[tfc[q] & 0xffff], s_row[tfc[q + 1] & 0xffff]), hi = pk(s_row[tfc[q] >> 16], s_row[tfc[q + 1] >> 16]);
+          upk(fma2(pk(twf[q], twf[q + 1]), lo, mul2(pk(twc[q], twc[q + 1]), hi)), v[e], v[e + 1]);
         }
         if (REDUCE) {
-          lo = fminf(fminf(lo, v[0]), fminf(fminf(v[1], v[2]), v[3]));
-          hi = fmaxf(fmaxf(hi, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
+          lo_ = fminf(fminf(lo_, v[0]), fminf(fminf(v[1], v[2]), v[3]));
+          hi_ = fmaxf(fmaxf(hi_, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
         } else {
+          if (post == 1) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (post == 1) v[e] = div_nr(v[e], vmax, rmax);
-            if (post == 2) v[e] = v[e] == vmax_eq ? 1.f : fminf(fmaxf(__fmaf_rn(v[e], pa, pb), 0.f), 1.f);  // the maximum maps to exactly 1 (ScaleIntensity)
+            for (int e = 0; e < 4; ++e) v[e] = div_nr(v[e], vmax, rmax);
+          }
+          if (post == 2) {
+            const P2 pa2 = pk(pa, pa), pb2 = pk(pb, pb);
+            float n0, n1, n2_, n3;
+            upk(fma2(pk(v[0], v[1]), pa2, pb2), n0, n1);
+            upk(fma2(pk(v[2], v[3]), pa2, pb2), n2_, n3);
+            v[0] = v[0] == vmax_eq ? 1.f : fminf(fmaxf(n0, 0.f), 1.f);  // the maximum maps to exactly 1 (ScaleIntensity)
+            v[1] = v[1] == vmax_eq ? 1.f : fminf(fmaxf(n1, 0.f), 1.f);
+            v[2] = v[2] == vmax_eq ? 1.f : fminf(fmaxf(n2_, 0.f), 1.f);
+            v[3] = v[3] == vmax_eq ? 1.f : fminf(fmaxf(n3, 0.f), 1.f);
           }
           __stcs(reinterpret_cast<float4*>(job.dst + (size_t)row * sz + 128 * m + 4 * lane), make_float4(v[0], v[1], v[2], v[3]));
         }
@@ -131,8 +146,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
         const float wc = __int_as_float(e.y), wf = sub_rn(1.0f, wc);
         float val = blend(wf, s_row[e.x & 0xffff], wc, s_row[e.x >> 16]);
         if (REDUCE) {
-          lo = fminf(lo, val);
-          hi = fmaxf(hi, val);
+          lo_ = fminf(lo_, val);
+          hi_ = fmaxf(hi_, val);
         } else {
           if (post == 1) val = div_nr(val, vmax, rmax);
           if (post == 2) val = val == vmax_eq ? 1.f : fminf(fmaxf(__fmaf_rn(val, pa, pb), 0.f), 1.f);
@@ -142,8 +157,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 3) zoom_rows_kernel(const __grid_c
     }
   }
   if (REDUCE) {
-    lo = warp_min(lo);
-    hi = warp_max(hi);
+    float lo = warp_min(lo_), hi = warp_max(hi_);
     __shared__ float slo[ZM_WARPS], shi[ZM_WARPS];
     if (lane == 0) {
       slo[warp] = lo;
