@@ -35,6 +35,10 @@ class _Slot:
 
 
 class HostPipeline:
+    """``batch`` volumes per slot, ``depth`` slots.  A caller that wants a step of N volumes can run it as
+    N / batch micro-steps (``run(steps * N // batch)``): the pipeline then fills and drains in units of
+    ``batch`` volumes instead of N, which matters when only a few steps are timed."""
+
     def __init__(self, generator, batch: int, depth: int = 2):
         self.gen = generator
         self.B = batch
