@@ -140,8 +140,16 @@ class FetalSynthGen:
         else:
             if img_dev is None:
                 raise ValueError("If no seeds are passed, an image must be loaded to be used as intensity prior!")
-            lo, hi = img_dev.min(), img_dev.max()
-            src = ((img_dev - lo) / (hi - lo) * 255).view(1, -1)  # model.py:138
+            # (image - min) / (max - min) * 255 (model.py:138): libfsg reduction + scale with the range
+            # pre-divided by 255 (two floats cross the bus; this is the rarely used image-prior path)
+            from .. import _lib
+            from ..engine import _stream
+
+            mm = torch.empty(2, dtype=torch.float32, device=eng.device)
+            _lib.call("fsg_minmax", img_dev.data_ptr(), img_dev.numel(), mm.data_ptr(), _stream())
+            lo, hi = (float(v) for v in mm.cpu())
+            mm2 = torch.tensor([lo, lo + (hi - lo) / 255.0], dtype=torch.float32).to(eng.device)
+            _lib.call("fsg_scale_intensity", img_dev.data_ptr(), src.data_ptr(), img_dev.numel(), mm2.data_ptr(), _stream())
         dst = torch.empty((1, eng.nvox), dtype=torch.float32, device=eng.device)
         dseg = torch.empty((1, eng.nvox), dtype=torch.uint8, device=eng.device)
         dst2 = None if img_dev is None else torch.empty((1, eng.nvox), dtype=torch.float32, device=eng.device)

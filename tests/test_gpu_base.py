@@ -382,3 +382,55 @@ def test_fixed_point_pairs_handover_stays_within_tolerance():
     assert res.returncode == 0, res.stderr[-1500:]
     errs = [float(l.split()[1]) for l in res.stdout.splitlines() if l.startswith("ERR")]
     assert len(errs) == 2 and max(errs) <= TOL, errs
+
+
+@pytest.mark.parametrize("shape,seed", [((64, 64, 64), 7), ((40, 52, 36), 8)])
+def test_second_image_channel_vs_oracle(shape, seed):
+    """load_image=True (datasets.py:279-306, affine_nonrigid.py:190-191): the real image rides through the
+    same deformation as the synthetic one (third fast_3D_interp_torch call) — generic warp kernel."""
+    rs = np.random.RandomState(seed)
+    seg, seeds = _phantom(rs, shape)
+    p = _random_plan(rs, shape, DEV, resample=False)
+    p.gamma, p.bf_low = None, None
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    image = (rs.rand(*shape) * 1000).astype(np.float32)
+    q = _plan_to_oracle(p)
+    q["gmm_noise"] = q["gmm_noise"].reshape(shape)
+    q["gamma"], q["bf_low"] = None, None
+    lab = sum(s.astype(np.int64) for s in seeds)
+    want_out = O.gmm_intensities(lab, q["mus"], q["sigmas"], q["gmm_noise"])
+    F = O.zoom_linear(q["Fsmall"], np.asarray(shape, dtype=np.float64) / np.asarray(q["Fsmall"].shape[:3], dtype=np.float64))
+    coords = O.deformation_coords(shape, shape, q["A"], q["c2"], F)
+    want_out, want_seg, want_img = O.apply_deformation(want_out, seg, coords, q["flip"], image)
+    src = torch.empty((1, eng.nvox), dtype=torch.float32, device=DEV)
+    dseeds = [torch.from_numpy(s).to(DEV).view(-1) for s in seeds]
+    eng.gmm([p], [dseeds], src)
+    dst, dseg, dst2 = torch.empty_like(src), torch.empty((1, eng.nvox), dtype=torch.uint8, device=DEV), torch.empty_like(src)
+    eng.warp([p], src, [torch.from_numpy(seg).to(DEV).view(-1)], dst, dseg, [torch.from_numpy(image).to(DEV).view(-1)], dst2, epilogue=False)
+    np.testing.assert_array_equal(dseg[0].cpu().numpy().reshape(shape), want_seg)
+    assert rel_err(dst[0].view(shape), want_out) <= TOL
+    assert rel_err(dst2[0].view(shape), np.ascontiguousarray(want_img)) <= TOL
+
+
+def test_image_as_intensity_prior_path():
+    """image_as_intensity=True (model.py:131-140): no seeds, the real image normalised to 0..255 is the
+    intensity prior; with every gate off the output is exactly that normalisation."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+
+    shape = (32, 32, 32)
+    gen = bench.build_generator(shape, DEV)
+    for st in (gen.spatial_deform, gen.resampled, gen.biasfield, gen.noise, gen.gamma):
+        st.prob = 0.0
+    rs = np.random.RandomState(0)
+    image = torch.from_numpy((rs.rand(*shape) * 900 + 50).astype(np.float32)).to(DEV)
+    seg = torch.from_numpy(rs.randint(0, 8, shape).astype(np.float32)).to(DEV)
+    np.random.seed(0)
+    out, sg, img2, params = gen.sample(image=image, segmentation=seg, seeds=None)
+    want = (image - image.min()) / (image.max() - image.min()) * 255
+    assert float((out - want).abs().max()) <= 255 * 2e-6
+    assert torch.equal(sg, seg) and torch.equal(img2, image)
+    assert params["selected_seeds"] == {} and params["seed_intensities"] == {}
