@@ -79,6 +79,12 @@ class FetalSynthGen:
             # sampling grids for every sample): all resolution-simulation tables of this generator
             for a in sorted(set(eng.shape)):
                 eng.tables.prewarm_resample(a, float(eng.resolution[eng.shape.index(a)]), key[0], key[1])
+                # zoom tables of the control grids (deformation: nonlin_scale * S nodes, bias: bf_scale * S)
+                for lo, hi in ((getattr(self.spatial_deform, "nonlin_scale_min", 0), getattr(self.spatial_deform, "nonlin_scale_max", 0)),
+                               (getattr(self.biasfield, "scale_min", 0), getattr(self.biasfield, "scale_max", 0))):
+                    if hi and hi > 0:
+                        for n in range(max(int(np.floor(lo * a)), 1), min(int(np.ceil(hi * a)) + 1, a) + 1):
+                            eng.tables.zoom(n, a / n, a)
             eng._prewarmed = key
         return eng
 
@@ -245,6 +251,23 @@ class FetalSynthGen:
         shape = tuple(self.shape)
         eng = self.engine(shape)
         plans, params, vols = [], [], []
+        if sample_ids is not None and not genparams:
+            # throughput path: every sample of the step drawn at once (batch_draw.py), a pure function of
+            # (base_seed, sample id)
+            from ..batch_draw import draw_plans
+
+            use_dict = any(isinstance(sd, dict) for sd in seeds)
+            out = draw_plans(self, list(sample_ids), int(base_seed or 0), shape, with_subclusters=use_dict)
+            plans, params = out[0], out[1]
+            for b, sd in enumerate(seeds):
+                if isinstance(sd, dict):
+                    m2s = {m: int(out[2][b, m - 1]) for m in range(1, self.intensity_generator.meta_labels + 1)}
+                    vols.append([v.view(-1) for v in self.intensity_generator.select_seeds(sd, m2s, eng.device)])
+                    params[b]["selected_seeds"] = {"mlabel2subclusters": m2s}
+                else:
+                    vols.append([v.view(-1) for v in sd])
+            img, seg = eng.run_base(plans, vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)
+            return img, seg, params
         for b in range(len(segmentations)):
             if sample_ids is not None:
                 from ..sharding import sample_seed

@@ -232,3 +232,62 @@ def test_bench_reference_arm_nonzero_rank_exits_without_work():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+# ----------------------------------------------------------------------------- vectorised batch draws
+def test_batch_draw_matches_the_stage_classes_statistically():
+    """batch_draw.draw_plans (one counter-based draw for a whole step) must follow the same
+    distributions as the per-sample stage draws that mirror the reference (KS tests on every scalar,
+    moments of the GMM tables) and be a pure function of (base_seed, sample id)."""
+    from scipy.stats import ks_2samp
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from fetalsyngen_b200.batch_draw import draw_plans, uniforms
+    from fetalsyngen_b200.engine import SamplePlan
+
+    shape = (256, 256, 256)
+    gen = bench.build_generator(shape, "cuda:0")
+    for st in (gen.spatial_deform, gen.resampled, gen.biasfield, gen.noise, gen.gamma):
+        st.prob = 0.8
+    n = 3000
+    plans, params = draw_plans(gen, list(range(n)), 99, shape)
+    # determinism / independence of the batch composition
+    p2, _ = draw_plans(gen, [7, 2999, 0], 99, shape)
+    for a, b in zip(p2, (plans[7], plans[2999], plans[0])):
+        assert np.array_equal(a.mus, b.mus) and (a.A is None) == (b.A is None) and (a.A is None or np.array_equal(a.A, b.A)) and a.gamma == b.gamma
+    assert not np.array_equal(draw_plans(gen, [7], 100, shape)[0][0].mus, plans[7].mus)
+    u = uniforms(1, np.arange(2000), 50)
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01 and abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 0.08
+
+    np.random.seed(5)
+    torch.manual_seed(5)
+    ref = []
+    for _ in range(n):
+        p = SamplePlan()
+        gen._draw_generate(p, None, shape, {}, None, device_grids=True)
+        p.mus, p.sigmas = gen.intensity_generator.draw_gmm({})
+        gen._draw_augment(p, shape, {}, None, device_grids=True)
+        ref.append(p)
+
+    def col(ps, f):
+        return np.array([f(p) for p in ps if f(p) is not None], dtype=np.float64)
+
+    feats = {
+        "A00": lambda p: None if p.A is None else p.A[0, 0], "A01": lambda p: None if p.A is None else p.A[0, 1], "A21": lambda p: None if p.A is None else p.A[2, 1],
+        "A22": lambda p: None if p.A is None else p.A[2, 2], "nonlin_std": lambda p: None if p.fsmall_dev is None else p.fsmall_dev[1],
+        "fsize": lambda p: None if p.fsmall_dev is None else p.fsmall_dev[0][0], "gamma": lambda p: p.gamma,
+        "bf_std": lambda p: None if p.bf_dev is None else p.bf_dev[1], "bf_size": lambda p: None if p.bf_dev is None else p.bf_dev[0][1],
+        "spacing": lambda p: None if p.spacing is None else p.spacing[0], "std0": lambda p: None if p.stds is None else p.stds[0], "noise_std": lambda p: p.noise_std,
+        "mus0": lambda p: p.mus[0], "mus15": lambda p: p.mus[15], "mus45": lambda p: p.mus[45], "sig22": lambda p: p.sigmas[22],
+    }
+    for name, f in feats.items():
+        a, b = col(plans, f), col(ref, f)
+        assert abs(len(a) - len(b)) < 5 * np.sqrt(n * 0.8 * 0.2) + 1, (name, len(a), len(b))  # gate probabilities
+        assert ks_2samp(a, b).pvalue > 1e-4, (name, ks_2samp(a, b))
+    flips = np.mean([p.flip for p in plans if p.deform]), np.mean([p.flip for p in ref if p.deform])
+    assert abs(flips[0] - flips[1]) < 0.06
+    # c2 = centre of the volume when shape == size; float64
+    assert all(np.allclose(p.c2, 127.5) and p.c2.dtype == np.float64 for p in plans if p.deform)
+    # parameter dictionaries keep the reference's keys
+    assert set(params[0]) == {"selected_seeds", "seed_intensities", "deform_params", "gamma_params", "bf_params", "resample_params", "noise_params"}
