@@ -77,11 +77,16 @@ class GridJob(C.Structure):
     _fields_ = [("out", _vp), ("rng", Rng), ("scale", _f32), ("n", _i32)]
 
 
+class EmJob(C.Structure):
+    _fields_ = [("x", _vp), ("index", _vp), ("n", _i64), ("k", _i32), ("label_base", _i32), ("params", _vp), ("trace", _vp), ("state", _vp), ("seeds", _vp),
+                ("labels", _vp), ("out", _vp), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64)]
+
+
 class SepComposeJob(C.Structure):
     _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32)]
 
 
-_STRUCTS = {"fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
+_STRUCTS = {"fsg_em_job": EmJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
@@ -127,6 +132,12 @@ SIGNATURES = {
     "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
     "fsg_draw_grids": (C.c_int, [C.POINTER(GridJob), C.c_int, _vp]),
     "fsg_fetch_params": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fsg_seed_partition_workspace": (_i64, [_i64]),
+    "fsg_seed_partition": (C.c_int, [_vp, _vp, C.c_char_p, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "fsg_em_workspace": (_i64, [C.c_int]),
+    "fsg_em_seed": (C.c_int, [C.POINTER(EmJob), C.c_int, _vp, _i64, _vp]),
+    "fsg_em_fit": (C.c_int, [C.POINTER(EmJob), C.c_int, C.c_int, C.c_double, C.c_double, _vp, _i64, _vp]),
+    "fsg_em_predict": (C.c_int, [C.POINTER(EmJob), C.c_int, _vp, _i64, _vp]),
 }
 
 # kernels one call of an entry point launches on the fused base path (profiles/r01g_launches.csv);

@@ -336,6 +336,53 @@ typedef struct fsg_grid_job {
 } fsg_grid_job;
 int fsg_draw_grids(const fsg_grid_job* jobs_host, int njobs, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K6 — seed generation.  Replaces scripts/generate_seeds.py:133-211:
+ * label fusion into meta-labels + sklearn GaussianMixture(n_components, n_init=5,
+ * init_params="k-means++").fit_predict on the image voxels of each meta-label (one feature,
+ * full covariance, float64 like the reference's call: sklearn up-casts the torch tensor it is given).
+ *
+ * fsg_seed_partition (generate_seeds.py:133-146,190-198): meta = lut[seg]; lut value 4 marks the
+ *   labels treated as background, which become meta-label 4 where image != 0 and 0 elsewhere; NaN
+ *   image values count as 0.  Writes the image values of meta-labels 1..4 back to back, each in
+ *   voxel order, into x[n] with their flat voxel indices in index[n], and the four partition
+ *   sizes into counts[4] (device).  lut: 256 bytes of HOST memory.  n < 2^31.
+ *   workspace: >= fsg_seed_partition_workspace(n) bytes of device memory.
+ * fsg_em_seed: greedy k-means++ (sklearn/cluster/_kmeans.py:_kmeans_plusplus, 2 + int(ln k) local
+ *   trials, D^2 sampling by an exponential race over Philox uniforms) -> job.seeds[k] sample indices.
+ * fsg_em_fit: _initialize from the one-hot responsibilities at job.seeds, then E / M steps until
+ *   |delta lower bound| < tol or max_iter; every job is one initialisation, all jobs advance in the
+ *   same launches and a converged job's blocks exit at once (no host round trip inside the loop).
+ *   Results: job.params = weights | means | covariances (3 x FSG_EM_MAXK doubles), job.trace[i] =
+ *   lower bound of iteration i (1-based; the caller keeps the initialisation with the largest final
+ *   value, mixture/_base.py:282-287), job.state = {n_iter, converged}.
+ * fsg_em_predict: final E step, argmax component (first maximum) -> job.labels[i] (if non-NULL)
+ *   and job.out[job.index[i]] = label_base + component (if out non-NULL).
+ * Any njobs >= 1; job structs are HOST memory; workspace: >= fsg_em_workspace(njobs) bytes. */
+#define FSG_EM_MAXK 16
+typedef struct fsg_em_job {
+  const float* x;       /* [n] values of one meta-label (device) */
+  const int32_t* index; /* [n] flat voxel index of every value (device); may be NULL when out is NULL */
+  int64_t n;
+  int32_t k;            /* components, 1..FSG_EM_MAXK, k <= n */
+  int32_t label_base;   /* 10 * meta-label (generate_seeds.py:207-209) */
+  double* params;       /* [3 * FSG_EM_MAXK] (device) */
+  double* trace;        /* [max_iter + 1] (device) */
+  int32_t* state;       /* [2] (device) */
+  int32_t* seeds;       /* [FSG_EM_MAXK] initial sample indices (device): out of fsg_em_seed, in of fsg_em_fit */
+  uint8_t* labels;      /* [n] or NULL (device) */
+  int8_t* out;          /* seed volume or NULL (device) */
+  uint64_t rng_seed;    /* Philox key of the k-means++ draws */
+  uint64_t rng_stream;  /* ... and subsequence: one per initialisation */
+} fsg_em_job;
+int64_t fsg_seed_partition_workspace(int64_t n);
+int fsg_seed_partition(const float* image, const uint8_t* seg, const uint8_t* lut_host, int64_t n, float* x, int32_t* index, int64_t* counts, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+int64_t fsg_em_workspace(int njobs);
+int fsg_em_seed(const fsg_em_job* jobs_host, int njobs, void* workspace, int64_t workspace_bytes, void* stream);
+int fsg_em_fit(const fsg_em_job* jobs_host, int njobs, int max_iter, double tol, double reg_covar, void* workspace, int64_t workspace_bytes, void* stream);
+int fsg_em_predict(const fsg_em_job* jobs_host, int njobs, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* RNG self-test: fills out[n] with Philox standard normals exactly as the kernels draw them;
  * raw != 0 writes the raw 32-bit words instead (for the Random123 known-answer test). */
 int fsg_philox_fill(fsg_rng rng, float* out, int64_t n, int raw, void* stream);

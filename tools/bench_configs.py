@@ -258,9 +258,85 @@ def run_sample_api(args):
                       "results": res, "note": "host tensors out: float32 image (1,S,S,S) + int64 label on the CPU, as the reference returns them; seeds / segmentation decoded once and cached on the device"}))
 
 
+def seed_subject(S, seed=11):
+    """Synthetic subject for seed generation: phantom labels + a T2w-like image (tissue means, texture,
+    smooth shading, non-brain tissue around the labelled region, zero background)."""
+    shape = (S, S, S)
+    seg, _ = label_phantom(shape, seed=5)
+    rs = np.random.RandomState(seed)
+    base = np.array([0, 900, 300, 450, 820, 520, 330, 480], dtype=np.float32)[seg]
+    tex = rs.standard_normal(shape).astype(np.float32)
+    image = np.maximum(base + 40 * tex + 60 * np.sin(np.arange(S, dtype=np.float32) / (S / 13))[None, None, :], 0).astype(np.float32)
+    g = np.meshgrid(*[np.linspace(-1, 1, s, dtype=np.float32) for s in shape], indexing="ij", sparse=True)
+    r = np.sqrt(sum(gi**2 for gi in g))
+    outer = (seg == 0) & (r > 0.85)
+    ring = (seg == 0) & (r <= 0.85)
+    image[outer] = 0
+    image[ring] = np.maximum(200 + 70 * tex[ring], 1)
+    return image, seg
+
+
+def run_seeds(args):
+    """scripts/generate_seeds.py for one subject, sub-class counts 1..6 (what the
+    bundled seeds use): 20 fits x 5 initialisations.  GPU: SeedGenerator.split_labels from host arrays
+    (H2D, partition, k-means++, EM, predict, label volumes on the device).  CPU: the unmodified
+    scikit-learn call of the reference (GaussianMixture(k, n_init=5, init_params="k-means++")
+    .fit_predict on a torch tensor, i.e. float64) on a bounded sample of the same fits."""
+    import time
+    import warnings
+
+    from fetalsyngen_b200.seeds import SeedGenerator
+
+    S = args.shape
+    image, seg = seed_subject(S)
+    subs = list(range(1, 7))
+    gen = SeedGenerator("feta", DEV, seed=1)
+    out = gen.split_labels(image, seg, subs)  # warm-up (module load, allocator)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(args.reps):
+        t0 = time.perf_counter()
+        out = gen.split_labels(image, seg, subs)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    x, index, counts = gen.partition(image, seg)
+    fits = gen.last_fit
+    iters = {f"{s}x{m + 1}": f["n_iter"] for (s, m), f in fits.items()}
+    comp_evals = sum(counts[m] * s * f["n_iter"] for (s, m), f in fits.items())  # best initialisation only (lower bound on the work done)
+    # device-resident inputs
+    img_d, seg_d = torch.from_numpy(image).to(DEV), torch.from_numpy(seg).to(DEV)
+    t_dev = timed(lambda: gen.split_labels(img_d, seg_d.cpu().numpy(), subs), reps=args.reps)
+    line = {"config": "seed generation, one subject, sub-class counts 1..6 (scripts/generate_seeds.py)", "shape": [S, S, S], "voxels_per_meta_label": counts,
+            "fits": len(fits), "initialisations": len(fits) * gen.n_init, "gpu_s_host_arrays": float(np.median(times)), "gpu_s_min": float(np.min(times)), "gpu_ms_device_image": t_dev,
+            "n_iter_of_best_init": iters, "component_evaluations_best_inits": int(comp_evals), "seed_volumes": sum(len(v) for v in out.values())}
+    # CPU: the reference's sklearn call on a bounded sample of the fits
+    try:
+        from sklearn.mixture import GaussianMixture
+    except Exception:  # noqa: BLE001
+        GaussianMixture = None
+    off = np.concatenate([[0], np.cumsum(counts)])
+    cpu = {}
+    if GaussianMixture is not None:
+        xh = x.cpu()
+        for (s, m) in ((2, 0), (3, 2), (6, 1)):
+            xt = xh[off[m] : off[m + 1]].reshape(-1, 1)
+            np.random.seed(0)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                t0 = time.perf_counter()
+                GaussianMixture(n_components=s, n_init=5, init_params="k-means++").fit_predict(xt)
+                cpu[f"{s}x{m + 1}"] = {"n": int(xt.shape[0]), "sklearn_s": time.perf_counter() - t0}
+        # the same three fits alone on the GPU
+        specs = [(x[off[m] : off[m + 1]], s) for (s, m) in ((2, 0), (3, 2), (6, 1))]
+        ms = timed(lambda: gen.fit_jobs(specs), reps=args.reps)
+        line["cpu_sample"] = {"fits": cpu, "sklearn_s_total": sum(v["sklearn_s"] for v in cpu.values()), "gpu_ms_same_fits": ms, "cores": torch.get_num_threads(),
+                              "kind": "reference dependency (scikit-learn, unmodified), float64"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", choices=["artifacts", "sweep", "motion", "sample_api"], required=True)
+    ap.add_argument("--config", choices=["artifacts", "sweep", "motion", "sample_api", "seeds"], required=True)
     ap.add_argument("--shape", type=int, default=256)
     ap.add_argument("--sizes", type=int, nargs="+", default=[128, 256, 384])
     ap.add_argument("--batches", type=int, nargs="+", default=[1, 8])
@@ -269,7 +345,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device")
     _lib.load()
-    {"artifacts": run_artifacts, "sweep": run_sweep, "motion": run_motion, "sample_api": run_sample_api}[args.config](args)
+    {"artifacts": run_artifacts, "sweep": run_sweep, "motion": run_motion, "sample_api": run_sample_api, "seeds": run_seeds}[args.config](args)
 
 
 if __name__ == "__main__":
