@@ -434,3 +434,46 @@ def test_image_as_intensity_prior_path():
     assert float((out - want).abs().max()) <= 255 * 2e-6
     assert torch.equal(sg, seg) and torch.equal(img2, image)
     assert params["selected_seeds"] == {} and params["seed_intensities"] == {}
+
+
+# ----------------------------------------------------------------------------- min/max pass of the up-sampling
+@pytest.mark.parametrize("shape,coarse,kind", [
+    ((64, 64, 128), (49, 50, 99), "noise_zero_background"),
+    ((64, 64, 128), (64, 64, 128), "noise_zero_background"),
+    ((48, 40, 72), (17, 23, 31), "noise"),
+    ((48, 40, 72), (30, 30, 50), "negative"),
+    ((48, 40, 72), (30, 30, 50), "flat"),
+    ((48, 40, 72), (30, 30, 50), "plateau"),
+    ((32, 32, 32), (11, 32, 20), "single_peak_corner"),
+])
+def test_zoom_minmax_equals_extrema_of_zoomed_volume(shape, coarse, kind):
+    """fsg_zoom_minmax must return, bit for bit, the extrema of what fsg_zoom writes (the write pass maps
+    the maximum to exactly 1)."""
+    from fetalsyngen_b200.engine import engine_for
+
+    eng = engine_for(DEV, shape)
+    rs = np.random.RandomState(len(kind) * 7 + coarse[0])
+    x = rs.randn(*coarse).astype(np.float32) * 20 + 100
+    if kind == "noise_zero_background":
+        g = np.meshgrid(*[np.linspace(-1, 1, n) for n in coarse], indexing="ij")
+        x = np.where(sum(a * a for a in g) < 0.5, x, 0).astype(np.float32)
+        x = np.maximum(x, 0)
+    elif kind == "negative":
+        x = -x
+    elif kind == "flat":
+        x[:] = 3.25
+    elif kind == "plateau":
+        x = np.minimum(x, 110).astype(np.float32)
+    elif kind == "single_peak_corner":
+        x[:] = 1.0
+        x[-1, -1, -1] = 7.0
+        x[0, 0, 0] = -2.0
+    src = torch.from_numpy(x).to(DEV).contiguous()
+    factors = [s / c for s, c in zip(shape, coarse)]
+    dst = torch.empty((1, *shape), dtype=torch.float32, device=DEV)
+    eng.zoom([src], [coarse], [factors], dst, post=0)
+    want = (float(dst.min()), float(dst.max()))
+    mm = eng.zoom([src], [coarse], [factors], torch.empty_like(dst), post=1)
+    torch.cuda.synchronize()
+    got = tuple(float(v) for v in mm[0].cpu())
+    assert got == want, (got, want)
