@@ -82,11 +82,15 @@ class EmJob(C.Structure):
                 ("labels", _vp), ("out", _vp), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64)]
 
 
+class UnpackJob(C.Structure):
+    _fields_ = [("words", _vp), ("out", _vp), ("shift", _i32 * 4), ("mask", _i32 * 4), ("word_bytes", _i32), ("_pad", _i32)]
+
+
 class SepComposeJob(C.Structure):
     _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32)]
 
 
-_STRUCTS = {"fsg_em_job": EmJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
+_STRUCTS = {"fsg_em_job": EmJob, "fsg_unpack_job": UnpackJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
@@ -132,6 +136,7 @@ SIGNATURES = {
     "fsg_philox_fill": (C.c_int, [Rng, _vp, _i64, C.c_int, _vp]),
     "fsg_draw_grids": (C.c_int, [C.POINTER(GridJob), C.c_int, _vp]),
     "fsg_fetch_params": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fsg_unpack_seeds": (C.c_int, [C.POINTER(UnpackJob), C.c_int, _i64, _vp]),
     "fsg_seed_partition_workspace": (_i64, [_i64]),
     "fsg_seed_partition": (C.c_int, [_vp, _vp, C.c_char_p, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "fsg_em_workspace": (_i64, [C.c_int]),

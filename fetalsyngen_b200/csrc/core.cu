@@ -117,6 +117,7 @@ int fsg_sizeof(const char* name) {
   FSG_SZ(fsg_perlin_octave)
   FSG_SZ(fsg_grid_job)
   FSG_SZ(fsg_em_job)
+  FSG_SZ(fsg_unpack_job)
 #undef FSG_SZ
   return -1;
 }

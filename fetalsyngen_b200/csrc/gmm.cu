@@ -107,6 +107,41 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
   }
 }
 
+// Bit-packed seed cache -> label volume of one sample (see fsg.h).  HBM-bound: 2 or 4 bytes in, 1 out.
+template <typename Word>
+__global__ void __launch_bounds__(256) unpack_seeds_kernel(const __grid_constant__ Batch<fsg_unpack_job> batch, int64_t nvox) {
+  const fsg_unpack_job& job = batch.j[blockIdx.y];
+  const Word* __restrict__ words = static_cast<const Word*>(job.words);
+  // per meta-label: shift | mask << 8 | base << 16 in one register, selected by the 3-bit meta field
+  uint32_t tab[5];
+  tab[0] = 0;
+#pragma unroll
+  for (int m = 1; m <= 4; ++m) tab[m] = (uint32_t)job.shift[m - 1] | ((uint32_t)job.mask[m - 1] << 8) | ((uint32_t)(10 * m) << 16);
+  constexpr int PER = 16 / sizeof(Word);  // words per 16-byte load
+  const int64_t ngroups = nvox / PER;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto decode = [&](uint32_t w) -> uint32_t {
+    const uint32_t m = w & 7u;
+    const uint32_t t = m == 1 ? tab[1] : (m == 2 ? tab[2] : (m == 3 ? tab[3] : (m == 4 ? tab[4] : 0u)));
+    return (t >> 16) + ((w >> (t & 0xffu)) & ((t >> 8) & 0xffu));
+  };
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(words) + g);
+    const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+    if (sizeof(Word) == 2) {
+      uint32_t o[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        o[h] = decode(q[2 * h] & 0xffffu) | (decode(q[2 * h] >> 16) << 8) | (decode(q[2 * h + 1] & 0xffffu) << 16) | (decode(q[2 * h + 1] >> 16) << 24);
+      *reinterpret_cast<uint2*>(job.out + g * PER) = make_uint2(o[0], o[1]);
+    } else {
+      *reinterpret_cast<uint32_t*>(job.out + g * PER) = decode(q[0]) | (decode(q[1]) << 8) | (decode(q[2]) << 16) | (decode(q[3]) << 24);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t v = ngroups * PER; v < nvox; ++v) job.out[v] = (uint8_t)decode((uint32_t)words[v]);
+}
+
 template <bool RAW>
 __global__ void __launch_bounds__(256) philox_fill_kernel(fsg_rng rng, float* out, int64_t n) {
   const int64_t ngroups = (n + 3) / 4;
@@ -211,4 +246,27 @@ extern "C" int fsg_philox_fill(fsg_rng rng, float* out, int64_t n, int raw, void
   else
     philox_fill_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(rng, out, n);
   return check_launch("fsg_philox_fill");
+}
+
+extern "C" int fsg_unpack_seeds(const fsg_unpack_job* jobs, int njobs, int64_t nvox, void* stream) {
+  Batch<fsg_unpack_job> b;
+  if (int rc = fill_batch(b, jobs, njobs)) return rc;
+  FSG_REQUIRE(nvox >= 1, "fsg_unpack_seeds: nvox must be positive");
+  const int wb = jobs[0].word_bytes;
+  FSG_REQUIRE(wb == 2 || wb == 4, "fsg_unpack_seeds: word_bytes must be 2 or 4");
+  for (int i = 0; i < njobs; ++i) {
+    const fsg_unpack_job& j = jobs[i];
+    FSG_REQUIRE(j.words && j.out, "fsg_unpack_seeds: job %d has a NULL pointer", i);
+    FSG_REQUIRE(j.word_bytes == wb, "fsg_unpack_seeds: jobs of one call must share word_bytes");
+    FSG_REQUIRE(((reinterpret_cast<uintptr_t>(j.words) & 15) | (reinterpret_cast<uintptr_t>(j.out) & 7)) == 0, "fsg_unpack_seeds: job %d: words must be 16-byte and out 8-byte aligned", i);
+    for (int m = 0; m < 4; ++m)
+      FSG_REQUIRE(j.shift[m] >= 0 && j.shift[m] < 8 * wb && j.mask[m] >= 0 && j.mask[m] <= 15, "fsg_unpack_seeds: job %d: bad field for meta-label %d", i, m + 1);
+  }
+  const int64_t want = (nvox / (16 / wb) + 255) / 256;
+  const unsigned gx = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+  if (wb == 2)
+    unpack_seeds_kernel<uint16_t><<<dim3(gx, njobs), 256, 0, as_stream(stream)>>>(b, nvox);
+  else
+    unpack_seeds_kernel<uint32_t><<<dim3(gx, njobs), 256, 0, as_stream(stream)>>>(b, nvox);
+  return check_launch("fsg_unpack_seeds");
 }

@@ -340,7 +340,7 @@ extern "C" int fsg_sepconv(const fsg_sepconv_job* jobs, int njobs, int sx, int s
   FSG_REQUIRE(sx >= 1 && sy >= 1 && sz >= 1 && sx <= 32767 && sy <= 32767 && sz <= 32767, "fsg_sepconv: bad shape");
   cudaStream_t s = as_stream(stream);
   const int n_in[3] = {sx, sy, sz};
-  bool inject = false, any_noise = false;
+  bool inject = false;
   for (int i = 0; i < njobs; ++i) {
     const fsg_sepconv_job& j = jobs[i];
     FSG_REQUIRE(j.src && j.dst && j.tmp1 && j.tmp2, "fsg_sepconv: job %d has a NULL buffer", i);
@@ -351,13 +351,9 @@ extern "C" int fsg_sepconv(const fsg_sepconv_job* jobs, int njobs, int sx, int s
       FSG_REQUIRE(ax.n_out >= 1 && ax.n_out <= 32767, "fsg_sepconv: job %d axis %d bad n_out", i, a);
       FSG_REQUIRE(ax.width >= 1 && ax.width <= n_in[a] && ax.width <= 2 * FSG_MAX_TAPS, "fsg_sepconv: job %d axis %d width %d outside [1,min(%d,%d)]", i, a, ax.width, n_in[a], 2 * FSG_MAX_TAPS);
     }
-    if (j.has_noise) {
-      any_noise = true;
-      if (j.noise) inject = true;
-    }
+    if (j.has_noise && j.noise) inject = true;
   }
   for (int i = 0; i < njobs; ++i) FSG_REQUIRE(!jobs[i].has_noise || ((jobs[i].noise != nullptr) == inject), "fsg_sepconv: jobs mix injected and Philox noise");
-  (void)any_noise;
 
   SepNoise nz;
   memset(&nz, 0, sizeof(nz));

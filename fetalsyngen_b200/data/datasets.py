@@ -119,7 +119,10 @@ class FetalSynthDataset(FetalDataset):
     """On-the-fly generation / augmentation of fetal images (datasets.py:201-370)."""
 
     def __init__(self, bids_path: str, generator: FetalSynthGen, seed_path: str | None, sub_list: list[str] | None,
-                 load_image: bool = False, image_as_intensity: bool = False):
+                 load_image: bool = False, image_as_intensity: bool = False, packed_cache: str | None = None):
+        """``packed_cache``: directory of bit-packed subject files (``data/packed.py``).  A missing file is
+        written from the subject's NIfTIs on first use (the one-time conversion); afterwards a process
+        start reads one file per subject instead of decoding 25 gzip volumes."""
         self._needs_images = bool(load_image or image_as_intensity)
         super().__init__(bids_path, sub_list)
         self.seed_path = Path(seed_path) if isinstance(seed_path, (str, Path)) else None
@@ -127,6 +130,8 @@ class FetalSynthDataset(FetalDataset):
         self.generator = generator
         self.image_as_intensity = image_as_intensity
         self._seg_cache: dict = {}
+        self.packed_cache = Path(packed_cache) if packed_cache is not None else None
+        self._packed: dict = {}
         if not self.image_as_intensity and isinstance(self.seed_path, Path):
             if not self.seed_path.exists():
                 raise FileNotFoundError(f"Provided seed path {self.seed_path} does not exist.")
@@ -148,9 +153,34 @@ class FetalSynthDataset(FetalDataset):
                     self.seed_paths[self._sub_ses_string(sub, ses)][n_sub][i] = file
 
     # ------------------------------------------------------------------ device caches
+    def _packed_subject(self, idx):
+        """(uint8 segmentation, PackedSeeds) of subject idx from the packed cache, converting on first use."""
+        hit = self._packed.get(idx)
+        if hit is None:
+            from .packed import load_packed, pack_subject
+
+            name = self._sub_ses_string(*self.sub_ses[idx])
+            f = self.packed_cache / f"{name}.fsgpack.npz"
+            if not f.exists():
+                pack_subject(self.segm_paths[idx], self.seed_paths[name], f)
+            seg, seeds, _ = load_packed(f)
+            hit = (seg, seeds)
+            self._packed[idx] = hit
+        return hit
+
+    def _seeds(self, idx):
+        """What the generator receives as ``seeds``: the reference's {n_subclasses: {meta_label: path}} or the packed cache."""
+        if self.packed_cache is not None:
+            return self._packed_subject(idx)[1]
+        return self.seed_paths[self._sub_ses_string(*self.sub_ses[idx])]
+
     def _segmentation(self, idx) -> torch.Tensor:
         """uint8 label map of subject idx, decoded once and kept on the generator's device."""
         seg = self._seg_cache.get(idx)
+        if seg is None and self.packed_cache is not None and not self.image_as_intensity and self.seed_path is not None:
+            raw = torch.from_numpy(self._packed_subject(idx)[0])
+            seg = raw.to(self.generator.engine(tuple(raw.shape)).device).contiguous()
+            self._seg_cache[idx] = seg
         if seg is None:
             raw = self.loader(self.segm_paths[idx])
             seg = raw.to(torch.uint8).to(self.generator.engine(tuple(raw.shape)).device).contiguous()
@@ -165,7 +195,7 @@ class FetalSynthDataset(FetalDataset):
         name = self._sub_ses_string(*self.sub_ses[idx])
         seeds = None
         if self.seed_path is not None:
-            seeds = self.seed_paths[name]
+            seeds = self._seeds(idx)
         if self.image_as_intensity:
             seeds = None
         generation_params["idx"] = idx
@@ -219,7 +249,7 @@ class FetalSynthDataset(FetalDataset):
             raise ValueError("sample_batch needs seed-based intensity generation")
         segs = [self._segmentation(i) for i in indices]
         names = [self._sub_ses_string(*self.sub_ses[i]) for i in indices]
-        img, seg, params = self.generator.sample_batch(segs, [self.seed_paths[n] for n in names], scale=scale)
+        img, seg, params = self.generator.sample_batch(segs, [self._seeds(i) for i in indices], scale=scale)
         return {"image": img.unsqueeze(1), "label": seg.unsqueeze(1), "name": names}, params
 
 
@@ -276,7 +306,7 @@ class DeviceBatchLoader:
         with torch.cuda.stream(self.stream):
             if self._released[slot] is not None:
                 self.stream.wait_event(self._released[slot])
-            _, _, params = self.ds.generator.sample_batch(segs, [self.ds.seed_paths[n] for n in names], scale=True, out_img=self._img[slot], out_seg=self._seg[slot], **kw)
+            _, _, params = self.ds.generator.sample_batch(segs, [self.ds._seeds(i) for i in idx], scale=True, out_img=self._img[slot], out_seg=self._seg[slot], **kw)
             if self._lab is not None:
                 self.eng._call("fsg_u8_to_i64", self._seg[slot].data_ptr(), self._lab[slot].data_ptr(), self._seg[slot].numel())
             done = torch.cuda.Event()

@@ -81,7 +81,13 @@ class ImageFromSeeds:
             self._cache[key] = vol
         return vol
 
-    def select_seeds(self, seeds: dict, mlabel2subclusters: dict, device) -> list[torch.Tensor]:
+    def select_seeds(self, seeds, mlabel2subclusters: dict, device) -> list[torch.Tensor]:
+        """The volumes whose sum is the sample's label map: the four selected seed files, or — for a
+        bit-packed subject cache (``data/packed.py``) — the one label volume unpacked on the device."""
+        from ...data.packed import PackedSeeds
+
+        if isinstance(seeds, PackedSeeds):
+            return [seeds.labels(mlabel2subclusters, device)]
         return [self.seed_volume(seeds[mlabel2subclusters[m]][m], device) for m in range(1, self.meta_labels + 1)]
 
     # ------------------------------------------------------------------ reference-compatible API

@@ -256,11 +256,13 @@ class FetalSynthGen:
             # (base_seed, sample id)
             from ..batch_draw import draw_plans
 
-            use_dict = any(isinstance(sd, dict) for sd in seeds)
+            from ..data.packed import PackedSeeds
+
+            use_dict = any(isinstance(sd, (dict, PackedSeeds)) for sd in seeds)
             out = draw_plans(self, list(sample_ids), int(base_seed or 0), shape, with_subclusters=use_dict)
             plans, params = out[0], out[1]
             for b, sd in enumerate(seeds):
-                if isinstance(sd, dict):
+                if isinstance(sd, (dict, PackedSeeds)):
                     m2s = {m: int(out[2][b, m - 1]) for m in range(1, self.intensity_generator.meta_labels + 1)}
                     vols.append([v.view(-1) for v in self.intensity_generator.select_seeds(sd, m2s, eng.device)])
                     params[b]["selected_seeds"] = {"mlabel2subclusters": m2s}
@@ -279,7 +281,7 @@ class FetalSynthGen:
             else:
                 plan = self._new_plan()
             sd = seeds[b]
-            if isinstance(sd, dict):
+            if isinstance(sd, dict) or type(sd).__name__ == "PackedSeeds":
                 pr = self._draw_generate(plan, sd, shape, genparams, None, device_grids=True)
                 vols.append([v.view(-1) for v in plan.meta["seed_vols"]])
             else:

@@ -336,6 +336,23 @@ typedef struct fsg_grid_job {
 } fsg_grid_job;
 int fsg_draw_grids(const fsg_grid_job* jobs_host, int njobs, void* stream);
 
+/* Bit-packed seed cache.  A subject's seed volumes for every sub-class count
+ * share the meta-label support, so one word per voxel holds them all: bits 0-2 the meta-label
+ * (0 = background, 1..4), then one field per sub-class count n >= 2 holding the voxel's sub-class
+ * index (ceil(log2 n) bits; 14 bits in total for counts 1..6 -> uint16, 28 bits for 1..10 -> uint32).
+ * fsg_unpack_seeds writes the label volume a sample needs — what the sum of the four selected seed
+ * files gives (rand_gmm.py:90-97): out[v] = meta ? 10 * meta + ((word >> shift[meta-1]) & mask[meta-1]) : 0
+ * with shift / mask the field of the count drawn for that meta-label (mask 0 for one sub-class). */
+typedef struct fsg_unpack_job {
+  const void* words; /* [nvox] uint16 or uint32 (device) */
+  uint8_t* out;      /* [nvox] (device) */
+  int32_t shift[4];
+  int32_t mask[4];
+  int32_t word_bytes; /* 2 or 4 */
+  int32_t _pad;
+} fsg_unpack_job;
+int fsg_unpack_seeds(const fsg_unpack_job* jobs_host, int njobs, int64_t nvox, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K6 — seed generation.  Replaces scripts/generate_seeds.py:133-211:
  * label fusion into meta-labels + sklearn GaussianMixture(n_components, n_init=5,

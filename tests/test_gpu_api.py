@@ -213,3 +213,72 @@ def test_device_batch_loader_matches_sample_batch_and_keeps_batches_valid(tmp_pa
         assert torch.equal(img.unsqueeze(1), kept[step][2]) and torch.equal(seg.unsqueeze(1).long(), kept[step][3])
     with pytest.raises(ValueError):
         DeviceBatchLoader(ds, batch_size=2, depth=1)
+
+
+# ----------------------------------------------------------------------------- bit-packed seed cache
+@pytest.mark.parametrize("smax,nvox_shape", [(6, (24, 20, 28)), (10, (24, 20, 28)), (6, (5, 7, 3)), (3, (1, 1, 13))])
+def test_unpack_seeds_kernel_equals_sum_of_selected_seed_files(smax, nvox_shape):
+    """fsg_unpack_seeds (uint16 and uint32 words, vector body + scalar tail) against the reference's
+    definition of the label map: the sum of the four selected seed volumes (rand_gmm.py:90-97)."""
+    from fetalsyngen_b200.data import packed as K
+
+    seeds = {}
+    for n in range(1, smax + 1):
+        _, sv = label_phantom(nvox_shape, n_sub=(n, n, n, n), seed=n)
+        seeds[n] = {m + 1: sv[m] for m in range(4)}
+    words, counts = K.pack_seed_volumes(seeds)
+    ps = K.PackedSeeds(words, counts, DEV)
+    rs = np.random.RandomState(1)
+    for _ in range(6):
+        m2s = {m: int(rs.randint(1, smax + 1)) for m in range(1, 5)}
+        want = sum(seeds[m2s[m]][m].astype(np.int32) for m in range(1, 5)).astype(np.uint8)
+        got = ps.labels(m2s, DEV).cpu().numpy()
+        assert np.array_equal(got, want), m2s
+        assert np.array_equal(got, K.unpack_numpy(words, counts, m2s))
+    with pytest.raises(KeyError):
+        ps.labels({1: smax + 1, 2: 1, 3: 1, 4: 1}, DEV)
+
+
+def test_dataset_with_packed_cache_gives_identical_samples(tmp_path):
+    """FetalSynthDataset(packed_cache=...) converts on first use, reloads from the cache file afterwards,
+    and produces bit-identical samples to the NIfTI-backed dataset (per-sample API and batched path)."""
+    from fetalsyngen_b200.data.datasets import FetalSynthDataset
+    from fetalsyngen_b200.utils import nifti
+
+    shape = (48, 48, 48)
+    aff = np.diag([0.5, 0.5, 0.5, 1.0])
+    for si, sub in enumerate(("sub-a", "sub-b")):
+        d = tmp_path / "bids" / sub / "anat"
+        d.mkdir(parents=True)
+        seg_h, _ = label_phantom(shape, seed=si)
+        nifti.write_nifti(d / f"{sub}_rec-x_T2w_dseg.nii.gz", seg_h.astype(np.float32), aff)
+        for n in range(1, 5):
+            _, sv = label_phantom(shape, n_sub=(n, n, n, n), seed=10 * si + n)
+            sd = tmp_path / "seeds" / f"subclasses_{n}" / sub / "anat"
+            sd.mkdir(parents=True)
+            for m in range(1, 5):
+                nifti.write_nifti(sd / f"{sub}_rec-x_T2w_dseg_mlabel_{m}.nii.gz", sv[m - 1], aff)
+    gen = _gen(shape)
+    gen.intensity_generator.min_subclusters, gen.intensity_generator.max_subclusters = 1, 4
+    plain = FetalSynthDataset(str(tmp_path / "bids"), gen, str(tmp_path / "seeds"), None)
+    cache = tmp_path / "cache"
+    for attempt in range(2):  # first pass converts, second pass only reads the cache files
+        packed = FetalSynthDataset(str(tmp_path / "bids"), gen, str(tmp_path / "seeds"), None, packed_cache=str(cache))
+        for idx in (0, 1):
+            outs = []
+            for ds in (plain, packed):
+                np.random.seed(5 + idx)
+                torch.manual_seed(5 + idx)
+                gen._sample_counter = 0
+                o, p = ds.sample(idx)
+                outs.append((o, p))
+            (a, pa), (b, pb) = outs
+            assert torch.equal(a["image"], b["image"]) and torch.equal(a["label"], b["label"])
+            assert pa["selected_seeds"] == pb["selected_seeds"]
+        assert sorted(f.name for f in cache.glob("*.npz")) == ["sub-a.fsgpack.npz", "sub-b.fsgpack.npz"]
+    a, _ = plain.sample_batch([0, 1, 0])
+    np.random.seed(3)
+    torch.manual_seed(3)
+    ia, sa, _ = gen.sample_batch([plain._segmentation(i) for i in (0, 1)], [plain._seeds(i) for i in (0, 1)], sample_ids=[4, 9], base_seed=77)
+    ib, sb, _ = gen.sample_batch([packed._segmentation(i) for i in (0, 1)], [packed._seeds(i) for i in (0, 1)], sample_ids=[4, 9], base_seed=77)
+    assert torch.equal(ia, ib) and torch.equal(sa, sb)

@@ -291,3 +291,22 @@ def test_batch_draw_matches_the_stage_classes_statistically():
     assert all(np.allclose(p.c2, 127.5) and p.c2.dtype == np.float64 for p in plans if p.deform)
     # parameter dictionaries keep the reference's keys
     assert set(params[0]) == {"selected_seeds", "seed_intensities", "deform_params", "gamma_params", "bf_params", "resample_params", "noise_params"}
+
+
+def test_pack_dataset_tool_writes_one_cache_file_per_subject(tmp_path):
+    """tools/pack_dataset.py: the one-time converter of a BIDS + seeds tree into the bit-packed cache."""
+    import importlib.util
+
+    from fetalsyngen_b200.data.packed import load_packed, unpack_numpy
+
+    bids, seeds = _bids(tmp_path)
+    spec = importlib.util.spec_from_file_location("pack_dataset", ROOT / "tools" / "pack_dataset.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(["--bids_path", str(bids), "--seed_path", str(seeds), "--out_path", str(tmp_path / "cache")]) == 0
+    for s in ("sub-a", "sub-b"):
+        seg, ps, _ = load_packed(tmp_path / "cache" / f"{s}.fsgpack.npz")
+        assert seg.shape == (8, 8, 8) and seg.max() == 3 and ps.counts == [1, 2]
+        lab = unpack_numpy(ps._host, ps.counts, {1: 2, 2: 1, 3: 2, 4: 1})
+        for m in range(1, 5):
+            assert (lab[m : m + 1] == 10 * m).all()

@@ -96,3 +96,74 @@ def test_seed_generator_needs_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(_lib.FsgError):
         P.SeedGenerator()
+
+
+# ----------------------------------------------------------------------------- bit-packed seed cache (host side)
+def _phantom_seeds(shape, smax):
+    from fetalsyngen_b200.utils.phantom import label_phantom
+
+    seeds, seg = {}, None
+    for n in range(1, smax + 1):
+        seg, sv = label_phantom(shape, n_sub=(n, n, n, n), seed=n)
+        seeds[n] = {m + 1: sv[m] for m in range(4)}
+    return seg, seeds
+
+
+@pytest.mark.parametrize("smax,dtype", [(6, np.uint16), (10, np.uint32), (1, np.uint16)])
+def test_packed_seeds_round_trip(smax, dtype):
+    from fetalsyngen_b200.data import packed as K
+
+    _, seeds = _phantom_seeds((20, 24, 28), smax)
+    words, counts = K.pack_seed_volumes(seeds)
+    assert words.dtype == dtype and counts == list(range(1, smax + 1))
+    rs = np.random.RandomState(0)
+    for _ in range(8):
+        m2s = {m: int(rs.randint(1, smax + 1)) for m in range(1, 5)}
+        want = sum(seeds[m2s[m]][m].astype(np.int32) for m in range(1, 5)).astype(np.uint8)  # rand_gmm.py:90-97
+        assert np.array_equal(K.unpack_numpy(words, counts, m2s), want)
+
+
+def test_packed_seeds_reject_what_cannot_be_packed():
+    from fetalsyngen_b200.data import packed as K
+
+    _, seeds = _phantom_seeds((12, 12, 12), 3)
+    bad = {n: {m: v.copy() for m, v in per.items()} for n, per in seeds.items()}
+    bad[2][1][bad[2][2] != 0] = 10  # overlapping supports
+    with pytest.raises(ValueError, match="overlap"):
+        K.pack_seed_volumes(bad)
+    bad = {n: {m: v.copy() for m, v in per.items()} for n, per in seeds.items()}
+    bad[3][1][:] = 0  # support changes with the sub-class count
+    with pytest.raises(ValueError, match="differs"):
+        K.pack_seed_volumes(bad)
+    bad = {n: {m: v.copy() for m, v in per.items()} for n, per in seeds.items()}
+    bad[2][3][bad[2][3] != 0] = 35  # sub-class index 5 of a 2-class split
+    with pytest.raises(ValueError, match="outside"):
+        K.pack_seed_volumes(bad)
+    with pytest.raises(ValueError):
+        K.field_layout([1, 2, 40])
+
+
+def test_packed_cache_file_and_converter(tmp_path):
+    from fetalsyngen_b200.data import packed as K
+    from fetalsyngen_b200.utils.nifti import write_nifti
+
+    shape = (16, 20, 24)
+    seg, seeds = _phantom_seeds(shape, 4)
+    aff = np.diag([0.5, 0.5, 0.5, 1.0])
+    segf = tmp_path / "sub-a_dseg.nii.gz"
+    write_nifti(segf, seg.astype(np.float32), aff)
+    paths = {}
+    for n, per in seeds.items():
+        paths[n] = {}
+        for m, v in per.items():
+            paths[n][m] = tmp_path / f"s{n}_m{m}.nii.gz"
+            write_nifti(paths[n][m], v, aff)
+    f = K.pack_subject(segf, paths, tmp_path / "cache" / "sub-a.fsgpack.npz")
+    seg2, ps, aff2 = K.load_packed(f)
+    assert np.array_equal(seg2, seg) and seg2.dtype == np.uint8 and np.allclose(aff2, aff)
+    assert ps.counts == [1, 2, 3, 4] and ps.shape == shape and ps.word_bytes == 2
+    m2s = {1: 4, 2: 1, 3: 3, 4: 2}
+    want = sum(seeds[m2s[m]][m].astype(np.int32) for m in range(1, 5)).astype(np.uint8)
+    assert np.array_equal(K.unpack_numpy(ps._host, ps.counts, m2s), want)
+    with pytest.raises(KeyError):
+        ps.job(type("J", (), {"shift": [0] * 4, "mask": [0] * 4})(), {1: 5, 2: 1, 3: 1, 4: 1}, "cpu", None)

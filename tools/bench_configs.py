@@ -226,8 +226,9 @@ def run_sample_api(args):
         for n in range(1, 7):
             sd = root / "seeds" / f"subclasses_{n}" / "sub-phantom" / "anat"
             sd.mkdir(parents=True)
+            _, seeds_n = label_phantom(shape, n_sub=(n, n, n, n), seed=n)  # labels 10 m .. 10 m + n - 1, as generate_seeds.py writes them
             for m in range(1, 5):
-                nifti.write_nifti(sd / f"sub-phantom_rec-x_T2w_dseg_mlabel_{m}.nii.gz", seeds_h[m - 1], aff)
+                nifti.write_nifti(sd / f"sub-phantom_rec-x_T2w_dseg_mlabel_{m}.nii.gz", seeds_n[m - 1], aff)
         res = {}
         for name, arts in (("base stages (default probabilities)", None), ("with the four SR artifacts (default probabilities)", bench.default_artifacts(0.4))):
             gen = bench.build_generator(shape, DEV, artifacts=arts)
@@ -254,6 +255,31 @@ def run_sample_api(args):
             assert out["image"].shape == (1, *shape) and out["label"].dtype == torch.int64 and out["image"].device.type == "cpu"
             res[name] = {"first_call_s": first, "seed_cache_warmup_calls": nwarm, "seed_cache_warmup_s": warm, "mean_s": float(np.mean(times)), "median_s": float(np.median(times)), "min_s": float(np.min(times)), "max_s": float(np.max(times)),
                          "generation_time_last": params["generation_time"]}
+        # bit-packed subject cache (data/packed.py): one-time conversion, then the cold start of a new process
+        from fetalsyngen_b200.data.packed import PackedSeeds, load_packed
+
+        gen = bench.build_generator(shape, DEV, artifacts=None)
+        t0 = time.perf_counter()
+        ds = FetalSynthDataset(str(root / "bids"), gen, str(root / "seeds"), None, packed_cache=str(root / "cache"))
+        ds.sample(0)
+        convert = time.perf_counter() - t0
+        cache_file = root / "cache" / "sub-phantom.fsgpack.npz"
+        gen = bench.build_generator(shape, DEV, artifacts=None)
+        t0 = time.perf_counter()
+        ds = FetalSynthDataset(str(root / "bids"), gen, str(root / "seeds"), None, packed_cache=str(root / "cache"))
+        ds.sample(0)
+        cold = time.perf_counter() - t0
+        times = []
+        for _ in range(args.reps * 4):
+            t0 = time.perf_counter()
+            ds.sample(0)
+            times.append(time.perf_counter() - t0)
+        _, ps, _ = load_packed(cache_file)
+        ps.on(DEV)
+        unpack_ms = timed(lambda: ps.labels({1: 3, 2: 6, 3: 2, 4: 5}, DEV), reps=20)
+        res["bit-packed subject cache"] = {"convert_and_first_call_s": convert, "cold_start_first_call_s": cold, "median_s": float(np.median(times)), "cache_file_MiB": cache_file.stat().st_size / 2**20,
+                                           "nifti_gz_files_replaced": 25, "device_bytes_per_subject_MiB": ps._host.nbytes / 2**20, "device_bytes_unpacked_int8_MiB": 24 * ps._host.size / 2**20,
+                                           "unpack_kernel_ms": unpack_ms}
     print(json.dumps({"config": "FetalSynthDataset.sample wall clock (reference: generation_time 0.5616 s / 0.6192 s, docs/datasets.md:76,131)", "shape": list(shape), "calls": args.reps * 4,
                       "results": res, "note": "host tensors out: float32 image (1,S,S,S) + int64 label on the CPU, as the reference returns them; seeds / segmentation decoded once and cached on the device"}))
 
