@@ -210,6 +210,37 @@ __device__ __forceinline__ float psf_at_voxel(const SliceGeom& g, const float* _
   return v;
 }
 
+// Lean form for the warp kernel: the same quantity with contracted multiply-adds (the reference's
+// extension is compiled with FMA contraction as well), the PSF-grid centre folded into the FMA chain,
+// the trilinear blend as seven nested lerps instead of eight three-factor products, PSF in shared
+// memory.  Agrees with psf_at_voxel to float rounding; `ok` false when the voxel falls off the PSF grid.
+struct PsfGrid {
+  const float* q;  // shared memory
+  int wp, hpwp;
+  float cx, cy, cz, mx, my, mz;  // (n - 1) / 2 and n - 1 per axis
+};
+__device__ __forceinline__ float psf_lerp(const SliceGeom& g, const PsfGrid& P, float xr, float yr, float zr, bool& ok) {
+  const float dx = xr - g.xc, dy = yr - g.yc, dz = zr - g.zc;
+  const float xp = __fmaf_rn(g.r11, dx, __fmaf_rn(g.r21, dy, __fmaf_rn(g.r31, dz, P.cx)));
+  const float yp = __fmaf_rn(g.r12, dx, __fmaf_rn(g.r22, dy, __fmaf_rn(g.r32, dz, P.cy)));
+  const float zp = __fmaf_rn(g.r13, dx, __fmaf_rn(g.r23, dy, __fmaf_rn(g.r33, dz, P.cz)));
+  ok = !(xp < 0.f || yp < 0.f || zp < 0.f || xp >= P.mx || yp >= P.my || zp >= P.mz);
+  if (!ok) return 0.f;
+  const float fx = floorf(xp), fy = floorf(yp), fz = floorf(zp);
+  const float wx = xp - fx, wy = yp - fy, wz = zp - fz;
+  const float* q = P.q + ((int)fz * P.hpwp + (int)fy * P.wp + (int)fx);
+  const float* q1 = q + P.hpwp;
+  const float a00 = __fmaf_rn(wx, q[1] - q[0], q[0]), a01 = __fmaf_rn(wx, q[P.wp + 1] - q[P.wp], q[P.wp]);
+  const float a10 = __fmaf_rn(wx, q1[1] - q1[0], q1[0]), a11 = __fmaf_rn(wx, q1[P.wp + 1] - q1[P.wp], q1[P.wp]);
+  const float b0 = __fmaf_rn(wy, a01 - a00, a00), b1 = __fmaf_rn(wy, a11 - a10, a10);
+  return fmaxf(__fmaf_rn(wz, b1 - b0, b0), 0.f);
+}
+// round half away from zero for x >= 0 (C round(), as the reference uses), exact
+__device__ __forceinline__ float round_nonneg(float x) {
+  const float f = floorf(x);
+  return (x - f >= 0.5f) ? f + 1.0f : f;
+}
+
 __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const float* __restrict__ transforms, const float* __restrict__ psf, int dp, int hp, int wp,
                                                                         const float4* __restrict__ taps, int ntaps, float radius, const float* __restrict__ slices,
                                                                         const int* __restrict__ slice_idx, float2* __restrict__ acc, int h, int w, int D, int H, int W, float res) {
@@ -267,7 +298,7 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_kernel(const flo
 // like the reference, evaluates every tap twice), lanes of a warp never diverge on the pixel cull and
 // consecutive taps land on neighbouring voxels.  A block still owns a 16x16 pixel tile of one slice
 // (rotated tap offsets staged once); each warp walks 32 of its pixels.  TPL = taps per lane.
-template <int TPL>
+template <int TPL, bool LEAN>
 __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_warp_kernel(const float* __restrict__ transforms, const float* __restrict__ psf, int dp, int hp, int wp,
                                                                              const float4* __restrict__ taps, int ntaps, float radius, const float* __restrict__ slices,
                                                                              const int* __restrict__ slice_idx, float2* __restrict__ acc, int h, int w, int D, int H, int W, float res) {
@@ -288,7 +319,20 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_warp_kernel(cons
     z = z + t[10] * q.z;
     s_tap[p] = make_float4(x, y, z, q.w);
   }
+  float* s_psf = reinterpret_cast<float*>(s_tap + ntaps);
+  if (LEAN)
+    for (int p = tid; p < dp * hp * wp; p += ACQ_TILE * ACQ_TILE) s_psf[p] = psf[p];
   __syncthreads();
+  PsfGrid P;
+  P.q = s_psf;
+  P.wp = wp;
+  P.hpwp = hp * wp;
+  P.cx = 0.5f * (float)(wp - 1);
+  P.cy = 0.5f * (float)(hp - 1);
+  P.cz = 0.5f * (float)(dp - 1);
+  P.mx = (float)(wp - 1);
+  P.my = (float)(hp - 1);
+  P.mz = (float)(dp - 1);
   const int lane = tid & 31, warp = tid >> 5;
   const int Sy = W, Sz = H * W;
   const float mx = (float)(W - 1), my = (float)(H - 1), mz = (float)(D - 1);
@@ -321,20 +365,32 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_adj_warp_kernel(cons
         const float4 o = s_tap[p];
         const float x = g.xc + o.x, y = g.yc + o.y, z = g.zc + o.z;
         if (!(x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz)) {
-          const float xr = roundf(x), yr = roundf(y), zr = roundf(z);
-          pv[u] = psf_at_voxel(g, psf, dp, hp, wp, xr, yr, zr);
-          iv[u] = (int)zr * Sz + (int)yr * Sy + (int)xr;
-          if (pv[u] >= 0.f) weight += pv[u];
+          if (LEAN) {
+            const float xr = round_nonneg(x), yr = round_nonneg(y), zr = round_nonneg(z);
+            bool ok;
+            const float v = psf_lerp(g, P, xr, yr, zr, ok);
+            iv[u] = (int)zr * Sz + (int)yr * Sy + (int)xr;
+            if (ok) {
+              pv[u] = v;
+              weight += v;
+            }
+          } else {
+            const float xr = roundf(x), yr = roundf(y), zr = roundf(z);
+            pv[u] = psf_at_voxel(g, psf, dp, hp, wp, xr, yr, zr);
+            iv[u] = (int)zr * Sz + (int)yr * Sy + (int)xr;
+            if (pv[u] >= 0.f) weight += pv[u];
+          }
         }
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) weight += __shfl_xor_sync(0xffffffffu, weight, o);
     if (weight < 0.5f) continue;  // border
+    const float inv = __frcp_rn(weight);
 #pragma unroll
     for (int u = 0; u < TPL; ++u) {
       if (pv[u] >= 0.f) {
-        const float v = __fdiv_rn(pv[u], weight);
+        const float v = LEAN ? pv[u] * inv : __fdiv_rn(pv[u], weight);
         atomicAdd(acc + iv[u], make_float2(v * s, v));
       }
     }
@@ -507,11 +563,23 @@ extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, 
   const size_t smem = sizeof(float4) * ntaps;
   if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const float4* taps4 = reinterpret_cast<const float4*>(taps);
-#define FSG_ADJ_WARP(TPL)                                                                                                                                           \
-  do {                                                                                                                                                              \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_warp_kernel<TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                 \
-    slice_adj_warp_kernel<TPL><<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, taps4, ntaps, radius, slices, slice_idx, acc, h, w, D, H, W, \
-                                                                           res_slice);                                                                             \
+  static const bool lean = [] {
+    const char* e = getenv("FSG_ADJ_LEAN");  // A/B: 0 = the reference's operation order (uncontracted, eight-product blend, IEEE divide)
+    return !(e && e[0] == '0');
+  }();
+  const size_t smem_w = smem + (lean ? sizeof(float) * (size_t)dp * hp * wp : 0);
+  FSG_REQUIRE(smem_w <= 200 * 1024, "fsg_slice_acq_adjoint: %d taps + a %dx%dx%d PSF do not fit in shared memory", ntaps, dp, hp, wp);
+#define FSG_ADJ_WARP(TPL)                                                                                                                                                  \
+  do {                                                                                                                                                                     \
+    if (lean) {                                                                                                                                                            \
+      if (smem_w > 48 * 1024) cudaFuncSetAttribute(slice_adj_warp_kernel<TPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);                            \
+      slice_adj_warp_kernel<TPL, true><<<grid, dim3(ACQ_TILE, ACQ_TILE), smem_w, s>>>(transforms, psf, dp, hp, wp, taps4, ntaps, radius, slices, slice_idx, acc, h, w, D, H, \
+                                                                                      W, res_slice);                                                                      \
+    } else {                                                                                                                                                               \
+      if (smem_w > 48 * 1024) cudaFuncSetAttribute(slice_adj_warp_kernel<TPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);                           \
+      slice_adj_warp_kernel<TPL, false><<<grid, dim3(ACQ_TILE, ACQ_TILE), smem_w, s>>>(transforms, psf, dp, hp, wp, taps4, ntaps, radius, slices, slice_idx, acc, h, w, D,  \
+                                                                                       H, W, res_slice);                                                                  \
+    }                                                                                                                                                                      \
   } while (0)
   const int tpl = (ntaps + 31) / 32;
   static const bool per_thread = [] {
