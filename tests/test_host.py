@@ -50,7 +50,8 @@ def test_no_cpu_fallback_and_no_oracle_in_product():
             SynthEngine((8, 8, 8), (1.0, 1.0, 1.0), "cuda:0")
     for p in (ROOT / "fetalsyngen_b200").rglob("*.py"):
         src = p.read_text()
-        assert "np_oracle" not in src and "np_motion" not in src and "np_artifacts" not in src and "ref_import" not in src, p
+        assert "np_oracle" not in src and "np_motion" not in src and "np_artifacts" not in src and "np_seeds" not in src and "ref_import" not in src, p
+        assert "import sklearn" not in src and "from sklearn" not in src, p  # the reference's clustering dependency is a checker, never a code path
 
 
 def test_c_abi_argument_checks_without_a_gpu():
