@@ -201,7 +201,10 @@ class Scanner:
             transform_motion = transform_motion[interleave_idx]
             transform_target = transform_motion.compose(transform_init)
             mat = svort.mat_update_resolution(transform_target.matrix(), res_r, res)
-            slices = slice_acquisition(mat, vol, psf_acq, (ss, ss), res_s / res)
+            # The reference acquires the image stack and the mask stack, then keeps the slices whose mask
+            # content passes a random threshold (simulate_reco.py:355-371).  Slices are independent, so the
+            # cheap one-tap mask stack goes first: the read-back that decides which slices survive waits for
+            # it alone, and the PSF acquisition of the image runs for the surviving run of slices only.
             slices_no_psf = slice_acquisition(mat, data["mask"], psf_one, (ss, ss), res_s / res)
             _lib.call("fsg_slice_sums", slices_no_psf.data_ptr(), ns, ss * ss, sums_d.data_ptr(), _stream())
             nnz = sums_d.cpu().numpy()
@@ -211,7 +214,8 @@ class Scanner:
             nz = np.nonzero(idx)[0]
             idx[nz[0] : nz[-1]] = True
             lo, hi = int(nz[0]), int(nz[-1]) + 1  # the kept slices are one contiguous run
-            slices, slices_no_psf = slices[lo:hi], slices_no_psf[lo:hi]
+            slices = slice_acquisition(np.ascontiguousarray(mat[lo:hi]), vol, psf_acq, (ss, ss), res_s / res)
+            slices_no_psf = slices_no_psf[lo:hi]
             transform_init = svort.reset_transform(transform_init[idx])
             transform_target = transform_target[idx]
             k = attempt
