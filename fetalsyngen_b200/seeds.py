@@ -232,6 +232,19 @@ class SeedGenerator:
         return written
 
 
+    def pack_subject(self, image_path, label_path, out_file, subclasses):
+        """Seeds of one subject straight into the bit-packed cache format (``data/packed.py``) that
+        ``FetalSynthDataset(packed_cache=...)`` loads — no intermediate NIfTI files."""
+        from .data.packed import pack_seed_volumes, save_packed
+
+        image = read_nifti(image_path).astype(np.float32)
+        label, affine = read_nifti(label_path, with_affine=True)
+        res = self.split_labels(image, label, subclasses)
+        words, counts = pack_seed_volumes({n: {m: v.cpu().numpy() for m, v in per.items()} for n, per in res.items()})
+        save_packed(out_file, labels_to_u8(label), words, counts, affine)
+        return Path(out_file)
+
+
 def main(argv=None) -> int:
     """Same flags as the reference script (generate_seeds.py:32-59) plus --device / --seed."""
     p = argparse.ArgumentParser(description="Generate seeds for FetalSynthGen (GPU)",
@@ -240,6 +253,7 @@ def main(argv=None) -> int:
     p.add_argument("--out_path", type=str, required=True, help="Path to save the seeds")
     p.add_argument("--max_subclasses", type=int, default=10, help="How many subclasses to simulate for each tissue type (meta-label)")
     p.add_argument("--annotation", type=str, required=True, choices=["feta", "dhcp"], help="Annotation type. Should be either 'feta' or 'dhcp'")
+    p.add_argument("--packed", action="store_true", help="write one bit-packed cache file per subject (<out_path>/<sub>.fsgpack.npz) instead of NIfTI seed volumes")
     p.add_argument("--device", type=str, default="cuda:0")
     p.add_argument("--seed", type=int, default=None)
     a = p.parse_args(argv)
@@ -250,6 +264,10 @@ def main(argv=None) -> int:
     for sub in subjects:
         imgs = list(sub.glob("**/anat/*_T2w.nii.gz"))[0]
         label = list(sub.glob("**/anat/*_dseg.nii.gz"))[0]
+        if a.packed:
+            f = gen.pack_subject(imgs, label, Path(a.out_path) / f"{sub.name}.fsgpack.npz", range(1, int(a.max_subclasses) + 1))
+            print(f"{sub.name}: {f.name}, {f.stat().st_size / 2**20:.1f} MiB")
+            continue
         files = gen.process_subject(imgs, label, a.out_path, sub.name, range(1, int(a.max_subclasses) + 1))
         print(f"{sub.name}: {len(files)} seed volumes")
     return 0

@@ -195,3 +195,74 @@ def test_batch_entries_are_independent_at_full_size(data):
         im, sg = eng.run_base([p], [data["seeds"]], [data["seg"]], scale=True)
         assert torch.equal(im[0], img_b[i]) and torch.equal(sg[0], seg_b[i])
         assert float(im.min()) == 0.0 and float(im.max()) == 1.0
+
+
+# ----------------------------------------------------------------------------- seed generation and packed cache at 256^3
+def test_seed_generation_at_full_size(data):
+    """scripts/generate_seeds.py for one 256^3 subject through properties that hold for any input: the
+    partition covers every labelled voxel once, every fit converges with ordered lower bounds, the seed
+    volumes keep the meta-label support with labels 10 m .. 10 m + n - 1 and equal the oracle's argmax
+    under the fitted parameters, and the whole run is reproducible for a fixed seed."""
+    from fetalsyngen_b200.seeds import SeedGenerator
+
+    seg = data["seg_h"]
+    rs = np.random.RandomState(3)
+    base = np.array([0, 900, 300, 450, 820, 520, 330, 480], dtype=np.float32)[seg]
+    image = np.maximum(base + 45 * rs.standard_normal(SHAPE).astype(np.float32), 0)
+    image[(seg == 0) & (rs.rand(*SHAPE) < 0.7)] = 0  # most of the background is air
+    gen = SeedGenerator("feta", DEV, seed=12)
+    x, index, counts = gen.partition(image, seg)
+    meta = np.array([4, 1, 2, 3, 1, 3, 2, 3], dtype=np.uint8)[seg]
+    meta[(seg == 0) & (image == 0)] = 0
+    assert counts == [int((meta == m).sum()) for m in range(1, 5)]
+    out = gen.split_labels(image, seg, [1, 3, 5])
+    fits = gen.last_fit
+    for (n_sub, m), f in fits.items():
+        assert f["converged"] and 2 <= f["n_iter"] <= 100
+        assert np.all(np.diff(f["trace"][1:]) > -1e-6)  # EM never lowers the likelihood (first step starts from point masses)
+        assert abs(f["weights"].sum() - 1) < 1e-12 and np.all(f["covariances"] > 0)
+    for n_sub in (1, 3, 5):
+        for m in range(1, 5):
+            vol = out[n_sub][m].cpu().numpy()
+            sel = meta == m
+            assert not vol[~sel].any()
+            labs = np.unique(vol[sel])
+            assert labs.min() >= 10 * m and labs.max() <= 10 * m + n_sub - 1
+            if n_sub > 1:
+                # the labels are the argmax of the fitted mixture's weighted log-probabilities (oracle arithmetic, subsample)
+                import np_seeds as NS
+
+                pick = np.flatnonzero(sel.reshape(-1))[:: max(1, int(sel.sum()) // 50000)]
+                want = NS.predict(image.reshape(-1)[pick], fits[(n_sub, m - 1)]) + 10 * m
+                assert (vol.reshape(-1)[pick] != want).mean() <= 1e-4
+    again = SeedGenerator("feta", DEV, seed=12).split_labels(image, seg, [3])
+    assert all(torch.equal(again[3][m], out[3][m]) for m in range(1, 5))
+
+
+def test_packed_seed_cache_at_full_size(data):
+    """Six sub-class counts of a 256^3 subject in one uint16 volume: every draw of counts unpacks to the
+    sum of the four selected seed volumes, and the GMM image from the unpacked labels equals the one from
+    the four volumes (same Philox stream)."""
+    from fetalsyngen_b200.data import packed as K
+
+    seeds = {}
+    for n in range(1, 7):
+        _, sv = label_phantom(SHAPE, n_sub=(n, n, n, n), seed=n)
+        seeds[n] = {m + 1: sv[m] for m in range(4)}
+    words, counts = K.pack_seed_volumes(seeds)
+    assert words.dtype == np.uint16 and words.nbytes == 2 * S**3
+    ps = K.PackedSeeds(words, counts, DEV)
+    eng = data["eng"]
+    rs = np.random.RandomState(8)
+    for _ in range(3):
+        m2s = {m: int(rs.randint(1, 7)) for m in range(1, 5)}
+        lab = ps.labels(m2s, DEV)
+        vols = [torch.from_numpy(seeds[m2s[m]][m]).to(DEV).view(-1) for m in range(1, 5)]
+        want = sum(v.to(torch.int32) for v in vols).to(torch.uint8)
+        assert torch.equal(lab.view(-1), want)
+        p = _plan(rs)
+        a = torch.empty((1, S**3), dtype=torch.float32, device=DEV)
+        b = torch.empty_like(a)
+        eng.gmm([p], [vols], a)
+        eng.gmm([p], [[lab.view(-1)]], b)
+        assert torch.equal(a, b)

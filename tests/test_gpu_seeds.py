@@ -206,3 +206,27 @@ def test_process_subject_writes_reference_layout(tmp_path):
     # the written seeds feed the generator's dataset loader
     one = read_nifti(tmp_path / "out" / "subclasses_1" / "sub-x" / "anat" / "sub-x_rec-irtk_T2w_dseg_mlabel_3.nii.gz")
     assert np.array_equal(one, g["sub1_m3"])
+
+
+def test_cli_packed_output_feeds_the_dataset_cache(tmp_path):
+    """--packed: seeds go straight into the bit-packed subject cache; unpacking any draw of sub-class counts
+    gives volumes with the right support and label range, and the one-sub-class draw equals the reference golden."""
+    from fetalsyngen_b200.data.packed import load_packed, unpack_numpy
+    from fetalsyngen_b200.utils.nifti import write_nifti
+
+    g = load("seeds_split")
+    aff = np.diag([0.5, 0.5, 0.5, 1.0])
+    anat = tmp_path / "bids" / "sub-x" / "anat"
+    anat.mkdir(parents=True)
+    write_nifti(anat / "sub-x_rec-irtk_T2w.nii.gz", np.nan_to_num(g["image"]), aff)
+    write_nifti(anat / "sub-x_rec-irtk_T2w_dseg.nii.gz", g["seg"].astype(np.float32), aff)
+    assert P.main(["--bids_path", str(tmp_path / "bids"), "--out_path", str(tmp_path / "cache"), "--max_subclasses", "4", "--annotation", "feta", "--seed", "2", "--packed"]) == 0
+    seg, ps, aff2 = load_packed(tmp_path / "cache" / "sub-x.fsgpack.npz")
+    assert np.array_equal(seg, g["seg"].astype(np.uint8)) and ps.counts == [1, 2, 3, 4] and np.allclose(aff2, aff)
+    one = unpack_numpy(ps._host, ps.counts, {m: 1 for m in range(1, 5)})
+    assert np.array_equal(one, sum(g[f"sub1_m{m}"].astype(np.int32) for m in range(1, 5)).astype(np.uint8))
+    lab = ps.labels({1: 4, 2: 2, 3: 3, 4: 1}, DEV).cpu().numpy()
+    for m, n in ((1, 4), (2, 2), (3, 3), (4, 1)):
+        sel = g[f"sub1_m{m}"] > 0
+        assert lab[sel].min() >= 10 * m and lab[sel].max() <= 10 * m + n - 1
+    assert not lab[one == 0].any()
