@@ -153,6 +153,16 @@ def bind_to_gpu_numa_node(local: int) -> str:
 
 
 # ---------------------------------------------------------------------------------- synthetic inputs
+def reference_motion_extension():
+    """Baseline leg of `tools/bench_configs.py --config motion`: the reference's own slice-acquisition
+    extension, built from the reference's sources into oracle/_ref by oracle/build_ref.py (None when it
+    is absent).  It is only timed next to libfsg, never called by the product."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+
+    return build_ref.load_built()
+
+
 def draw_oracle_params(rs, shape, res=0.5):
     """Drawn parameters for one sample in np_oracle.generate_base form (all gates on)."""
     from fetalsyngen_b200.tables import make_affine_matrix, resample_size, resample_stds

@@ -54,6 +54,17 @@ def test_no_cpu_fallback_and_no_oracle_in_product():
         assert "import sklearn" not in src and "from sklearn" not in src, p  # the reference's clustering dependency is a checker, never a code path
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: tools/ and the package never import it (bench.py and
+    __graft_entry__.py hold the only measurement / smoke legs that do)."""
+    names = ("np_oracle", "np_motion", "np_artifacts", "np_seeds", "ref_import", "build_ref")
+    for folder in ("tools", "fetalsyngen_b200"):
+        for p in (ROOT / folder).rglob("*.py"):
+            src = p.read_text()
+            for n in names:
+                assert f"import {n}" not in src, (p, n)
+
+
 def test_c_abi_argument_checks_without_a_gpu():
     """Argument validation happens before any CUDA call: bad arguments give rc != 0 + a message."""
     from fetalsyngen_b200 import _lib

@@ -167,13 +167,10 @@ def run_sweep(args):
 def run_motion(args):
     """Slice-acquisition forward / PSF-reconstruction adjoint at the default config's sizes: libfsg vs
     the reference's own extension (oracle/_ref, built from the reference's sources for sm_100a)."""
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import build_ref
-    import np_motion as M
     from fetalsyngen_b200.generator.artifacts import simulate_reco as SR
     from fetalsyngen_b200.generator.artifacts import svort
 
-    ext = build_ref.load_built()
+    ext = bench.reference_motion_extension()  # baseline leg: lives in bench.py, the one measurement file that may touch oracle/
     S = args.shape
     seg_h, _ = label_phantom((S, S, S))
     rs = np.random.RandomState(0)
