@@ -39,6 +39,11 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.fsg_last_error(), bytes)
 
 
+def test_integration_doc_names_every_entry_point():
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    assert [n for n in _declared() if n not in doc] == []
+
+
 def test_no_cpu_fallback_and_no_oracle_in_product():
     from fetalsyngen_b200 import _lib
     from fetalsyngen_b200.engine import SynthEngine
