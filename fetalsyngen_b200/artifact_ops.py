@@ -17,6 +17,17 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def upload(arr, dtype, device) -> torch.Tensor:
+    """Small host array -> device without stalling the host: a blocking ``.to(device)`` from pageable
+    memory synchronises the stream, i.e. waits for every kernel queued so far (measured: 0.7 ms per
+    call inside SimulateMotion, ~40 calls per sample).  The copy goes through torch's caching pinned
+    allocator instead, which keeps the staging block alive until the copy has run."""
+    h = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
+    if torch.device(device).type != "cuda":
+        return h.to(device)
+    return h.pin_memory().to(device, non_blocking=True)
+
+
 def upsample_table(n_in: int, n_out: int) -> np.ndarray:
     """1-D table of ``F.interpolate(mode='trilinear', align_corners=False)``
     (reference call site: augmentation/artifacts.py:315-320)."""

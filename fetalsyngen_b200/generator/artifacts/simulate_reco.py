@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ...artifact_ops import ArtifactOps, _stream
+from ...artifact_ops import ArtifactOps, _stream, upload
 from ...engine import engine_for
 from . import svort
 from .svort import RigidTransform
@@ -32,11 +32,25 @@ F32 = np.float32
 
 
 def _dev_f32(arr, device):
-    return torch.from_numpy(np.ascontiguousarray(arr, dtype=F32)).to(device)
+    return upload(arr, F32, device)
 
 
 def _dev_i32(arr, device):
-    return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)).to(device)
+    return upload(arr, np.int32, device)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """Per-device stream for the cheap mask acquisitions whose read-back decides which slices survive:
+    on the main stream that read-back would wait for the previous stack's PSF acquisition."""
+    key = str(torch.device(device))
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device, priority=-1)  # its small kernels must not queue behind the main stream's grids
+        _SIDE_STREAMS[key] = s
+    return s
 
 
 def slice_acquisition(mat, vol, psf, slice_shape, res_slice, out=None):
@@ -192,6 +206,8 @@ class Scanner:
         num_stacks = np.random.randint(self.min_num_stack, self.max_num_stack + 1)
         rng_seed = int(torch.randint(0, 2**62, (1,)).item())
         sums_d = torch.empty(ns, dtype=torch.float32, device=device)
+        main, side = torch.cuda.current_stream(device), _side_stream(device)
+        side.wait_stream(main)  # the mask volume was produced on the main stream
         attempt = 0
         while True:
             transform_init = svort.random_init_stack_transforms(ns, gap, self.restrict_transform, self.txy)
@@ -205,9 +221,11 @@ class Scanner:
             # content passes a random threshold (simulate_reco.py:355-371).  Slices are independent, so the
             # cheap one-tap mask stack goes first: the read-back that decides which slices survive waits for
             # it alone, and the PSF acquisition of the image runs for the surviving run of slices only.
-            slices_no_psf = slice_acquisition(mat, data["mask"], psf_one, (ss, ss), res_s / res)
-            _lib.call("fsg_slice_sums", slices_no_psf.data_ptr(), ns, ss * ss, sums_d.data_ptr(), _stream())
-            nnz = sums_d.cpu().numpy()
+            with torch.cuda.stream(side):
+                slices_no_psf = slice_acquisition(mat, data["mask"], psf_one, (ss, ss), res_s / res)
+                _lib.call("fsg_slice_sums", slices_no_psf.data_ptr(), ns, ss * ss, sums_d.data_ptr(), _stream())
+                nnz = sums_d.cpu().numpy()  # synchronises the side stream only
+            slices_no_psf.record_stream(main)  # consumed on the main stream later (PSFReconstructor)
             idx = nnz > (nnz.max() * np.random.uniform(0.1, 0.3))
             if idx.sum() == 0:
                 continue
@@ -233,6 +251,7 @@ class Scanner:
             positions.append(np.arange(slices.shape[0], dtype=F32) - slices.shape[0] // 2)
             if len(stacks) >= num_stacks:
                 break
+        main.wait_stream(side)  # the mask stacks are read on the main stream from here on
         stacks_ids = np.random.choice(20, len(stacks), replace=False)
         data["positions"] = np.concatenate([np.stack((positions[i], np.full_like(positions[i], s_i)), -1) for i, s_i in enumerate(stacks_ids)], 0)
         data["slice_shape"] = (ss, ss)

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ...artifact_ops import STAGE_PYRAMID, STAGE_RING, ArtifactOps, _stream
+from ...artifact_ops import STAGE_PYRAMID, STAGE_RING, ArtifactOps, _stream, upload
 from ...engine import SamplePlan, engine_for
 from ..artifacts.utils import ReconParams, ScannerParams, StructNoiseMergeParams
 from .synthseg import RandTransform
@@ -60,13 +60,13 @@ class BlurCortex(RandTransform):
         src = output.to(eng.device, torch.float32).contiguous().view(-1)
         if "centers" in inject:  # reference voxel indices (i0, i1, i2): blob at axis position (i2, i1, i0)
             c = np.asarray(inject["centers"], dtype=np.float32)[:, ::-1].copy()
-            centers, count = torch.from_numpy(c).to(eng.device), c.shape[0]
+            centers, count = upload(c, np.float32, eng.device), c.shape[0]
         else:
             # frontal-lobe prior (blur_proba, :63-81): centres (0,y,z//2),(x,y,z//2) unpacked x<->last axis
             prior = ([(z // 2, y, 0), (z // 2, y, x)], [[x // 5] * 3, [y // 5] * 3])
             centers, count = ops.sample_voxels(seg8, int(nblur), match=self.cortex_label, prior=prior, transpose_out=True, rng=_rng_pair())
         sig = np.asarray(inject["sigmas"], dtype=np.float64) if "sigmas" in inject else np.random.gamma(self.sigma_gamma_loc, self.sigma_gamma_scale, (int(nblur), 3))
-        sig_axis = torch.from_numpy(np.ascontiguousarray(sig[:count, ::-1], dtype=np.float32)).to(eng.device)
+        sig_axis = upload(sig[:count, ::-1], np.float32, eng.device)
         blurred, t1, t2 = ops.f32("a"), ops.f32("b"), ops.f32("c")
         eng.sepconv([SamplePlan(stds=std_blurs)], [src], [blurred], [t1], [t2], positions=False)
         out = torch.empty_like(src)
@@ -125,7 +125,7 @@ class StructNoise(RandTransform):
             g[-1, :, :] = g[0, :, :]
             g[:, -1, :] = g[:, 0, :]
             g[:, :, -1] = g[:, :, 0]
-            gd = g.float().contiguous().to(eng.device)
+            gd = upload(g.float().numpy(), np.float32, eng.device)  # non-blocking: a plain .to() here waits for the whole reconstruction
             keep.append(gd)
             octs[o].grad = gd.data_ptr()
             for a in range(3):
@@ -281,11 +281,11 @@ class SimulatedBoundaries(RandTransform):
         mask_modif = cur
         if "centers" in inject:
             c = np.asarray(inject["centers"], dtype=np.float32)[:, ::-1].copy()
-            centers, count = torch.from_numpy(c).to(eng.device), c.shape[0]
+            centers, count = upload(c, np.float32, eng.device), c.shape[0]
         else:
             centers, count = ops.sample_voxels(mask, int(self.n_centers), labels2=mask_modif, transpose_out=True, rng=_rng_pair())
         sigmas = np.asarray(inject["sigmas"], dtype=np.float64) if "sigmas" in inject else np.array([self.base_sigma + 10 * np.random.beta(2, 5) for _ in range(count)])
-        sig_axis = torch.from_numpy(np.repeat(sigmas[:count, None], 3, 1).astype(np.float32)).to(eng.device)
+        sig_axis = upload(np.repeat(sigmas[:count, None], 3, 1), np.float32, eng.device)
         mog = ops.f32("a")
         ops.mog(centers[:count].contiguous(), sig_axis, out=mog)
         n_dilate = 6 * (self.n_generate_fuzzy - 1)
