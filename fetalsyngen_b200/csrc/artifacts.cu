@@ -303,6 +303,58 @@ __global__ void __launch_bounds__(ART_THREADS) morph_axis_kernel(const uint8_t* 
   }
 }
 
+// Vector forms of the window op (bit-identical to morph_axis_kernel): SIMD byte max / min / add on
+// packed voxels.  Zero padding needs no special case: out-of-range words are 0, which is the identity
+// of max / add and the padding value of the zero-padded erosion.
+template <int OP>
+__device__ __forceinline__ uint32_t morph_op4(uint32_t a, uint32_t b) {
+  return OP == MORPH_MAX ? __vmaxu4(a, b) : (OP == MORPH_MIN ? __vminu4(a, b) : __vadd4(a, b));
+}
+
+// axis 0 / 1 (stride >= one z row): 16 consecutive z voxels per thread, one 16-byte load per tap.
+template <int OP>
+__global__ void __launch_bounds__(ART_THREADS) morph_axis_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int sx, int sy, int sz, int axis, int r) {
+  const unsigned n16 = (unsigned)sx * sy * sz / 16u;
+  const int stride = axis == 0 ? sy * sz : sz;
+  const int len = axis == 0 ? sx : sy;
+  for (unsigned g = blockIdx.x * ART_THREADS + threadIdx.x; g < n16; g += gridDim.x * ART_THREADS) {
+    const unsigned v = g * 16u;
+    const int pos = axis == 1 ? (int)((v / (unsigned)sz) % (unsigned)sy) : (int)(v / ((unsigned)sy * sz));
+    const int t0 = max(-r, -pos), t1 = min(r, len - 1 - pos);
+    const uint32_t init = (OP == MORPH_MIN && t0 == -r && t1 == r) ? 0xffffffffu : 0u;
+    uint4 acc = make_uint4(init, init, init, init);
+    for (int t = t0; t <= t1; ++t) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (int)v + t * stride));
+      acc.x = morph_op4<OP>(acc.x, q.x);
+      acc.y = morph_op4<OP>(acc.y, q.y);
+      acc.z = morph_op4<OP>(acc.z, q.z);
+      acc.w = morph_op4<OP>(acc.w, q.w);
+    }
+    *reinterpret_cast<uint4*>(dst + v) = acc;
+  }
+}
+
+// axis 2 (along z), half-width R <= 3: 4 consecutive voxels per thread; the shifted windows come from
+// the word itself and its two neighbours by funnel shifts.
+template <int OP, int R>
+__global__ void __launch_bounds__(ART_THREADS) morph_z_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, unsigned n4, int sz) {
+  const uint32_t* __restrict__ s32 = reinterpret_cast<const uint32_t*>(src);
+  const unsigned wz = (unsigned)sz / 4u;  // words per row
+  for (unsigned g = blockIdx.x * ART_THREADS + threadIdx.x; g < n4; g += gridDim.x * ART_THREADS) {
+    const unsigned col = g % wz;
+    const uint32_t w0 = __ldg(s32 + g);
+    const uint32_t wm = col > 0 ? __ldg(s32 + g - 1) : 0u;
+    const uint32_t wp = col + 1 < wz ? __ldg(s32 + g + 1) : 0u;
+    uint32_t acc = w0;
+#pragma unroll
+    for (int t = 1; t <= R; ++t) {
+      acc = morph_op4<OP>(acc, __funnelshift_r(w0, wp, 8 * t));        // voxels z + t
+      acc = morph_op4<OP>(acc, __funnelshift_r(wm, w0, 32 - 8 * t));   // voxels z - t
+    }
+    reinterpret_cast<uint32_t*>(dst)[g] = acc;
+  }
+}
+
 // squared / L1 distance to the nearest set voxel, separable min-plus passes with window r.
 // pass over `axis`: dst = min_t src[v + t] + cost(t), cost = t^2 (SQ) or |t|; INF = 65535.
 template <bool SQ, bool FIRST>
@@ -454,6 +506,40 @@ extern "C" int fsg_struct_blend(const float* x, const uint8_t* seg, const float*
   return check_launch("fsg_struct_blend");
 }
 
+// Packed form of dist_axis_kernel for axis 0 / 1 (bit-identical): 8 consecutive z voxels per thread,
+// saturating halfword add + unsigned halfword min (min(s + c, 65535) == saturating add).
+template <bool SQ, bool FIRST>
+__global__ void __launch_bounds__(ART_THREADS) dist_axis_vec_kernel(const void* __restrict__ src_, uint16_t* __restrict__ dst, int sx, int sy, int sz, int axis, int r) {
+  const unsigned n8 = (unsigned)sx * sy * sz / 8u;
+  const int stride = axis == 0 ? sy * sz : sz;
+  const int len = axis == 0 ? sx : sy;
+  const uint8_t* m8 = reinterpret_cast<const uint8_t*>(src_);
+  const uint16_t* d16 = reinterpret_cast<const uint16_t*>(src_);
+  for (unsigned g = blockIdx.x * ART_THREADS + threadIdx.x; g < n8; g += gridDim.x * ART_THREADS) {
+    const unsigned v = g * 8u;
+    const int pos = axis == 1 ? (int)((v / (unsigned)sz) % (unsigned)sy) : (int)(v / ((unsigned)sy * sz));
+    const int t0 = max(-r, -pos), t1 = min(r, len - 1 - pos);
+    uint4 best = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int t = t0; t <= t1; ++t) {
+      const uint32_t c = (uint32_t)(SQ ? t * t : abs(t));
+      const uint32_t c2 = c | (c << 16);
+      uint4 q;
+      if (FIRST) {
+        const uint2 m = __ldg(reinterpret_cast<const uint2*>(m8 + (int)v + t * stride));
+        const uint32_t z0 = __vcmpeq4(m.x, 0u), z1 = __vcmpeq4(m.y, 0u);  // 0xff where the mask is clear -> distance 65535
+        q = make_uint4(__byte_perm(z0, 0u, 0x1100), __byte_perm(z0, 0u, 0x3322), __byte_perm(z1, 0u, 0x1100), __byte_perm(z1, 0u, 0x3322));
+      } else {
+        q = __ldg(reinterpret_cast<const uint4*>(d16 + (int)v + t * stride));
+      }
+      best.x = __vminu2(best.x, __vaddus2(q.x, c2));
+      best.y = __vminu2(best.y, __vaddus2(q.y, c2));
+      best.z = __vminu2(best.z, __vaddus2(q.z, c2));
+      best.w = __vminu2(best.w, __vaddus2(q.w, c2));
+    }
+    *reinterpret_cast<uint4*>(dst + v) = best;
+  }
+}
+
 // op: 0 = box dilation (max), 1 = box erosion (min, zero padded), 2 = box count (sum, k^3 <= 255)
 extern "C" int fsg_morph_box(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int k, int op, int sx, int sy, int sz, void* stream) {
   if (int rc = check_shape("fsg_morph_box", sx, sy, sz)) return rc;
@@ -464,14 +550,39 @@ extern "C" int fsg_morph_box(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int
   const int r = k / 2;
   const uint8_t* in[3] = {src, dst, tmp};
   uint8_t* outp[3] = {dst, tmp, dst};
+  // packed-voxel kernels when rows are whole 16-byte words (bit-identical results)
+  const bool vec = sz % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(tmp)) & 15) == 0;
+  const int64_t nvox = (int64_t)sx * sy * sz;
+#define FSG_MORPH_OPS(CALL)                 \
+  do {                                      \
+    if (op == 0) { CALL(MORPH_MAX); }       \
+    else if (op == 1) { CALL(MORPH_MIN); }  \
+    else { CALL(MORPH_SUM); }               \
+  } while (0)
   for (int a = 0; a < 3; ++a) {
-    if (op == 0)
-      morph_axis_kernel<MORPH_MAX><<<g, ART_THREADS, 0, s>>>(in[a], outp[a], sx, sy, sz, a, r);
-    else if (op == 1)
-      morph_axis_kernel<MORPH_MIN><<<g, ART_THREADS, 0, s>>>(in[a], outp[a], sx, sy, sz, a, r);
-    else
-      morph_axis_kernel<MORPH_SUM><<<g, ART_THREADS, 0, s>>>(in[a], outp[a], sx, sy, sz, a, r);
+    if (vec && a < 2) {
+      const unsigned gv = art_grid(nvox / 16);
+#define FSG_CALL(OP) morph_axis_vec_kernel<OP><<<gv, ART_THREADS, 0, s>>>(in[a], outp[a], sx, sy, sz, a, r)
+      FSG_MORPH_OPS(FSG_CALL);
+#undef FSG_CALL
+    } else if (vec && r >= 1 && r <= 3) {
+      const unsigned gv = art_grid(nvox / 4);
+      const unsigned n4 = (unsigned)(nvox / 4);
+#define FSG_CALL(OP)                                                                              \
+  do {                                                                                            \
+    if (r == 1) morph_z_vec_kernel<OP, 1><<<gv, ART_THREADS, 0, s>>>(in[a], outp[a], n4, sz);      \
+    else if (r == 2) morph_z_vec_kernel<OP, 2><<<gv, ART_THREADS, 0, s>>>(in[a], outp[a], n4, sz); \
+    else morph_z_vec_kernel<OP, 3><<<gv, ART_THREADS, 0, s>>>(in[a], outp[a], n4, sz);             \
+  } while (0)
+      FSG_MORPH_OPS(FSG_CALL);
+#undef FSG_CALL
+    } else {
+#define FSG_CALL(OP) morph_axis_kernel<OP><<<g, ART_THREADS, 0, s>>>(in[a], outp[a], sx, sy, sz, a, r)
+      FSG_MORPH_OPS(FSG_CALL);
+#undef FSG_CALL
+    }
   }
+#undef FSG_MORPH_OPS
   return check_launch("fsg_morph_box");
 }
 
@@ -483,13 +594,26 @@ extern "C" int fsg_morph_dist(const uint8_t* mask, uint16_t* dist_out, uint16_t*
   FSG_REQUIRE(r >= 1 && r <= 120 && (metric == 0 || metric == 1), "fsg_morph_dist: bad radius / metric");
   cudaStream_t s = as_stream(stream);
   const unsigned g = art_grid((int64_t)sx * sy * sz);
+  // packed halfword kernels for the two strided passes when rows are whole 16-byte words
+  const bool vec = sz % 8 == 0 && ((reinterpret_cast<uintptr_t>(mask) & 7) | ((reinterpret_cast<uintptr_t>(dist_out) | reinterpret_cast<uintptr_t>(tmp)) & 15)) == 0;
+  const unsigned gv = art_grid((int64_t)sx * sy * sz / 8);
   if (metric == 0) {
-    dist_axis_kernel<true, true><<<g, ART_THREADS, 0, s>>>(mask, dist_out, sx, sy, sz, 0, r);
-    dist_axis_kernel<true, false><<<g, ART_THREADS, 0, s>>>(dist_out, tmp, sx, sy, sz, 1, r);
+    if (vec) {
+      dist_axis_vec_kernel<true, true><<<gv, ART_THREADS, 0, s>>>(mask, dist_out, sx, sy, sz, 0, r);
+      dist_axis_vec_kernel<true, false><<<gv, ART_THREADS, 0, s>>>(dist_out, tmp, sx, sy, sz, 1, r);
+    } else {
+      dist_axis_kernel<true, true><<<g, ART_THREADS, 0, s>>>(mask, dist_out, sx, sy, sz, 0, r);
+      dist_axis_kernel<true, false><<<g, ART_THREADS, 0, s>>>(dist_out, tmp, sx, sy, sz, 1, r);
+    }
     dist_axis_kernel<true, false><<<g, ART_THREADS, 0, s>>>(tmp, dist_out, sx, sy, sz, 2, r);
   } else {
-    dist_axis_kernel<false, true><<<g, ART_THREADS, 0, s>>>(mask, dist_out, sx, sy, sz, 0, r);
-    dist_axis_kernel<false, false><<<g, ART_THREADS, 0, s>>>(dist_out, tmp, sx, sy, sz, 1, r);
+    if (vec) {
+      dist_axis_vec_kernel<false, true><<<gv, ART_THREADS, 0, s>>>(mask, dist_out, sx, sy, sz, 0, r);
+      dist_axis_vec_kernel<false, false><<<gv, ART_THREADS, 0, s>>>(dist_out, tmp, sx, sy, sz, 1, r);
+    } else {
+      dist_axis_kernel<false, true><<<g, ART_THREADS, 0, s>>>(mask, dist_out, sx, sy, sz, 0, r);
+      dist_axis_kernel<false, false><<<g, ART_THREADS, 0, s>>>(dist_out, tmp, sx, sy, sz, 1, r);
+    }
     dist_axis_kernel<false, false><<<g, ART_THREADS, 0, s>>>(tmp, dist_out, sx, sy, sz, 2, r);
   }
   return check_launch("fsg_morph_dist");

@@ -232,3 +232,51 @@ def test_sample_voxels_distribution():
     # fewer candidates than requested: everything is taken at most once
     c, n = ops.sample_voxels(labd, 100, match=3, transpose_out=False, rng=(7, 1))
     assert n <= 64 and n >= 40
+
+
+@pytest.mark.parametrize("shape", [(32, 48, 64), (20, 24, 30), (16, 16, 16), (9, 33, 20)])
+def test_box_morphology_packed_and_scalar_paths_match_scipy(shape):
+    """fsg_morph_box (max / zero-padded min / count) on shapes that take the packed-voxel kernels
+    (z extent a multiple of 16) and on shapes that fall back to the voxel-per-thread kernel, including
+    half-widths above the packed z kernel's range — all bit-exact against scipy.ndimage."""
+    from scipy import ndimage
+
+    eng = engine_for(DEV, shape, (1.0, 1.0, 1.0))
+    ops = ArtifactOps(eng)
+    rs = np.random.RandomState(shape[0])
+    m = (rs.rand(*shape) > 0.6).astype(np.uint8)
+    a = dev(m).view(-1)
+    b, c = torch.empty_like(a), torch.empty_like(a)
+    for k in (3, 5, 7, 9):
+        got = ops.box(a, b, c, k, 0).cpu().numpy().reshape(shape)
+        np.testing.assert_array_equal(got, ndimage.maximum_filter(m, size=k, mode="constant", cval=0))
+        got = ops.box(a, b, c, k, 1).cpu().numpy().reshape(shape)
+        np.testing.assert_array_equal(got, ndimage.minimum_filter(m, size=k, mode="constant", cval=0))
+    for k in (3, 5):
+        got = ops.box(a, b, c, k, 2).cpu().numpy().reshape(shape)
+        want = ndimage.uniform_filter(m.astype(np.float64), size=k, mode="constant", cval=0) * k**3
+        np.testing.assert_array_equal(got, np.round(want).astype(np.uint8))
+
+
+@pytest.mark.parametrize("shape", [(32, 48, 64), (20, 24, 30), (8, 8, 8)])
+def test_windowed_distance_packed_and_scalar_paths(shape):
+    """fsg_morph_dist (squared Euclidean / L1 distance to the nearest set voxel inside a +-r window,
+    65535 = none) against a brute-force numpy evaluation, on shapes that take the packed halfword
+    kernels for the strided passes and on shapes that do not."""
+    eng = engine_for(DEV, shape, (1.0, 1.0, 1.0))
+    ops = ArtifactOps(eng)
+    rs = np.random.RandomState(shape[1])
+    m = (rs.rand(*shape) > 0.97).astype(np.uint8)
+    d16, t16 = ops.u16("d0"), ops.u16("d1")
+    for r, metric in ((3, 0), (2, 1), (5, 0)):
+        want = np.full(shape, 65535, dtype=np.int64)
+        pad = np.pad(m, r)
+        for dx in range(-r, r + 1):
+            for dy in range(-r, r + 1):
+                for dz in range(-r, r + 1):
+                    c = dx * dx + dy * dy + dz * dz if metric == 0 else abs(dx) + abs(dy) + abs(dz)
+                    sh = pad[r + dx : r + dx + shape[0], r + dy : r + dy + shape[1], r + dz : r + dz + shape[2]]
+                    want = np.where(sh > 0, np.minimum(want, c), want)
+        ops.dist(dev(m).view(-1), d16, t16, r, metric)
+        got = d16.cpu().numpy().view(np.uint16).reshape(-1)[: m.size].reshape(shape).astype(np.int64)
+        np.testing.assert_array_equal(got, want)
