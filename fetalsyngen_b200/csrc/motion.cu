@@ -49,7 +49,40 @@ __device__ __forceinline__ SliceGeom slice_geom(const float* __restrict__ t, int
   return g;
 }
 
+// The eight corners of a trilinear sample.  PAIRS: `vol` is the x-pair volume of fsg_volume_xpairs
+// ((v[i], v[i+1]) per voxel), so the two x corners of a row arrive in one 8-byte load — half the gather
+// instructions of the acquisition kernels, which are bound by L1 wavefronts, not by bytes.
+template <int PAIRS>
+__device__ __forceinline__ void load_corners(const float* __restrict__ vol, int idx, int Sy, int Sz, float& c000, float& c100, float& c010, float& c110, float& c001, float& c101,
+                                             float& c011, float& c111) {
+  if (PAIRS == 4) {  // xy-quad volume: (v[i], v[i+1], v[i+Sy], v[i+Sy+1]) per voxel, two 16-byte loads
+    const float4* v4 = reinterpret_cast<const float4*>(vol) + idx;
+    const float4 a = __ldg(v4), b = __ldg(v4 + Sz);
+    c000 = a.x; c100 = a.y; c010 = a.z; c110 = a.w; c001 = b.x; c101 = b.y; c011 = b.z; c111 = b.w;
+  } else if (PAIRS == 2) {
+    const float2* v2 = reinterpret_cast<const float2*>(vol) + idx;
+    const float2 a = __ldg(v2), b = __ldg(v2 + Sy), c = __ldg(v2 + Sz), d = __ldg(v2 + Sy + Sz);
+    c000 = a.x; c100 = a.y; c010 = b.x; c110 = b.y; c001 = c.x; c101 = c.y; c011 = d.x; c111 = d.y;
+  } else {
+    const float* v = vol + idx;
+    c000 = __ldg(v); c100 = __ldg(v + 1); c010 = __ldg(v + Sy); c110 = __ldg(v + 1 + Sy);
+    c001 = __ldg(v + Sz); c101 = __ldg(v + 1 + Sz); c011 = __ldg(v + Sy + Sz); c111 = __ldg(v + Sy + Sz + 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) xyquads_kernel(const float* __restrict__ vol, float4* __restrict__ quads, int64_t n, int Sy) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    quads[i] = make_float4(vol[i], i + 1 < n ? vol[i + 1] : 0.f, i + Sy < n ? vol[i + Sy] : 0.f, i + Sy + 1 < n ? vol[i + Sy + 1] : 0.f);
+}
+
+__global__ void __launch_bounds__(256) xpairs_kernel(const float* __restrict__ vol, float2* __restrict__ pairs, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) pairs[i] = make_float2(vol[i], i + 1 < n ? vol[i + 1] : 0.f);
+}
+
 // ---------------------------------------------------------------------------------- forward
+template <int PAIRS>
 __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const float* __restrict__ transforms, const float* __restrict__ vol, const float4* __restrict__ taps, int ntaps,
                                                                         float radius, float* __restrict__ slices, int h, int w, int D, int H, int W, float res) {
   extern __shared__ float4 s_tap[];  // R * tap offset (x, y, z) and weight
@@ -83,25 +116,26 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const flo
     if (x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz) continue;
     const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
     const float wx = x - fx, wy = y - fy, wz = z - fz;
-    const float* v = vol + ((int)fz * Sz + (int)fy * Sy + (int)fx);
     const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
     const float p000 = ux * uy * uz * q.w, p100 = wx * uy * uz * q.w, p010 = ux * wy * uz * q.w, p001 = ux * uy * wz * q.w;
     const float p110 = wx * wy * uz * q.w, p101 = wx * uy * wz * q.w, p011 = ux * wy * wz * q.w, p111 = wx * wy * wz * q.w;
-    val += p000 * __ldg(v);
+    float c000, c100, c010, c110, c001, c101, c011, c111;
+    load_corners<PAIRS>(vol, (int)fz * Sz + (int)fy * Sy + (int)fx, Sy, Sz, c000, c100, c010, c110, c001, c101, c011, c111);
+    val += p000 * c000;
     weight += p000;
-    val += p100 * __ldg(v + 1);
+    val += p100 * c100;
     weight += p100;
-    val += p010 * __ldg(v + Sy);
+    val += p010 * c010;
     weight += p010;
-    val += p001 * __ldg(v + Sz);
+    val += p001 * c001;
     weight += p001;
-    val += p110 * __ldg(v + 1 + Sy);
+    val += p110 * c110;
     weight += p110;
-    val += p101 * __ldg(v + 1 + Sz);
+    val += p101 * c101;
     weight += p101;
-    val += p011 * __ldg(v + Sy + Sz);
+    val += p011 * c011;
     weight += p011;
-    val += p111 * __ldg(v + Sy + Sz + 1);
+    val += p111 * c111;
     weight += p111;
   }
   if (weight > 0.f) slices[((size_t)in * h + iy) * w + ix] = __fdiv_rn(val, weight);
@@ -110,6 +144,7 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const flo
 // Warp-per-pixel acquisition for large PSFs: the lanes split the taps of one pixel (consecutive taps
 // sample neighbouring voxels: coalesced gathers), partial sums are reduced with shuffles.  Summation
 // order differs from the sequential tap loop (float tolerance).
+template <int PAIRS>
 __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_warp_kernel(const float* __restrict__ transforms, const float* __restrict__ vol, const float4* __restrict__ taps, int ntaps,
                                                                              float radius, float* __restrict__ slices, int h, int w, int D, int H, int W, float res) {
   extern __shared__ float4 s_tap[];
@@ -151,25 +186,26 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_warp_kernel(cons
       if (x < 0.f || y < 0.f || z < 0.f || x >= mx || y >= my || z >= mz) continue;
       const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
       const float wx = x - fx, wy = y - fy, wz = z - fz;
-      const float* v = vol + ((int)fz * Sz + (int)fy * Sy + (int)fx);
-      const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
+        const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
       const float p000 = ux * uy * uz * o.w, p100 = wx * uy * uz * o.w, p010 = ux * wy * uz * o.w, p001 = ux * uy * wz * o.w;
       const float p110 = wx * wy * uz * o.w, p101 = wx * uy * wz * o.w, p011 = ux * wy * wz * o.w, p111 = wx * wy * wz * o.w;
-      val += p000 * __ldg(v);
+      float c000, c100, c010, c110, c001, c101, c011, c111;
+      load_corners<PAIRS>(vol, (int)fz * Sz + (int)fy * Sy + (int)fx, Sy, Sz, c000, c100, c010, c110, c001, c101, c011, c111);
+      val += p000 * c000;
       weight += p000;
-      val += p100 * __ldg(v + 1);
+      val += p100 * c100;
       weight += p100;
-      val += p010 * __ldg(v + Sy);
+      val += p010 * c010;
       weight += p010;
-      val += p001 * __ldg(v + Sz);
+      val += p001 * c001;
       weight += p001;
-      val += p110 * __ldg(v + 1 + Sy);
+      val += p110 * c110;
       weight += p110;
-      val += p101 * __ldg(v + 1 + Sz);
+      val += p101 * c101;
       weight += p101;
-      val += p011 * __ldg(v + Sy + Sz);
+      val += p011 * c011;
       weight += p011;
-      val += p111 * __ldg(v + Sy + Sz + 1);
+      val += p111 * c111;
       weight += p111;
     }
 #pragma unroll
@@ -523,28 +559,76 @@ static int check_acq(const char* who, int ntaps, int n, int h, int w, int D, int
   return 0;
 }
 
-extern "C" int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
-                                     float res_slice, void* stream) {
-  if (int rc = check_acq("fsg_slice_acq_forward", ntaps, n, h, w, D, H, W)) return rc;
-  FSG_REQUIRE(transforms && vol && taps && slices, "fsg_slice_acq_forward: NULL pointer");
-  FSG_REQUIRE((reinterpret_cast<uintptr_t>(taps) & 15) == 0, "fsg_slice_acq_forward: taps must be 16-byte aligned");
+static int acq_forward(const char* who, int pairs, const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D,
+                       int H, int W, float res_slice, void* stream) {
+  if (int rc = check_acq(who, ntaps, n, h, w, D, H, W)) return rc;
+  FSG_REQUIRE(transforms && vol && taps && slices, "%s: NULL pointer", who);
+  FSG_REQUIRE((reinterpret_cast<uintptr_t>(taps) & 15) == 0, "%s: taps must be 16-byte aligned", who);
+  FSG_REQUIRE(pairs == 1 || (reinterpret_cast<uintptr_t>(vol) & (4 * pairs - 1)) == 0, "%s: the packed volume must be %d-byte aligned", who, 4 * pairs);
   cudaStream_t s = as_stream(stream);
   cudaMemsetAsync(slices, 0, sizeof(float) * (size_t)n * h * w, s);
   dim3 grid((w + ACQ_TILE - 1) / ACQ_TILE, (h + ACQ_TILE - 1) / ACQ_TILE, n);
+  const dim3 block(ACQ_TILE, ACQ_TILE);
   const size_t smem = sizeof(float4) * ntaps;
+  const float4* taps4 = reinterpret_cast<const float4*>(taps);
   // large PSFs: lanes over taps (coalesced gathers); small ones (the 1-tap mask acquisition): thread per pixel
   static const int warp_min_taps = [] {
     const char* e = getenv("FSG_FWD_WARP_MIN_TAPS");
     return e ? atoi(e) : 400;  // r01: 215 taps 2.5 ms (thread) vs 3.9 ms (warp); 729 taps 12.7 vs 9.3 ms
   }();
+#define FSG_FWD_LAUNCH(KERNEL)                                                                                  \
+  do {                                                                                                          \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    KERNEL<<<grid, block, smem, s>>>(transforms, vol, taps4, ntaps, radius, slices, h, w, D, H, W, res_slice);  \
+  } while (0)
   if (ntaps >= warp_min_taps) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(slice_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    slice_fwd_warp_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, vol, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, h, w, D, H, W, res_slice);
+    if (pairs == 4)
+      FSG_FWD_LAUNCH(slice_fwd_warp_kernel<4>);
+    else if (pairs == 2)
+      FSG_FWD_LAUNCH(slice_fwd_warp_kernel<2>);
+    else
+      FSG_FWD_LAUNCH(slice_fwd_warp_kernel<1>);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(slice_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    slice_fwd_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, vol, reinterpret_cast<const float4*>(taps), ntaps, radius, slices, h, w, D, H, W, res_slice);
+    if (pairs == 4)
+      FSG_FWD_LAUNCH(slice_fwd_kernel<4>);
+    else if (pairs == 2)
+      FSG_FWD_LAUNCH(slice_fwd_kernel<2>);
+    else
+      FSG_FWD_LAUNCH(slice_fwd_kernel<1>);
   }
-  return check_launch("fsg_slice_acq_forward");
+#undef FSG_FWD_LAUNCH
+  return check_launch(who);
+}
+
+extern "C" int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
+                                     float res_slice, void* stream) {
+  return acq_forward("fsg_slice_acq_forward", 1, transforms, vol, taps, ntaps, radius, slices, n, h, w, D, H, W, res_slice, stream);
+}
+
+extern "C" int fsg_slice_acq_forward_xpairs(const float* transforms, const float* vol_pairs, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D,
+                                            int H, int W, float res_slice, void* stream) {
+  return acq_forward("fsg_slice_acq_forward_xpairs", 2, transforms, vol_pairs, taps, ntaps, radius, slices, n, h, w, D, H, W, res_slice, stream);
+}
+
+extern "C" int fsg_slice_acq_forward_xyquads(const float* transforms, const float* vol_quads, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D,
+                                             int H, int W, float res_slice, void* stream) {
+  return acq_forward("fsg_slice_acq_forward_xyquads", 4, transforms, vol_quads, taps, ntaps, radius, slices, n, h, w, D, H, W, res_slice, stream);
+}
+
+extern "C" int fsg_volume_xyquads(const float* vol, float* quads, int64_t nvox, int row_len, void* stream) {
+  FSG_REQUIRE(vol && quads && nvox >= 1 && row_len >= 1, "fsg_volume_xyquads: bad arguments");
+  FSG_REQUIRE((reinterpret_cast<uintptr_t>(quads) & 15) == 0, "fsg_volume_xyquads: quads must be 16-byte aligned");
+  const int64_t want = (nvox + 255) / 256;
+  xyquads_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, as_stream(stream)>>>(vol, reinterpret_cast<float4*>(quads), nvox, row_len);
+  return check_launch("fsg_volume_xyquads");
+}
+
+extern "C" int fsg_volume_xpairs(const float* vol, float* pairs, int64_t nvox, void* stream) {
+  FSG_REQUIRE(vol && pairs && nvox >= 1, "fsg_volume_xpairs: bad arguments");
+  FSG_REQUIRE((reinterpret_cast<uintptr_t>(pairs) & 7) == 0, "fsg_volume_xpairs: pairs must be 8-byte aligned");
+  const int64_t want = (nvox + 255) / 256;
+  xpairs_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, as_stream(stream)>>>(vol, reinterpret_cast<float2*>(pairs), nvox);
+  return check_launch("fsg_volume_xpairs");
 }
 
 extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,

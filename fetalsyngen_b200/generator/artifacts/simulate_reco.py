@@ -53,17 +53,37 @@ def _side_stream(device) -> "torch.cuda.Stream":
     return s
 
 
-def slice_acquisition(mat, vol, psf, slice_shape, res_slice, out=None):
+def volume_xpairs(vol):
+    """(v[i], v[i+1]) per voxel of a (D,H,W) device volume: the gather format of the PSF acquisition
+    (built once per volume; a Scanner acquires 2-6 stacks from it)."""
+    v = vol.contiguous()
+    pairs = torch.empty((v.numel(), 2), dtype=torch.float32, device=v.device)
+    _lib.call("fsg_volume_xpairs", v.data_ptr(), pairs.data_ptr(), v.numel(), _stream())
+    return pairs
+
+
+def volume_xyquads(vol):
+    """(v[i], v[i+1], v[i+W], v[i+W+1]) per voxel: two 16-byte loads per trilinear sample."""
+    v = vol.contiguous()
+    quads = torch.empty((v.numel(), 4), dtype=torch.float32, device=v.device)
+    _lib.call("fsg_volume_xyquads", v.data_ptr(), quads.data_ptr(), v.numel(), int(v.shape[-1]), _stream())
+    return quads
+
+
+def slice_acquisition(mat, vol, psf, slice_shape, res_slice, out=None, pairs=None):
     """``svort.slice_acquisition(mat, vol, None, None, psf, slice_shape, res_slice, False, False)``
-    (slice_acq.py:193-226): mat (n,3,4) host float32, vol (D,H,W) device float32, psf host array."""
+    (slice_acq.py:193-226): mat (n,3,4) host float32, vol (D,H,W) device float32, psf host array.
+    ``pairs``: ``volume_xpairs(vol)`` — same result, half the gather instructions."""
     dev = vol.device
     taps, radius = svort.psf_taps(psf)
     n, (h, w) = mat.shape[0], slice_shape
     D, H, W = (int(s) for s in vol.shape[-3:])
     out = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) if out is None else out
     t_d, taps_d = _dev_f32(mat, dev), _dev_f32(taps, dev)
-    _lib.call("fsg_slice_acq_forward", t_d.data_ptr(), vol.data_ptr(), taps_d.data_ptr(), int(taps.shape[0]), float(radius), out.data_ptr(), n, h, w, D, H, W,
-              float(F32(res_slice)), _stream())
+    name, src = "fsg_slice_acq_forward", vol
+    if pairs is not None:
+        name, src = ("fsg_slice_acq_forward_xyquads" if pairs.shape[-1] == 4 else "fsg_slice_acq_forward_xpairs"), pairs
+    _lib.call(name, t_d.data_ptr(), src.data_ptr(), taps_d.data_ptr(), int(taps.shape[0]), float(radius), out.data_ptr(), n, h, w, D, H, W, float(F32(res_slice)), _stream())
     return out
 
 
@@ -206,6 +226,7 @@ class Scanner:
         num_stacks = np.random.randint(self.min_num_stack, self.max_num_stack + 1)
         rng_seed = int(torch.randint(0, 2**62, (1,)).item())
         sums_d = torch.empty(ns, dtype=torch.float32, device=device)
+        vol_pairs = volume_xyquads(vol)  # 2 x 16-byte gathers per trilinear sample instead of 8 x 4-byte: the acquisition is L1-wavefront bound
         main, side = torch.cuda.current_stream(device), _side_stream(device)
         side.wait_stream(main)  # the mask volume was produced on the main stream
         attempt = 0
@@ -232,7 +253,7 @@ class Scanner:
             nz = np.nonzero(idx)[0]
             idx[nz[0] : nz[-1]] = True
             lo, hi = int(nz[0]), int(nz[-1]) + 1  # the kept slices are one contiguous run
-            slices = slice_acquisition(np.ascontiguousarray(mat[lo:hi]), vol, psf_acq, (ss, ss), res_s / res)
+            slices = slice_acquisition(np.ascontiguousarray(mat[lo:hi]), vol, psf_acq, (ss, ss), res_s / res, pairs=vol_pairs)
             slices_no_psf = slices_no_psf[lo:hi]
             transform_init = svort.reset_transform(transform_init[idx])
             transform_target = transform_target[idx]

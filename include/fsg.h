@@ -296,6 +296,17 @@ int fsg_label_mask(const uint8_t* labels, int match, uint8_t* out, int64_t n, vo
  * slices: [n][h][w].  fsg_slice_acq_adjoint zero-fills its accumulator itself. */
 int fsg_slice_acq_forward(const float* transforms, const float* vol, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H, int W,
                           float res_slice, void* stream);
+/* Acquisition from the x-pair volume: pairs[2 i] = vol[i], pairs[2 i + 1] = vol[i + 1] (built once per
+ * volume by fsg_volume_xpairs; a Scanner acquires 2-6 stacks from the same volume).  Same result as
+ * fsg_slice_acq_forward bit for bit; the two x corners of every trilinear sample arrive in one 8-byte
+ * load, which halves the gather instructions of a kernel bound by L1 wavefronts. */
+int fsg_volume_xpairs(const float* vol, float* pairs, int64_t nvox, void* stream);
+/* ... and from the xy-quad volume (v[i], v[i+1], v[i+row_len], v[i+row_len+1]; row_len = W): two 16-byte loads per sample. */
+int fsg_volume_xyquads(const float* vol, float* quads, int64_t nvox, int row_len, void* stream);
+int fsg_slice_acq_forward_xyquads(const float* transforms, const float* vol_quads, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H,
+                                  int W, float res_slice, void* stream);
+int fsg_slice_acq_forward_xpairs(const float* transforms, const float* vol_pairs, const float* taps, int ntaps, float radius, float* slices, int n, int h, int w, int D, int H,
+                                 int W, float res_slice, void* stream);
 int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,
                           const int32_t* slice_idx, float* vol, float* vol_weight, float* workspace, int n, int h, int w, int D, int H, int W, float res_slice, int equalize,
                           void* stream);

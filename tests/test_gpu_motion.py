@@ -205,3 +205,34 @@ def test_simulate_motion_philox_mode_and_gate():
     diff = (out - img).abs()
     assert float(diff.max()) > 1e-3            # something was degraded ...
     assert float(out.min()) >= -1e-6 and float(out.max()) <= float(img.max()) * 1.5 + 0.5
+
+
+@pytest.mark.parametrize("psf_ratio", [(1.2, 1.2, 5.0), (2.0, 2.0, 7.0)])
+def test_xpairs_acquisition_is_bit_identical(psf_ratio):
+    """fsg_slice_acq_forward_xpairs (two x corners per 8-byte load from the pair volume) must give exactly
+    the slices of fsg_slice_acq_forward, for the thread-per-pixel and the lanes-over-taps kernels."""
+    from fetalsyngen_b200.generator.artifacts import simulate_reco as SR
+    from fetalsyngen_b200.generator.artifacts import svort
+
+    rs = np.random.RandomState(4)
+    vol = torch.from_numpy(rs.rand(40, 44, 48).astype(np.float32)).to("cuda:0")
+    psf = svort.get_PSF(res_ratio=psf_ratio)
+    ax = np.concatenate([rs.randn(9, 3) * 0.5, rs.randn(9, 2) * 3, np.linspace(-15, 15, 9)[:, None]], 1).astype(np.float32)
+    mat = svort.axisangle2mat(ax)
+    a = SR.slice_acquisition(mat, vol, psf, (64, 64), 1.2)
+    b = SR.slice_acquisition(mat, vol, psf, (64, 64), 1.2, pairs=SR.volume_xpairs(vol))
+    assert torch.equal(a, b) and float(a.abs().max()) > 0
+
+
+def test_xyquads_acquisition_is_bit_identical():
+    from fetalsyngen_b200.generator.artifacts import simulate_reco as SR
+    from fetalsyngen_b200.generator.artifacts import svort
+
+    rs = np.random.RandomState(6)
+    vol = torch.from_numpy(rs.rand(40, 44, 48).astype(np.float32)).to("cuda:0")
+    psf = svort.get_PSF(res_ratio=(1.2, 1.2, 5.0))
+    ax = np.concatenate([rs.randn(9, 3) * 0.5, rs.randn(9, 2) * 3, np.linspace(-15, 15, 9)[:, None]], 1).astype(np.float32)
+    mat = svort.axisangle2mat(ax)
+    a = SR.slice_acquisition(mat, vol, psf, (64, 64), 1.2)
+    b = SR.slice_acquisition(mat, vol, psf, (64, 64), 1.2, pairs=SR.volume_xyquads(vol))
+    assert torch.equal(a, b) and float(a.abs().max()) > 0

@@ -188,10 +188,15 @@ def run_motion(args):
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
         empty = torch.empty(0, device=DEV)
         ours_f = timed(lambda: SR.slice_acquisition(mat, vol, psf, (ss, ss), res_s / 0.5), reps=args.reps)
+        pairs = SR.volume_xpairs(vol)
+        ours_fp = timed(lambda: SR.slice_acquisition(mat, vol, psf, (ss, ss), res_s / 0.5, pairs=pairs), reps=args.reps)
+        t_pairs = timed(lambda: SR.volume_xpairs(vol), reps=args.reps)
+        quads = SR.volume_xyquads(vol)
+        ours_fq = timed(lambda: SR.slice_acquisition(mat, vol, psf, (ss, ss), res_s / 0.5, pairs=quads), reps=args.reps)
         sl = SR.slice_acquisition(mats, vol, psf, (ss, ss), res_s / 0.5)
         ours_a = timed(lambda: SR.slice_acquisition_adjoint(mats, psf, sl, (S, S, S), res_s / 0.5), reps=args.reps)
         line = {"config": "motion kernels", "shape": S, "res_slice": res_s, "slice_thickness": thick, "gap": gap, "slice_size": ss, "slices_per_stack": ns, "psf_shape": list(psf.shape),
-                "psf_taps": int((psf != 0).sum()), "forward_ms_ours": ours_f, "adjoint_slices": int(mats.shape[0]), "adjoint_ms_ours": ours_a}
+                "psf_taps": int((psf != 0).sum()), "forward_ms_ours": ours_f, "forward_ms_ours_xpairs": ours_fp, "xpairs_build_ms": t_pairs, "forward_ms_ours_xyquads": ours_fq, "adjoint_slices": int(mats.shape[0]), "adjoint_ms_ours": ours_a}
         if ext is not None:
             tm, tp, tms = t(mat), t(psf), t(mats)
             ref_f = timed(lambda: ext.forward(tm, vol[None, None], empty, empty, tp, [ss, ss], float(res_s / 0.5), False, False), reps=args.reps)
