@@ -28,14 +28,14 @@ class Rng(C.Structure):
 
 class GmmJob(C.Structure):
     _fields_ = [("seed", _vp * 4), ("mus", _vp), ("sigmas", _vp), ("noise", _vp), ("out", _vp), ("labels_out", _vp),
-                ("rng", Rng), ("nlabels", _i32), ("row_len", _i32), ("out_pairs", _vp)]
+                ("rng", Rng), ("nlabels", _i32), ("row_len", _i32), ("out_pairs", _vp), ("pairs_float", _i32), ("_pad", _i32)]
 
 
 class WarpJob(C.Structure):
     _fields_ = [("src_img", _vp), ("src_pairs", _vp), ("src_seg", _vp), ("src_img2", _vp), ("dst_img", _vp), ("dst_seg", _vp), ("dst_img2", _vp),
                 ("fsmall", _vp), ("ftab", _vp * 3), ("bf_low", _vp), ("btab", _vp * 3), ("shift", _vp),
                 ("A", _f32 * 9), ("c2", _f32 * 3), ("center", _f32 * 3), ("gamma", _f32),
-                ("fs", _i32 * 3), ("bs", _i32 * 3), ("mode", _i32), ("flip", _i32), ("has_gamma", _i32), ("_pad", _i32)]
+                ("fs", _i32 * 3), ("bs", _i32 * 3), ("mode", _i32), ("flip", _i32), ("has_gamma", _i32), ("pairs_float", _i32)]
 
 
 class BlurJob(C.Structure):

@@ -77,6 +77,12 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
             nxt = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
           }
         }
+        if (job.pairs_float) {  // lossless float2 pairs: (I[v], I[v+1]) per voxel, two 16-byte stores
+          float4* o2 = reinterpret_cast<float4*>(reinterpret_cast<float2*>(pairs) + v0);
+          o2[0] = make_float4(o.x, o.y, o.y, o.z);
+          o2[1] = make_float4(o.z, o.w, o.w, nxt);
+          continue;
+        }
         // round(I * 128) by the 2^23 magic add (round-to-nearest-even in the FMA); the low 16 bits of the
         // float's mantissa are the fixed-point value (I <= 511.99 after the clamp)
         const float cap = 511.9921875f;

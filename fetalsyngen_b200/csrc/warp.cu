@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
 // PAIRS: the source image is fsg_gmm's out_pairs volume — 16-bit fixed point (I[z] | I[z+1] << 16), so
 // ONE 32-bit gather brings both z corners of an (x, y) row: four gather instructions per voxel instead
 // of eight (the kernel is bound by L1 wavefronts per gather, not by bytes).
-template <bool EPI, bool PAIRS>
+template <bool EPI, int PAIRS>
 __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
   const fsg_warp_job& job = batch.j[blockIdx.z];
   const int tid = threadIdx.x;
@@ -432,12 +432,13 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
   const float shx = job.shift[0], shy = job.shift[1], shz = job.shift[2];
   const float gam = (EPI && job.has_gamma) ? job.gamma : 1.0f;
   // lg2(300) (1 - gamma); the fixed-point scale 2^-7 of the pairs format folds in as -7 gamma
-  const float c0 = ((EPI && job.has_gamma) ? 8.22881869049588f * (1.0f - job.gamma) : 0.f) - (PAIRS ? 7.0f * gam : 0.f);
+  const float c0 = ((EPI && job.has_gamma) ? 8.22881869049588f * (1.0f - job.gamma) : 0.f) - (PAIRS == 1 ? 7.0f * gam : 0.f);
 
   const P2 cen2 = pk(cen_x, cen_x), sh2x = pk(shx, shx), sh2y = pk(shy, shy), sh2z = pk(shz, shz), magic2 = pk(MAGIC, MAGIC);
   const P2 c2x = pk(aff.c[0], aff.c[0]), c2y = pk(aff.c[1], aff.c[1]), c2z = pk(aff.c[2], aff.c[2]);
   const char* const img_b = reinterpret_cast<const char*>(src_img);
-  const ptrdiff_t by_row = (ptrdiff_t)sz * 4, by_plane = (ptrdiff_t)xs * 4;
+  constexpr int ESZ = PAIRS == 2 ? 8 : 4;  // bytes per source voxel (float2 pairs: 8)
+  const ptrdiff_t by_row = (ptrdiff_t)sz * ESZ, by_plane = (ptrdiff_t)xs * ESZ;
 
   for (int k = tid; k < sz; k += WARP_THREADS) {
     const Tab tf = load_tab(job.ftab[2], k);
@@ -486,16 +487,29 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
         const unsigned ba = (unsigned)__float_as_int(txa) * (unsigned)xs + (unsigned)__float_as_int(tya) * (unsigned)sz + (unsigned)__float_as_int(tza) + kbias;
         const unsigned bb = (unsigned)__float_as_int(txb) * (unsigned)xs + (unsigned)__float_as_int(tyb) * (unsigned)sz + (unsigned)__float_as_int(tzb) + kbias;
         const P2 wx2 = sub2(ii, sub2(tx2, magic2)), wy2 = sub2(jj, sub2(ty2, magic2)), wz2 = sub2(kk, sub2(tz2, magic2));
-        const char* a00 = img_b + (size_t)ba * 4;
+        const char* a00 = img_b + (size_t)ba * ESZ;
         const char* a01 = a00 + by_row;
         const char* a10 = a00 + by_plane;
         const char* a11 = a10 + by_row;
-        const char* b00 = img_b + (size_t)bb * 4;
+        const char* b00 = img_b + (size_t)bb * ESZ;
         const char* b01 = b00 + by_row;
         const char* b10 = b00 + by_plane;
         const char* b11 = b10 + by_row;
         P2 c000, c001, c010, c011, c100, c101, c110, c111;
-        if (PAIRS) {
+        if (PAIRS == 2) {  // float2 (I[z], I[z+1]): both z corners of a row in one 8-byte gather, exact
+#define LD2(p) __ldg(reinterpret_cast<const float2*>(p))
+          const float2 qa00 = LD2(a00), qa01 = LD2(a01), qa10 = LD2(a10), qa11 = LD2(a11);
+          const float2 qb00 = LD2(b00), qb01 = LD2(b01), qb10 = LD2(b10), qb11 = LD2(b11);
+#undef LD2
+          c000 = pk(qa00.x, qb00.x);
+          c001 = pk(qa00.y, qb00.y);
+          c010 = pk(qa01.x, qb01.x);
+          c011 = pk(qa01.y, qb01.y);
+          c100 = pk(qa10.x, qb10.x);
+          c101 = pk(qa10.y, qb10.y);
+          c110 = pk(qa11.x, qb11.x);
+          c111 = pk(qa11.y, qb11.y);
+        } else if (PAIRS == 1) {
 #define LDU(p) __ldg(reinterpret_cast<const unsigned*>(p))
           const unsigned ua00 = LDU(a00), ua01 = LDU(a01), ua10 = LDU(a10), ua11 = LDU(a11);
           const unsigned ub00 = LDU(b00), ub01 = LDU(b01), ub10 = LDU(b10), ub11 = LDU(b11);
@@ -540,7 +554,7 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
         upk(fma2(wz2, sub2(c1_, c0_), c0_), va, vb);
         va = fminf(fminf(iia, jja), kka) > 0.f ? va : 0.f;
         vb = fminf(fminf(iib, jjb), kkb) > 0.f ? vb : 0.f;
-        if (PAIRS && !EPI) {
+        if (PAIRS == 1 && !EPI) {
           va *= 0.0078125f;
           vb *= 0.0078125f;
         }
@@ -641,18 +655,18 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
   // partition the batch: fast kernel with / without epilogue, generic kernel for everything else
   // groups: 0/1 = fast kernel on a float source with / without epilogue, 2 = generic, 3/4 = fast kernel on
   // the fixed-point pairs source with / without epilogue
-  fsg_warp_job part[5][FSG_MAX_JOBS];
-  int cnt[5] = {0, 0, 0, 0, 0};
+  fsg_warp_job part[7][FSG_MAX_JOBS];  // 5/6: fast kernel on the float2 pairs source with / without epilogue
+  int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int n = 0; n < njobs; ++n) {
     const fsg_warp_job& j = jobs[n];
     const bool fast = fast_eligible(j, sx, sy, sz);
-    FSG_REQUIRE(!j.src_pairs || (fast && (reinterpret_cast<uintptr_t>(j.src_pairs) & 3) == 0), "fsg_warp: job %d: src_pairs is only read by the fast path", n);
-    const int g = !fast ? 2 : ((j.src_pairs ? 3 : 0) + ((j.has_gamma || j.bf_low) ? 0 : 1));
+    FSG_REQUIRE(!j.src_pairs || (fast && (reinterpret_cast<uintptr_t>(j.src_pairs) & (j.pairs_float ? 7 : 3)) == 0), "fsg_warp: job %d: src_pairs is only read by the fast path", n);
+    const int g = !fast ? 2 : ((j.src_pairs ? (j.pairs_float ? 5 : 3) : 0) + ((j.has_gamma || j.bf_low) ? 0 : 1));
     part[g][cnt[g]++] = j;
   }
   cudaStream_t s = as_stream(stream);
   Batch<fsg_warp_job> b;
-  for (int g = 0; g < 5; ++g) {
+  for (int g = 0; g < 7; ++g) {
     if (!cnt[g] || g == 2) continue;
     // FSG_WARP_TILE=1 selects the TMA-staged cubic-tile variant (warp_tile.cu).  It is parity-green
     // but measured 2.4x slower than the full-z kernel at 256^3 (r01e: 2.17 ms vs 0.90 ms per 8
@@ -671,13 +685,17 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
     const dim3 grid((sy / WY) * (sx / WX), 1, cnt[g]);
     const size_t smem = field_smem(part[g], cnt[g]);
     if (g == 0)
-      warp_fast_kernel<true, false><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+      warp_fast_kernel<true, 0><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
     else if (g == 1)
-      warp_fast_kernel<false, false><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+      warp_fast_kernel<false, 0><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
     else if (g == 3)
-      warp_fast_kernel<true, true><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+      warp_fast_kernel<true, 1><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else if (g == 4)
+      warp_fast_kernel<false, 1><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else if (g == 5)
+      warp_fast_kernel<true, 2><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
     else
-      warp_fast_kernel<false, true><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+      warp_fast_kernel<false, 2><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
   }
   if (cnt[2]) {
     if (int rc = fill_batch(b, part[2], cnt[2])) return rc;

@@ -20,7 +20,10 @@ STAGE_GMM, STAGE_NOISE, STAGE_FIELD, STAGE_BIAS = 1, 2, 3, 4
 # FSG_GMM_PAIRS=1: hand the GMM image to the warp fast path as 16-bit fixed-point z-pairs (one 32-bit gather
 # per (x, y) row instead of two).  Measured r01h: warp 0.94 -> 0.79 ms, GMM 0.22 -> 0.29 ms per 8 volumes (net
 # -4 % of the step) for a float error of ~1.5e-5 of the range instead of 3e-7: not worth it by default.
-_PAIRS = __import__("os").environ.get("FSG_GMM_PAIRS", "0") == "1"
+# FSG_GMM_PAIRS=2: float2 z-pairs (I[z], I[z+1]) — lossless (results identical to the plain path), one 8-byte
+# gather per row in the warp; the GMM kernel writes 8 instead of 4 bytes per voxel.
+_PAIRS_MODE = int(__import__("os").environ.get("FSG_GMM_PAIRS", "0") or 0)
+_PAIRS = _PAIRS_MODE in (1, 2)
 
 
 @dataclass
@@ -192,6 +195,7 @@ class SynthEngine:
         sample b is written in the fixed-point pairs format of the warp fast path (same 4 bytes per
         voxel, into the same buffer) instead of float32."""
         B = len(plans)
+        nvox = int(out.shape[-1]) if torch.is_tensor(out) else self.nvox  # a list mixes [N] outputs and [2N] float-pair outputs
         small = self.upload([p.mus for p in plans] + [p.sigmas for p in plans])
         jobs = (_lib.GmmJob * B)()
         for b, p in enumerate(plans):
@@ -200,7 +204,7 @@ class SynthEngine:
             if not 1 <= len(vols) <= 4:
                 raise ValueError("each sample needs 1..4 seed volumes")
             for m, v in enumerate(vols):
-                if v.dtype not in (torch.int8, torch.uint8) or v.numel() != out.shape[-1]:
+                if v.dtype not in (torch.int8, torch.uint8) or v.numel() != nvox:
                     raise TypeError("seed volumes must be int8/uint8 tensors with one label per output voxel")
                 _check(v, v.dtype, self.device, "seed volume")
                 j.seed[m] = v.data_ptr()
@@ -209,11 +213,12 @@ class SynthEngine:
             j.noise = _ptr(None if p.gmm_noise is None else _check(p.gmm_noise, torch.float32, self.device, "gmm_noise"))
             if pairs is not None and pairs[b]:
                 j.out, j.out_pairs, j.row_len = None, out[b].data_ptr(), int(self.shape[2])
+                j.pairs_float = 1 if _PAIRS_MODE == 2 else 0
             else:
                 j.out = out[b].data_ptr()
             j.labels_out = None if labels_out is None else labels_out[b].data_ptr()
             j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_GMM, 0)
-        self._call("fsg_gmm", jobs, B, int(out.shape[-1]))
+        self._call("fsg_gmm", jobs, B, nvox)
         self._keep = (small,)
 
     # ------------------------------------------------------------------ K2
@@ -258,6 +263,7 @@ class SynthEngine:
             j.src_img, j.dst_img = _ptr(None if src_img is None else src_img[b]), _ptr(None if dst_img is None else dst_img[b])
             if pairs is not None and pairs[b]:
                 j.src_img, j.src_pairs = None, _ptr(src_img[b])
+                j.pairs_float = 1 if _PAIRS_MODE == 2 else 0
             j.src_seg, j.dst_seg = _ptr(None if src_seg is None else src_seg[b]), _ptr(None if dst_seg is None else dst_seg[b])
             j.src_img2, j.dst_img2 = _ptr(None if src_img2 is None else src_img2[b]), _ptr(None if dst_img2 is None else dst_img2[b])
             j.mode, j.flip = int(bool(p.deform)), int(bool(p.flip))
@@ -522,12 +528,16 @@ class SynthEngine:
     def _run_base(self, plans, seeds, segs, out_img, out_seg, scale, buf0, buf1, buf2):
         B = len(plans)
         pairs = [self.pairs_eligible(p) for p in plans]
-        self.gmm(plans, seeds, buf0, pairs=pairs)
+        gmm_out = buf0
+        if _PAIRS_MODE == 2 and any(pairs):  # float2 pairs need 8 bytes per voxel: their own scratch volume
+            wide = self.scratch("gmm_fpairs", B, torch.float32, 2 * self.nvox)
+            gmm_out = [wide[b] if pairs[b] else buf0[b] for b in range(B)]
+        self.gmm(plans, seeds, gmm_out, pairs=pairs)
         rs = [b for b, p in enumerate(plans) if p.spacing is not None]
         no_rs = [b for b, p in enumerate(plans) if p.spacing is None]
         # warp straight into the output for samples that skip the resolution simulation
         warp_dst = [out_img[b].view(-1) if (plans[b].spacing is None and plans[b].noise_std is None) else buf1[b] for b in range(B)]
-        self.warp(plans, buf0, segs, warp_dst, out_seg, pairs=pairs)
+        self.warp(plans, gmm_out, segs, warp_dst, out_seg, pairs=pairs)
         if rs:
             sub = [plans[b] for b in rs]
             # x pass -> buf2, y pass -> buf0 (the GMM image is dead), z pass (+noise) -> buf2

@@ -65,6 +65,9 @@ typedef struct fsg_gmm_job {
   uint32_t* out_pairs;   /* optional [nvox]: 16.7 fixed point pairs (I[v] | I[v+1] << 16), I * 128 rounded;
                           * the gather format of fsg_warp's fast path (one 32-bit load brings both z corners;
                           * quantisation <= 1/256 intensity unit, ~1e-5 of the intensity range) */
+  int32_t pairs_float;   /* != 0: out_pairs is a float2 volume [nvox][2] = (I[v], I[v+1]) instead — lossless,
+                          * one 8-byte gather per (x, y) row in fsg_warp; twice the bytes written here */
+  int32_t _pad;
 } fsg_gmm_job;
 int fsg_gmm(const fsg_gmm_job* jobs_host, int njobs, int64_t nvox, void* stream);
 
@@ -97,7 +100,7 @@ typedef struct fsg_warp_job {
   int32_t mode;
   int32_t flip;
   int32_t has_gamma;
-  int32_t _pad;
+  int32_t pairs_float;    /* src_pairs holds fsg_gmm's float2 pairs (pairs_float there) instead of fixed point */
 } fsg_warp_job;
 /* Pre-pass: writes floor(min over the volume of the clamped coordinate) per axis into
  * job.shift (affine_nonrigid.py:350-358).  No volume traffic; coordinates are recomputed. */

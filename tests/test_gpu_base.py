@@ -384,6 +384,43 @@ def test_fixed_point_pairs_handover_stays_within_tolerance():
     assert len(errs) == 2 and max(errs) <= TOL, errs
 
 
+def test_float_pairs_handover_is_bit_identical():
+    """FSG_GMM_PAIRS=2: the GMM -> warp hand-over as float2 z-pairs (I[z], I[z+1]) is lossless — image and
+    segmentation equal the plain path bit for bit (Philox noise and injected noise, with and without the
+    gamma / bias epilogue), and the reference goldens still hold."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path[:0]=['.','oracle','tests']\n"
+        "import numpy as np, torch\n"
+        "from golden_util import load_case\n"
+        "from gpu_util import plan_from_golden, seeds_from_golden, engine_from_golden, rel_err\n"
+        "import fetalsyngen_b200.engine as E\n"
+        "for name in ('c64_default','c32_all','c32_affine_only'):\n"
+        "    d=load_case(name); eng=engine_from_golden(d)\n"
+        "    seg=torch.from_numpy(d['seg_in']).cuda().contiguous().view(-1)\n"
+        "    outs=[]\n"
+        "    for mode in (2, 0):\n"
+        "        E._PAIRS_MODE, E._PAIRS = mode, mode in (1, 2)\n"
+        "        for philox in (False, True):\n"
+        "            plan=plan_from_golden(d)\n"
+        "            if philox: plan.gmm_noise=None; plan.noise=None; plan.rng_seed=5; plan.sample_id=9\n"
+        "            img,sg=eng.run_base([plan],[seeds_from_golden(d)],[seg],scale=False)\n"
+        "            outs.append((img[0].clone(), sg[0].clone()))\n"
+        "    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1]), name\n"
+        "    assert torch.equal(outs[1][0], outs[3][0]) and torch.equal(outs[1][1], outs[3][1]), name\n"
+        "    assert np.array_equal(outs[0][1].cpu().numpy(), d['seg_out'])\n"
+        "    print('ERR', rel_err(outs[0][0], d['final']), eng.pairs_eligible(plan_from_golden(d)))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, FSG_GMM_PAIRS="2"))
+    assert res.returncode == 0, res.stderr[-1500:]
+    errs = [float(l.split()[1]) for l in res.stdout.splitlines() if l.startswith("ERR")]
+    assert len(errs) == 3 and max(errs) <= TOL, errs
+
+
 @pytest.mark.parametrize("shape,seed", [((64, 64, 64), 7), ((40, 52, 36), 8)])
 def test_second_image_channel_vs_oracle(shape, seed):
     """load_image=True (datasets.py:279-306, affine_nonrigid.py:190-191): the real image rides through the
