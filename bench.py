@@ -414,6 +414,35 @@ def run_ours(args, shape):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(t.item())
 
+    # ---- same leg with the inputs in the bit-packed subject-cache format (FetalSynthDataset(packed_cache=...)):
+    # uint8 segmentation + one uint16 word per voxel for all six sub-class counts instead of four int8 seed
+    # volumes; the sub-class counts are drawn per sample and the label volume is unpacked on the device
+    e2e_bytes = (hp.h2d_bytes * micro, hp.d2h_bytes * micro)
+    e2e_packed = None
+    if e2e_steps and not args.no_packed_e2e:
+        from fetalsyngen_b200.data.packed import pack_seed_volumes
+
+        del hp
+        torch.cuda.empty_cache()
+        per_count = {}
+        for n in range(1, 7):
+            _, sv = label_phantom(shape, n_sub=(n, n, n, n), seed=n)
+            per_count[n] = {m + 1: sv[m] for m in range(4)}
+        words, counts = pack_seed_volumes(per_count)
+        del per_count
+        hp = HostPipeline(gen, mb, depth=args.depth + 1, packed_counts=counts)
+        hp.set_inputs_packed([seg_h] * mb, [words] * mb)
+        hp.run((args.depth + 1) * micro, on_result=consume)
+        barrier()
+        t0 = time.perf_counter()
+        hp.run(e2e_steps * micro, on_result=consume)
+        barrier()
+        t = torch.tensor([max(time.perf_counter() - t0, 1e-9)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_packed = {"value": world * B * e2e_steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes * micro, "d2h_bytes_per_step": hp.d2h_bytes * micro,
+                      "inputs": "uint8 segmentation + uint16 bit-packed seed words per voxel (subject-cache format), sub-class counts drawn per sample"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -443,7 +472,8 @@ def run_ours(args, shape):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[1]: batch of {B} volumes/GPU/step, {shape[0]}^3 @0.5mm phantom, deformation+GMM+gamma+bias+blur+resample+noise, all stage probs=1, Philox noise, ScaleIntensity fused", "shape": list(shape), "batch_per_gpu": B, "l2": f"inputs larger than L2 ({B * nvox * 4 / 2**20:.0f} MiB per buffer per step)", "host_affinity": numa},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes * micro, "d2h_bytes_per_step": hp.d2h_bytes * micro, "micro_batches_per_step": micro},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1], "micro_batches_per_step": micro},
+        "e2e_packed_inputs": e2e_packed,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "per_call_ms": {k: round(v[1] / v[0], 4) for k, v in per_call.items()}},
@@ -466,6 +496,7 @@ def main():
     ap.add_argument("--depth", type=int, default=2, help="buffer slots of the host pipeline (e2e leg); 2 slots = 2.5 GiB of pinned host memory per rank at 256^3 / batch 8")
     ap.add_argument("--micro", type=int, default=4, help="micro-batches per step in the e2e leg (pipeline granularity)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-packed-e2e", action="store_true", help="skip the additional host-buffer leg with bit-packed seed inputs")
     args = ap.parse_args()
     shape = (args.shape,) * 3
     if args.impl == "reference":

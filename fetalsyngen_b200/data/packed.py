@@ -117,6 +117,23 @@ class PackedSeeds:
         if device is not None:
             self.on(device)
 
+    @classmethod
+    def from_device(cls, words: torch.Tensor, counts) -> "PackedSeeds":
+        """Wrap packed words that already live on a device (int16 / int32 tensor holding the uint16 / uint32
+        bit patterns), e.g. a slot of the host pipeline that has just been uploaded."""
+        if words.dtype not in (torch.int16, torch.int32) or words.device.type != "cuda":
+            raise ValueError("from_device expects an int16 / int32 CUDA tensor")
+        self = cls.__new__(cls)
+        self.counts = [int(c) for c in counts]
+        self.layout = field_layout(self.counts)
+        self.word_bytes = words.element_size()
+        if np.dtype(word_dtype(self.layout)).itemsize != self.word_bytes:
+            raise ValueError(f"{8 * self.word_bytes}-bit words do not match the layout of counts {self.counts}")
+        self.shape = tuple(words.shape)
+        self._host = None
+        self._dev = {str(words.device): words}
+        return self
+
     def on(self, device) -> torch.Tensor:
         key = str(torch.device(device))
         t = self._dev.get(key)

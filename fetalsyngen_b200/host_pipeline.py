@@ -19,14 +19,17 @@ import torch
 
 
 class _Slot:
-    def __init__(self, batch, shape, dev):
+    def __init__(self, batch, shape, dev, word_dtype=None):
         shp = (batch, *shape)
         self.h_seg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
-        self.h_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, pin_memory=True)
+        if word_dtype is None:
+            self.h_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, pin_memory=True)
+        else:  # bit-packed seed words of the subject cache (data/packed.py): one word per voxel instead of 4 bytes
+            self.h_seeds = torch.empty(shp, dtype=word_dtype, pin_memory=True)
         self.h_img = torch.empty(shp, dtype=torch.float32, pin_memory=True)
         self.h_oseg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
         self.d_seg = torch.empty(shp, dtype=torch.uint8, device=dev)
-        self.d_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, device=dev)
+        self.d_seeds = torch.empty(self.h_seeds.shape, dtype=self.h_seeds.dtype, device=dev)
         self.d_img = torch.empty(shp, dtype=torch.float32, device=dev)
         self.d_oseg = torch.empty(shp, dtype=torch.uint8, device=dev)
         self.in_free = None    # compute of the previous use has consumed d_seg / d_seeds
@@ -39,16 +42,25 @@ class HostPipeline:
     N / batch micro-steps (``run(steps * N // batch)``): the pipeline then fills and drains in units of
     ``batch`` volumes instead of N, which matters when only a few steps are timed."""
 
-    def __init__(self, generator, batch: int, depth: int = 2):
+    def __init__(self, generator, batch: int, depth: int = 2, packed_counts=None):
+        """``packed_counts``: the inputs are bit-packed seed words (the ``FetalSynthDataset(packed_cache=...)``
+        format, sub-class counts ``packed_counts``) instead of four int8 seed volumes per sample; the
+        sub-class counts are then drawn per sample and the label volume is unpacked on the device."""
         self.gen = generator
         self.B = batch
         self.shape = tuple(generator.shape)
         self.eng = generator.engine(self.shape)
         dev = self.eng.device
-        self.slots = [_Slot(batch, self.shape, dev) for _ in range(max(1, depth))]
+        self.packed_counts = None if packed_counts is None else [int(c) for c in packed_counts]
+        wdt = None
+        if self.packed_counts is not None:
+            from .data.packed import field_layout, word_dtype
+
+            wdt = torch.int16 if np.dtype(word_dtype(field_layout(self.packed_counts))).itemsize == 2 else torch.int32
+        self.slots = [_Slot(batch, self.shape, dev, wdt) for _ in range(max(1, depth))]
         self.s_in = torch.cuda.Stream(device=dev)
         self.s_out = torch.cuda.Stream(device=dev)
-        self.h2d_bytes = self.slots[0].h_seg.numel() + self.slots[0].h_seeds.numel()
+        self.h2d_bytes = self.slots[0].h_seg.numel() + self.slots[0].h_seeds.numel() * self.slots[0].h_seeds.element_size()
         self.d2h_bytes = self.slots[0].h_img.numel() * 4 + self.slots[0].h_oseg.numel()
         self._next = 0
         self._inflight: deque = deque()
@@ -68,6 +80,16 @@ class HostPipeline:
                 for m in range(4):
                     s.h_seeds[b, m].copy_(torch.from_numpy(np.ascontiguousarray(seeds[b][m])))
 
+    def set_inputs_packed(self, segs, words):
+        """Copy the same host volumes into every slot: uint8 segmentations and packed seed words (uint16 / uint32)."""
+        if self.packed_counts is None:
+            raise RuntimeError("HostPipeline was built for int8 seed volumes")
+        for s in self.slots:
+            for b in range(self.B):
+                s.h_seg[b].copy_(torch.from_numpy(np.ascontiguousarray(segs[b])))
+                w = np.ascontiguousarray(words[b])
+                s.h_seeds[b].copy_(torch.from_numpy(w.view(np.int16 if w.dtype.itemsize == 2 else np.int32)))
+
     # ------------------------------------------------------------------ pipeline
     def submit(self, scale: bool = True, **kw):
         """Enqueue H2D -> generate -> D2H for the next slot; returns immediately."""
@@ -86,8 +108,13 @@ class HostPipeline:
         cur.wait_event(loaded)
         if s.out_done is not None:
             cur.wait_event(s.out_done)  # d_img / d_oseg of this slot are being read by the last D2H
-        _, _, s.params = self.gen.sample_batch([s.d_seg[b] for b in range(self.B)], [[s.d_seeds[b, m] for m in range(4)] for b in range(self.B)], scale=scale,
-                                               out_img=s.d_img, out_seg=s.d_oseg, **kw)
+        if self.packed_counts is None:
+            seeds = [[s.d_seeds[b, m] for m in range(4)] for b in range(self.B)]
+        else:
+            from .data.packed import PackedSeeds
+
+            seeds = [PackedSeeds.from_device(s.d_seeds[b], self.packed_counts) for b in range(self.B)]
+        _, _, s.params = self.gen.sample_batch([s.d_seg[b] for b in range(self.B)], seeds, scale=scale, out_img=s.d_img, out_seg=s.d_oseg, **kw)
         s.in_free = torch.cuda.Event()
         s.in_free.record(cur)
         with torch.cuda.stream(self.s_out):

@@ -139,6 +139,45 @@ def test_host_pipeline_matches_device_path_and_keeps_order():
     assert hp.h2d_bytes == B * 5 * 64**3 and hp.d2h_bytes == B * 5 * 64**3
 
 
+def test_host_pipeline_with_packed_seed_inputs_matches_device_path():
+    """HostPipeline(packed_counts=...): the host inputs are the bit-packed seed words of the subject cache
+    (3 bytes per voxel in instead of 5); results equal `sample_batch` on PackedSeeds for the same sample ids."""
+    from fetalsyngen_b200.data.packed import PackedSeeds, pack_seed_volumes
+    from fetalsyngen_b200.host_pipeline import HostPipeline
+
+    shape = (64, 64, 64)
+    gen = _gen(shape)
+    gen.intensity_generator.min_subclusters, gen.intensity_generator.max_subclusters = 1, 4
+    per = {}
+    seg_h = None
+    for n in range(1, 5):
+        seg_h, sv = label_phantom(shape, n_sub=(n, n, n, n), seed=n)
+        per[n] = {m + 1: sv[m] for m in range(4)}
+    words, counts = pack_seed_volumes(per)
+    B = 2
+    hp = HostPipeline(gen, B, depth=2, packed_counts=counts)
+    hp.set_inputs_packed([seg_h] * B, [words] * B)
+    assert hp.h2d_bytes == B * 3 * 64**3 and hp.d2h_bytes == B * 5 * 64**3
+    got = []
+    for it in range(3):
+        hp.submit(sample_ids=[2 * it, 2 * it + 1], base_seed=9)
+        img, seg, params = hp.collect()
+        got.append((img.clone(), seg.clone(), params))
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    ps = PackedSeeds(words, counts, DEV)
+    drawn = set()
+    for it in range(3):
+        img, seg, params = gen.sample_batch([seg_d] * B, [ps] * B, scale=True, sample_ids=[2 * it, 2 * it + 1], base_seed=9)
+        assert torch.equal(img.cpu(), got[it][0]) and torch.equal(seg.cpu(), got[it][1])
+        for b in range(B):
+            m2s = params[b]["selected_seeds"]["mlabel2subclusters"]
+            assert m2s == got[it][2][b]["selected_seeds"]["mlabel2subclusters"]
+            drawn |= set(m2s.values())
+    assert drawn <= {1, 2, 3, 4} and len(drawn) >= 2
+    with pytest.raises(RuntimeError):
+        HostPipeline(gen, B, depth=1).set_inputs_packed([seg_h] * B, [words] * B)
+
+
 def test_full_sample_with_all_artifacts_runs_at_96():
     shape = (96, 96, 96)
     gen = _gen(shape, artifacts=bench.default_artifacts(1.0))
