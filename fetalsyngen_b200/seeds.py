@@ -18,7 +18,6 @@ script's functions and flags, with the file layout the generator's dataset expec
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 from pathlib import Path
 
 import numpy as np
