@@ -136,9 +136,13 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const flo
       lean_accumulate(wx, wy, wz, q.w, c000, c100, c010, c110, c001, c101, c011, c111, val, weight);
       continue;
     }
+    // the eight weights share their (y, z, PSF) factors: 14 multiplies instead of 24 (the kernel is issue-bound
+    // once the gathers are packed); the reference multiplies left to right, this is its value to float rounding
     const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
-    const float p000 = ux * uy * uz * q.w, p100 = wx * uy * uz * q.w, p010 = ux * wy * uz * q.w, p001 = ux * uy * wz * q.w;
-    const float p110 = wx * wy * uz * q.w, p101 = wx * uy * wz * q.w, p011 = ux * wy * wz * q.w, p111 = wx * wy * wz * q.w;
+    const float uzq = uz * q.w, wzq = wz * q.w;
+    const float t00 = uy * uzq, t10 = wy * uzq, t01 = uy * wzq, t11 = wy * wzq;
+    const float p000 = ux * t00, p100 = wx * t00, p010 = ux * t10, p001 = ux * t01;
+    const float p110 = wx * t10, p101 = wx * t01, p011 = ux * t11, p111 = wx * t11;
     val += p000 * c000;
     weight += p000;
     val += p100 * c100;
@@ -211,8 +215,10 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_warp_kernel(cons
         continue;
       }
       const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
-      const float p000 = ux * uy * uz * o.w, p100 = wx * uy * uz * o.w, p010 = ux * wy * uz * o.w, p001 = ux * uy * wz * o.w;
-      const float p110 = wx * wy * uz * o.w, p101 = wx * uy * wz * o.w, p011 = ux * wy * wz * o.w, p111 = wx * wy * wz * o.w;
+      const float uzq = uz * o.w, wzq = wz * o.w;
+      const float t00 = uy * uzq, t10 = wy * uzq, t01 = uy * wzq, t11 = wy * wzq;
+      const float p000 = ux * t00, p100 = wx * t00, p010 = ux * t10, p001 = ux * t01;
+      const float p110 = wx * t10, p101 = wx * t01, p011 = ux * t11, p111 = wx * t11;
       val += p000 * c000;
       weight += p000;
       val += p100 * c100;
