@@ -143,22 +143,16 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_kernel(const flo
     const float t00 = uy * uzq, t10 = wy * uzq, t01 = uy * wzq, t11 = wy * wzq;
     const float p000 = ux * t00, p100 = wx * t00, p010 = ux * t10, p001 = ux * t01;
     const float p110 = wx * t10, p101 = wx * t01, p011 = ux * t11, p111 = wx * t11;
-    val += p000 * c000;
-    weight += p000;
-    val += p100 * c100;
-    weight += p100;
-    val += p010 * c010;
-    weight += p010;
-    val += p001 * c001;
-    weight += p001;
-    val += p110 * c110;
-    weight += p110;
-    val += p101 * c101;
-    weight += p101;
-    val += p011 * c011;
-    weight += p011;
-    val += p111 * c111;
-    weight += p111;
+    // contracted multiply-adds like the reference's own build; the eight weights of a tap sum to its PSF value
+    val = __fmaf_rn(p000, c000, val);
+    val = __fmaf_rn(p100, c100, val);
+    val = __fmaf_rn(p010, c010, val);
+    val = __fmaf_rn(p001, c001, val);
+    val = __fmaf_rn(p110, c110, val);
+    val = __fmaf_rn(p101, c101, val);
+    val = __fmaf_rn(p011, c011, val);
+    val = __fmaf_rn(p111, c111, val);
+    weight += q.w;
   }
   if (weight > 0.f) slices[((size_t)in * h + iy) * w + ix] = __fdiv_rn(val, weight);  // one per pixel: keep the IEEE divide
 }
@@ -219,22 +213,16 @@ __global__ void __launch_bounds__(ACQ_TILE* ACQ_TILE) slice_fwd_warp_kernel(cons
       const float t00 = uy * uzq, t10 = wy * uzq, t01 = uy * wzq, t11 = wy * wzq;
       const float p000 = ux * t00, p100 = wx * t00, p010 = ux * t10, p001 = ux * t01;
       const float p110 = wx * t10, p101 = wx * t01, p011 = ux * t11, p111 = wx * t11;
-      val += p000 * c000;
-      weight += p000;
-      val += p100 * c100;
-      weight += p100;
-      val += p010 * c010;
-      weight += p010;
-      val += p001 * c001;
-      weight += p001;
-      val += p110 * c110;
-      weight += p110;
-      val += p101 * c101;
-      weight += p101;
-      val += p011 * c011;
-      weight += p011;
-      val += p111 * c111;
-      weight += p111;
+      // contracted multiply-adds like the reference's own build; the eight weights of a tap sum to its PSF value
+      val = __fmaf_rn(p000, c000, val);
+      val = __fmaf_rn(p100, c100, val);
+      val = __fmaf_rn(p010, c010, val);
+      val = __fmaf_rn(p001, c001, val);
+      val = __fmaf_rn(p110, c110, val);
+      val = __fmaf_rn(p101, c101, val);
+      val = __fmaf_rn(p011, c011, val);
+      val = __fmaf_rn(p111, c111, val);
+      weight += o.w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
