@@ -22,6 +22,18 @@ int check_launch(const char* what);
     }                                     \
   } while (0)
 
+// A/B switches of DESIGN.md section 4, read from the environment ONCE when the library is loaded (core.cu);
+// launch wrappers only look at this struct.
+struct Config {
+  bool warp_tile;         // FSG_WARP_TILE=1: TMA-staged tile kernel for the warp
+  int fwd_warp_min_taps;  // FSG_FWD_WARP_MIN_TAPS: PSF size from which the acquisition splits taps over lanes
+  bool fwd_lean;          // FSG_FWD_LEAN=1: nested-lerp accumulation in the acquisition
+  bool adj_lean;          // FSG_ADJ_LEAN=0: reference operation order in the PSF reconstruction
+  bool adj_thread;        // FSG_ADJ_THREAD=1: thread-per-pixel PSF reconstruction
+  int tile_debug;         // FSG_TILE_DEBUG
+};
+const Config& config();
+
 // Jobs travel by value in the kernel parameter space (<= 32 KB on sm_70+ with CUDA 12.1+).
 template <typename Job>
 struct Batch {

@@ -1,11 +1,36 @@
 // libfsg core: error plumbing, ABI introspection, dtype plumbing, min/max + ScaleIntensity.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace fsg {
 
 static thread_local char g_err[512] = "";
+
+static Config read_config() {
+  auto flag = [](const char* name, bool dflt) {
+    const char* e = getenv(name);
+    return e ? e[0] == '1' : dflt;
+  };
+  auto num = [](const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+  };
+  Config c;
+  c.warp_tile = flag("FSG_WARP_TILE", false);
+  // r01: 215 taps 2.5 ms (thread) vs 3.9 ms (warp); 729 taps 12.7 vs 9.3 ms
+  c.fwd_warp_min_taps = num("FSG_FWD_WARP_MIN_TAPS", 400);
+  // opt-in: measured with the xy-quad volume 1.59 vs 1.27 ms (215 taps), 4.46 vs 4.62 ms (729 taps), 0.49 vs
+  // 0.65 ms (37 taps) — the nested lerps are a longer dependent chain than the eight independent products
+  c.fwd_lean = flag("FSG_FWD_LEAN", false);
+  c.adj_lean = flag("FSG_ADJ_LEAN", true);
+  c.adj_thread = flag("FSG_ADJ_THREAD", false);
+  c.tile_debug = num("FSG_TILE_DEBUG", 0);
+  return c;
+}
+static const Config g_config = read_config();  // static initialiser: runs at dlopen
+const Config& config() { return g_config; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;

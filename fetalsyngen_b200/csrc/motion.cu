@@ -588,21 +588,13 @@ static int acq_forward(const char* who, int pairs, const float* transforms, cons
   const size_t smem = sizeof(float4) * ntaps;
   const float4* taps4 = reinterpret_cast<const float4*>(taps);
   // large PSFs: lanes over taps (coalesced gathers); small ones (the 1-tap mask acquisition): thread per pixel
-  static const int warp_min_taps = [] {
-    const char* e = getenv("FSG_FWD_WARP_MIN_TAPS");
-    return e ? atoi(e) : 400;  // r01: 215 taps 2.5 ms (thread) vs 3.9 ms (warp); 729 taps 12.7 vs 9.3 ms
-  }();
+  const int warp_min_taps = config().fwd_warp_min_taps;
 #define FSG_FWD_LAUNCH(KERNEL)                                                                                  \
   do {                                                                                                          \
     if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     KERNEL<<<grid, block, smem, s>>>(transforms, vol, taps4, ntaps, radius, slices, h, w, D, H, W, res_slice);  \
   } while (0)
-  static const bool lean = [] {
-    // opt-in: measured with the xy-quad volume 1.59 vs 1.27 ms (215 taps), 4.46 vs 4.62 ms (729 taps), 0.49 vs
-    // 0.65 ms (37 taps) — the nested lerps are a longer dependent chain than the eight independent products
-    const char* e = getenv("FSG_FWD_LEAN");
-    return e && e[0] == '1';
-  }();
+  const bool lean = config().fwd_lean;
 #define FSG_FWD_PICK(KERNEL)                              \
   do {                                                    \
     if (lean) {                                           \
@@ -671,10 +663,7 @@ extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, 
   const size_t smem = sizeof(float4) * ntaps;
   if (smem > 48 * 1024) cudaFuncSetAttribute(slice_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const float4* taps4 = reinterpret_cast<const float4*>(taps);
-  static const bool lean = [] {
-    const char* e = getenv("FSG_ADJ_LEAN");  // A/B: 0 = the reference's operation order (uncontracted, eight-product blend, IEEE divide)
-    return !(e && e[0] == '0');
-  }();
+  const bool lean = config().adj_lean;  // A/B: false = the reference's operation order (uncontracted, eight-product blend, IEEE divide)
   const size_t smem_w = smem + (lean ? sizeof(float) * (size_t)dp * hp * wp : 0);
   FSG_REQUIRE(smem_w <= 200 * 1024, "fsg_slice_acq_adjoint: %d taps + a %dx%dx%d PSF do not fit in shared memory", ntaps, dp, hp, wp);
 #define FSG_ADJ_WARP(TPL)                                                                                                                                                  \
@@ -690,10 +679,7 @@ extern "C" int fsg_slice_acq_adjoint(const float* transforms, const float* psf, 
     }                                                                                                                                                                      \
   } while (0)
   const int tpl = (ntaps + 31) / 32;
-  static const bool per_thread = [] {
-    const char* e = getenv("FSG_ADJ_THREAD");  // A/B: the thread-per-pixel kernel
-    return e && e[0] == '1';
-  }();
+  const bool per_thread = config().adj_thread;  // A/B: the thread-per-pixel kernel
   if (per_thread || tpl > 32)
     slice_adj_kernel<<<grid, dim3(ACQ_TILE, ACQ_TILE), smem, s>>>(transforms, psf, dp, hp, wp, taps4, ntaps, radius, slices, slice_idx, acc, h, w, D, H, W, res_slice);
   else if (tpl <= 2)

@@ -672,11 +672,7 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
     // but measured 2.4x slower than the full-z kernel at 256^3 (r01e: 2.17 ms vs 0.90 ms per 8
     // volumes; one 163 KB block per SM, no overlap of the box load with the gathers), so it is
     // opt-in until it is double-buffered.
-    static const bool use_tile = [] {
-      const char* e = getenv("FSG_WARP_TILE");
-      return e && e[0] == '1';
-    }();
-    if (use_tile && g < 2) {
+    if (config().warp_tile && g < 2) {
       const int rc = launch_warp_tile(part[g], cnt[g], g == 0, sx, sy, sz, s);
       if (rc == 0) continue;
       if (rc > 0) return rc;

@@ -443,10 +443,7 @@ int launch_warp_tile(const fsg_warp_job* jobs, int njobs, bool epi, int sx, int 
     }
   }
   box_bytes = (box_bytes + 127) / 128 * 128;
-  {
-    const char* dbg = getenv("FSG_TILE_DEBUG");
-    tp.debug = dbg ? atoi(dbg) : 0;
-  }
+  tp.debug = config().tile_debug;
   tp.fnodes = fnodes;
   tp.bnodes = bnodes;
   tp.box_floats = (box_floats + 31) / 32 * 32;

@@ -23,60 +23,68 @@ from ..generator.model import FetalSynthGen
 from ..utils.image_reading import SimpleITKReader
 
 
+class BidsIndex:
+    """One walk over a BIDS tree: ``entries[(subject, session)]`` lists the ``anat`` files of that scan.
+
+    The reference globs the tree once per (subject, suffix) (``datasets.py:74-95``); here the directory is read
+    once and suffix look-ups are dictionary scans, which matters for seed trees (24 look-ups per subject)."""
+
+    def __init__(self, root, subjects=None):
+        self.root = Path(root)
+        want = None if subjects is None else set(subjects)
+        self.entries: dict = {}
+        for sub_dir in sorted(d for d in self.root.glob("sub-*") if d.is_dir()):
+            if want is not None and sub_dir.name not in want:
+                continue
+            for child in sorted(c for c in sub_dir.iterdir() if c.is_dir()):
+                # <sub>/anat (no session) or <sub>/<ses>/anat
+                ses, anat = (None, child) if child.name == "anat" else (child.name, child / "anat")
+                self.entries[(sub_dir.name, ses)] = sorted(anat.glob("*.nii.gz")) if anat.is_dir() else []
+
+    def keys(self):
+        return sorted(self.entries, key=lambda k: (k[0], k[1] or ""))
+
+    def find(self, key, suffix):
+        """Files of scan ``key`` named ``<sub>[_<ses>]*_<suffix>.nii.gz``."""
+        sub, ses = key
+        stem = sub if ses is None else f"{sub}_{ses}"
+        tail = f"_{suffix}.nii.gz"
+        return [f for f in self.entries.get(key, []) if f.name.startswith(stem) and f.name.endswith(tail)]
+
+
 class FetalDataset:
-    """Abstract class defining a dataset for loading fetal data (datasets.py:17-113)."""
+    """Subject discovery for the datasets below.  Public attributes follow the reference's ``FetalDataset``
+    (``datasets.py:17-113``): ``subjects``, ``sub_ses``, ``img_paths``, ``segm_paths``, ``loader``."""
 
     def __init__(self, bids_path: str, sub_list: list[str] | None):
-        super().__init__()
         self.bids_path = Path(bids_path)
-        self.subjects = self.find_subjects(sub_list)
-        if self.subjects is None:
-            self.subjects = [x.name for x in self.bids_path.glob("sub-*")]
-        self.subjects = sorted(self.subjects)
-        self.sub_ses = [(x, y) for x in self.subjects for y in self._get_ses(self.bids_path, x)]
+        self._index = BidsIndex(self.bids_path, sub_list)
+        self.sub_ses = self._index.keys()
+        self.subjects = sorted({sub for sub, _ in self.sub_ses})
         self.loader = SimpleITKReader()
-        self.img_paths = self._load_bids_path(self.bids_path, "T2w", required=getattr(self, "_needs_images", True))
-        self.segm_paths = self._load_bids_path(self.bids_path, "dseg")
+        self.img_paths = self._one_per_scan(self._index, "T2w", required=getattr(self, "_needs_images", True))
+        self.segm_paths = self._one_per_scan(self._index, "dseg")
 
-    def find_subjects(self, sub_list):
-        subj_found = [x.name for x in Path(self.bids_path).glob("sub-*")]
-        return list(set(subj_found) & set(sub_list)) if sub_list is not None else None
-
-    def _sub_ses_string(self, sub, ses):
-        return f"{sub}_{ses}" if ses is not None else sub
+    @staticmethod
+    def _sub_ses_string(sub, ses):
+        return sub if ses is None else f"{sub}_{ses}"
 
     def _sub_ses_idx(self, idx):
-        sub, ses = self.sub_ses[idx]
-        return self._sub_ses_string(sub, ses)
+        return self._sub_ses_string(*self.sub_ses[idx])
 
-    def _get_ses(self, bids_path, sub):
-        ses = []
-        for s in [x for x in (bids_path / sub).iterdir() if x.is_dir()]:
-            ses.append(None if "anat" in s.name else s.name)
-        return sorted(ses, key=lambda x: x or "")
-
-    def _get_pattern(self, sub, ses, suffix, extension=".nii.gz"):
-        if ses is None:
-            return f"{sub}/anat/{sub}*_{suffix}{extension}"
-        return f"{sub}/{ses}/anat/{sub}_{ses}*_{suffix}{extension}"
-
-    def _load_bids_path(self, path, suffix, required: bool = True):
-        """One file per (subject, session) with the given suffix (datasets.py:74-95).  With
-        ``required=False`` a missing file yields ``None`` (images are optional when the
-        generator synthesises intensities from seeds)."""
-        files_paths = []
-        for sub, ses in self.sub_ses:
-            pattern = self._get_pattern(sub, ses, suffix)
-            files = list(path.glob(pattern))
-            if len(files) == 0:
-                if not required:
-                    files_paths.append(None)
-                    continue
-                raise FileNotFoundError(f"No files found for requested subject {sub} in {path} ({pattern} returned nothing)")
-            if len(files) > 1:
-                raise RuntimeError(f"Multiple files found for requested subject {sub} in {path} ({pattern} returned {files})")
-            files_paths.append(files[0])
-        return files_paths
+    def _one_per_scan(self, index: BidsIndex, suffix: str, required: bool = True):
+        """Exactly one file per scan with the given suffix, in ``sub_ses`` order; ``required=False`` maps a
+        missing file to ``None`` (images are optional when intensities are synthesised from seeds).  Errors as
+        in the reference: ``FileNotFoundError`` for none, ``RuntimeError`` for several (``datasets.py:85-94``)."""
+        out = []
+        for key in self.sub_ses:
+            hits = index.find(key, suffix)
+            if len(hits) > 1:
+                raise RuntimeError(f"Multiple files found for requested subject {key[0]} in {index.root}: {[f.name for f in hits]}")
+            if not hits and required:
+                raise FileNotFoundError(f"No files found for requested subject {key[0]} in {index.root} (suffix {suffix})")
+            out.append(hits[0] if hits else None)
+        return out
 
     def __len__(self):
         return len(self.subjects)
@@ -86,33 +94,27 @@ class FetalDataset:
 
 
 class FetalTestDataset(FetalDataset):
-    """Offline loading of real images for validation/testing (datasets.py:116-198)."""
+    """Real images + segmentations for validation / testing (``datasets.py:116-198``): returns
+    ``{"image": (1,H,W,D), "label": (1,H,W,D) int64, "name"}`` with optional dictionary transforms."""
 
     def __init__(self, bids_path: str, sub_list: list[str] | None, transforms=None):
         super().__init__(bids_path, sub_list)
         self.transforms = transforms
 
-    def _load_data(self, idx):
-        image = self.loader(self.img_paths[idx])
-        segm = self.loader(self.segm_paths[idx])
-        if len(image.shape) == 3:
-            image, segm = image.unsqueeze(0), segm.unsqueeze(0)
-        elif len(image.shape) != 4:
-            raise ValueError(f"Expected 3D or 4D image, got {len(image.shape)}D image.")
-        name = self._sub_ses_string(*self.sub_ses[idx])
-        return {"image": image, "label": segm.long(), "name": name}
-
     def __getitem__(self, idx) -> dict:
-        data = self._load_data(idx)
+        image, segm = self.loader(self.img_paths[idx]), self.loader(self.segm_paths[idx])
+        if image.dim() not in (3, 4):
+            raise ValueError(f"Expected 3D or 4D image, got {image.dim()}D image.")
+        if image.dim() == 3:
+            image, segm = image[None], segm[None]
+        data = {"image": image, "label": segm.long(), "name": self._sub_ses_idx(idx)}
         if self.transforms:
             data = self.transforms(data)
-        data["label"] = data["label"].long()
+            data["label"] = data["label"].long()
         return data
 
     def reverse_transform(self, data: dict) -> dict:
-        if self.transforms:
-            data = self.transforms.inverse(data)
-        return data
+        return self.transforms.inverse(data) if self.transforms else data
 
 
 class FetalSynthDataset(FetalDataset):
@@ -143,12 +145,14 @@ class FetalSynthDataset(FetalDataset):
         avail = [int(x.name.replace("subclasses_", "")) for x in self.seed_path.glob("subclasses_*")]
         if not avail:
             raise FileNotFoundError(f"No subclasses_* folders under {self.seed_path}")
+        wanted = sorted({sub for sub, _ in self.sub_ses})
         for n_sub in range(min(avail), max(avail) + 1):
             seed_path = self.seed_path / f"subclasses_{n_sub}"
             if not seed_path.exists():
                 raise FileNotFoundError(f"Provided seed path {seed_path} does not exist.")
+            index = BidsIndex(seed_path, wanted)
             for i in range(1, 5):
-                files = self._load_bids_path(seed_path, f"mlabel_{i}")
+                files = self._one_per_scan(index, f"mlabel_{i}")
                 for (sub, ses), file in zip(self.sub_ses, files):
                     self.seed_paths[self._sub_ses_string(sub, ses)][n_sub][i] = file
 

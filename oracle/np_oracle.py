@@ -9,9 +9,9 @@ CUDA library is missing.
 
 Parity pin: ``tests/test_oracle_golden.py`` checks every function below against golden vectors
 produced by running the unmodified reference in the build container
-(``tests/golden/make_golden.py``); ``tests/test_oracle_vs_reference.py`` re-checks against the
-live reference when ``/root/reference`` is present.  The reference itself ships no golden
-vectors / KATs for this path.
+(``tests/golden/make_golden.py``), including two cases at the full 256^3 size on the reference's bundled
+subjects (``tests/golden/full_*.npz``).  The reference itself ships no golden vectors / KATs for this path
+(SURVEY.md §4).
 
 All ``file:line`` citations are relative to the reference tree (``fetalsyngen/...``).
 

@@ -34,11 +34,24 @@ def shrink(vol: np.ndarray, shape) -> np.ndarray:
     return np.ascontiguousarray(vol[np.ix_(*idx)])
 
 
-class Recorder:
-    """Monkeypatches torch.rand/randn so every drawn tensor is logged in call order."""
+BIG = 1 << 16  # draws with at least this many elements are "volume noise"
 
-    def __init__(self):
+
+def seeded_normal(seed: int, shape) -> np.ndarray:
+    """Volume noise of the full-size cases: numpy's legacy MT19937 normals are identical on every host and
+    version, so only the seed is committed and the tests regenerate the tensor (a 256^3 draw is 64 MiB)."""
+    return np.random.RandomState(int(seed)).standard_normal(int(np.prod(shape))).astype(np.float32).reshape(shape)
+
+
+class Recorder:
+    """Monkeypatches torch.rand/randn so every drawn tensor is logged in call order.  With
+    ``np_seed_base`` the volume-sized normal draws are *replaced* by ``seeded_normal(np_seed_base + k)``
+    (k = index among the big draws) and only ("randn_np", seed, shape) is logged."""
+
+    def __init__(self, np_seed_base=None):
         self.log = []
+        self.np_seed_base = np_seed_base
+        self._big = 0
 
     def __enter__(self):
         self._rand, self._randn = torch.rand, torch.randn
@@ -50,6 +63,12 @@ class Recorder:
 
         def randn(*a, **k):
             t = self._randn(*a, **k)
+            if self.np_seed_base is not None and t.numel() >= BIG:
+                seed = self.np_seed_base + self._big
+                self._big += 1
+                t = torch.from_numpy(seeded_normal(seed, tuple(t.shape))).to(t.device)
+                self.log.append(("randn_np", (seed, tuple(t.shape))))
+                return t
             self.log.append(("randn", t.detach().cpu().numpy().copy()))
             return t
 
@@ -60,7 +79,10 @@ class Recorder:
         torch.rand, torch.randn = self._rand, self._randn
 
 
-def run_case(name, shape, seed, overrides=None, force=None, keep_stages=True, subject="sub-sta30"):
+def run_case(name, shape, seed, overrides=None, force=None, keep_stages=True, subject="sub-sta30", compact=False):
+    """compact (full-size cases): volume noise is seeded (see ``seeded_normal``), the inputs are the committed
+    subject fixture (tests/golden/subjects), and only the warped segmentation, a strided sample of the image
+    and per-plane sums are stored."""
     ref_import.load_reference()
     import fetalsyngen.generator.augmentation.synthseg as ss
     import fetalsyngen.generator.deformation.affine_nonrigid as an
@@ -81,6 +103,9 @@ def run_case(name, shape, seed, overrides=None, force=None, keep_stages=True, su
     for n, d in ref_import.seed_paths(subject).items():
         seeds[n] = {}
         for m, p in d.items():
+            if compact and tuple(shape) == tuple(seg_full.shape):
+                seeds[n][m] = p  # full size: the reference reads its own bundled files
+                continue
             v = shrink(ref_import.read_nifti(p)[0], shape)
             fp = tmp / f"s{n}_m{m}.nii.gz"
             write_nifti(fp, v)
@@ -171,7 +196,7 @@ def run_case(name, shape, seed, overrides=None, force=None, keep_stages=True, su
     np.random.seed(seed)
     torch.manual_seed(seed)
     try:
-        with Recorder() as rec:
+        with Recorder(np_seed_base=100000 * seed if compact else None) as rec:
             out, seg_out, _, params = gen.sample(image=None, segmentation=torch.from_numpy(seg), seeds=seeds)
     finally:
         ss.gaussian_blur_3d = orig_blur
@@ -179,6 +204,8 @@ def run_case(name, shape, seed, overrides=None, force=None, keep_stages=True, su
 
     # ---- identify the random tensors by call order (Appendix A.3 / A.5 of SURVEY.md)
     log = rec.log
+    if compact:
+        return _save_compact(name, shape, cfg, subject, log, cap, params, seg_out, final)
     d = {
         "shape": np.array(shape),
         "resolution": np.array(cfg["resolution"], dtype=np.float64),
@@ -243,6 +270,52 @@ def run_case(name, shape, seed, overrides=None, force=None, keep_stages=True, su
     return d
 
 
+SUB = (slice(1, None, 4), slice(2, None, 4), slice(3, None, 4))  # strided image sample of the compact cases
+
+
+def _save_compact(name, shape, cfg, subject, log, cap, params, seg_out, final):
+    assert log[3][0] == "randn_np", log[3][0]
+    d = {
+        "shape": np.array(shape), "resolution": np.array(cfg["resolution"], dtype=np.float64), "subject": np.array(subject),
+        "mlabel2subclusters": cap["mlabel2subclusters"], "mus": cap["mus"], "sigmas": cap["sigmas"],
+        "gmm_noise_seed": np.int64(log[3][1][0]),
+        "seg_out": seg_out.numpy().astype(np.uint8),
+        "final_sub": np.ascontiguousarray(final[SUB]), "final_min": np.float32(final.min()), "final_max": np.float32(final.max()),
+        "final_plane_sums": final.astype(np.float64).sum(axis=(1, 2)), "intensity_plane_sums": cap["intensity"].astype(np.float64).sum(axis=(1, 2)),
+    }
+    i = 4
+    dp = params["deform_params"]
+    d["flip"] = np.array(bool(dp["flip"]))
+    if dp["affine"] is not None:
+        d["A"], d["c2"] = cap["A"], cap["c2"]
+        i += 1
+        if dp["non_rigid"]:
+            d["nonlin_std"] = np.float64(dp["non_rigid"]["nonlin_std"])
+            d["Fsmall_n"] = log[i][1]
+            i += 1
+    if params["gamma_params"]["gamma"] is not None:
+        d["gamma"] = np.float64(params["gamma_params"]["gamma"])
+    if params["bf_params"]["bf_std"] is not None:
+        d["bf_std"] = np.asarray(params["bf_params"]["bf_std"], dtype=np.float64)
+        d["bf_n"] = log[i][1]
+        i += 1
+    if params["resample_params"]["spacing"] is not None:
+        d["spacing"] = np.array(params["resample_params"]["spacing"], dtype=np.float64)
+        d["stds"] = cap["stds"]
+        d["factors"] = cap["factors"]
+        d["lowres_shape"] = np.array(cap["lowres"].shape)
+    if params["noise_params"]["noise_std"] is not None:
+        d["noise_std"] = np.float64(params["noise_params"]["noise_std"])
+        kind, val = log[i]
+        assert kind == "randn_np", kind
+        d["noise_seed"], d["noise_shape"] = np.int64(val[0]), np.array(val[1])
+        i += 1
+    assert i == len(log), (i, len(log), [(k, getattr(v, "shape", v)) for k, v in log])
+    np.savez_compressed(OUT / f"full_{name}.npz", **d)
+    print(name, {k: (v.shape if getattr(v, "shape", ()) else v) for k, v in d.items() if k not in ("seg_out", "final_sub", "Fsmall_n")})
+    return d
+
+
 SMALL = {
     "spatial_deform.nonlin_scale_min": 0.10,
     "spatial_deform.nonlin_scale_max": 0.20,
@@ -251,7 +324,16 @@ SMALL = {
 }
 ALL_ON = {"spatial_deform.prob": 1.0, "resampled.prob": 1.0, "biasfield.prob": 1.0, "gamma.prob": 1.0, "noise.prob": 1.0}
 
+def full_cases():
+    """BASELINE.json configs[0]: the bundled 256^3 subjects at the default configuration (stage gates forced)."""
+    run_case("sta30_all_flip", (256, 256, 256), 1234, None, {**ALL_ON, "spatial_deform.flip_prb": 1.0}, subject="sub-sta30", compact=True)
+    run_case("sta38_noresample", (256, 256, 256), 77, None, {**ALL_ON, "resampled.prob": 0.0, "spatial_deform.flip_prb": 0.0}, subject="sub-sta38", compact=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        full_cases()
+        raise SystemExit(0)
     run_case("c32_all", (32, 32, 32), 1234, SMALL, ALL_ON)
     run_case("c32_flip", (32, 32, 32), 7, SMALL, {**ALL_ON, "spatial_deform.flip_prb": 1.0})
     run_case("c32_noflip", (32, 32, 32), 8, SMALL, {**ALL_ON, "spatial_deform.flip_prb": 0.0})

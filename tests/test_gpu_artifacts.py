@@ -280,3 +280,46 @@ def test_windowed_distance_packed_and_scalar_paths(shape):
         ops.dist(dev(m).view(-1), d16, t16, r, metric)
         got = d16.cpu().numpy().view(np.uint16).reshape(-1)[: m.size].reshape(shape).astype(np.int64)
         np.testing.assert_array_equal(got, want)
+
+
+def test_boundaries_morphology_bit_exact_at_256():
+    """SimulatedBoundaries' integer morphology at BASELINE.json's full size on the bundled sub-sta30 label map:
+    halo (ball dilation == exact integer distance threshold, checked against scipy's Euclidean feature transform),
+    one fuzzy round against the oracle, and the L1 dilation stack — all bit-exact."""
+    from scipy import ndimage
+
+    from golden_util import load_subject
+
+    seg = load_subject("sub-sta30")[0]
+    shape = seg.shape
+    m = (seg > 0).astype(np.uint8)
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    ops = ArtifactOps(eng)
+    sb = SimulatedBoundaries(0.0, 1.0, 1.0)
+    mask = dev(m).view(-1)
+    halo = torch.empty_like(mask)
+    r = 9
+    sb.build_halo(ops, mask, r, halo)
+    idx = ndimage.distance_transform_edt(m == 0, return_distances=False, return_indices=True)
+    grid = np.indices(shape)
+    d2 = sum((idx[a].astype(np.int64) - grid[a]) ** 2 for a in range(3))
+    halo_np = halo.cpu().numpy().reshape(shape)
+    np.testing.assert_array_equal(halo_np, (d2 <= r * r).astype(np.uint8))
+    # one fuzzy round with an injected permutation of the ring voxels
+    diff = OA.dilate(halo_np, 7).astype(np.int32) - halo_np.astype(np.int32)
+    nz = np.nonzero(diff)
+    perm = np.random.RandomState(3).permutation(len(nz[0]))
+    keep = diff.astype(np.uint8)
+    drop = perm[: int(len(nz[0]) * 0.9)]
+    keep[nz[0][drop], nz[1][drop], nz[2][drop]] = 0
+    nxt = torch.empty_like(mask)
+    sb.generate_fuzzy_boundaries(ops, halo, nxt, dev(keep).view(-1))
+    np.testing.assert_array_equal(nxt.cpu().numpy().reshape(shape), OA.fuzzy_iteration(halo_np, perm))
+    # L1 distance thresholds == repeated 6-neighbour dilations of the halo
+    d16, t16 = ops.u16("d0"), ops.u16("d1")
+    ops.dist(halo, d16, t16, 4, 1)
+    d = d16.cpu().numpy().view(np.uint16).reshape(shape)
+    want = halo_np
+    for kk in range(1, 4):
+        want = OA.build_halo(want, 1)
+        np.testing.assert_array_equal((d <= kk).astype(np.uint8), want)

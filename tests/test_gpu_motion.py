@@ -74,6 +74,53 @@ def test_kernels_vs_numpy_oracle(seed):
     close(rel(gv, wv))
 
 
+def _reference_extension():
+    """oracle/_ref/slice_acq_cuda.so (built here by __graft_entry__.build(), it travels with the repo): on a CUDA
+    box its absence is a failure of the parity set-up, not a reason to skip."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+
+    ext = build_ref.load_built()
+    assert ext is not None, "oracle/_ref/slice_acq_cuda.so is missing: run __graft_entry__.build() in the build container before shipping the tree"
+    return ext
+
+
+@pytest.mark.parametrize("res_s,thick,gap", [(0.6, 2.5, 3.5), (1.0, 3.5, 1.6), (0.3, 1.5, 5.0)])
+def test_kernels_vs_reference_extension_at_full_size(res_s, thick, gap):
+    """The three 256^3 shapes that profiles/*_motion.jsonl times (288^2 / 160^2 / 544^2 slices; 215 / 729 / 37
+    PSF taps), on the bundled sub-sta30 label map: acquisition and PSF reconstruction asserted against the
+    reference's own extension, including the xy-quad source copy the production path acquires from."""
+    from fetalsyngen_b200.generator.artifacts import simulate_reco as SR
+    from fetalsyngen_b200.generator.artifacts import svort
+    from golden_util import load_subject
+
+    ext = _reference_extension()
+    seg, _, _ = load_subject("sub-sta30")
+    S = seg.shape[0]
+    rs = np.random.RandomState(5)
+    vol = torch.from_numpy((seg > 0).astype(np.float32) * (0.3 + 0.7 * rs.rand(S, S, S).astype(np.float32))).to(DEV)
+    np.random.seed(1)
+    psf = svort.get_PSF(res_ratio=(res_s / 0.5, res_s / 0.5, thick / 0.5))
+    ss = int(np.ceil(int(np.sqrt(3 * S * S / 2.0) * 0.5 / res_s) / 32.0) * 32)
+    ns = int(S * 0.5 / gap) + 2
+    init = svort.random_init_stack_transforms(ns, gap, False, 3.0)
+    motion = svort.sample_motion(np.arange(ns) * 1.5, True)
+    mat = svort.mat_update_resolution(motion.compose(init).matrix(), 0.5, 0.5)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    empty = torch.empty(0, device=DEV)
+    ref_s = ext.forward(t(mat), vol[None, None], empty, empty, t(psf), [ss, ss], float(res_s / 0.5), False, False)[0]
+    ref_np = ref_s[:, 0].cpu().numpy()
+    for pairs in (None, SR.volume_xyquads(vol)):
+        got = SR.slice_acquisition(mat, vol, psf, (ss, ss), res_s / 0.5, pairs=pairs)[:, 0]
+        close(rel(got, ref_np))
+    nstack = max(1, min(6, 250 // ns))
+    mats = np.concatenate([mat] * nstack)[:250]
+    sl = torch.cat([ref_s] * nstack)[:250].contiguous()
+    ref_v = ext.adjoint_forward(t(mats), t(psf), sl, empty, empty, [S, S, S], float(res_s / 0.5), True, True)[0][0, 0].cpu().numpy()
+    gv, _ = SR.slice_acquisition_adjoint(mats, psf, sl, (S, S, S), res_s / 0.5)
+    close(rel(gv[0, 0], ref_v))
+
+
 @pytest.mark.parametrize("seed", [0, 1])
 def test_kernels_and_oracle_vs_reference_extension(seed):
     """The reference's slice_acq_cuda extension (built by oracle/build_ref.py from /root/reference)
@@ -81,9 +128,7 @@ def test_kernels_and_oracle_vs_reference_extension(seed):
     sys.path.insert(0, str(ROOT / "oracle"))
     import build_ref
 
-    ext = build_ref.load_built()
-    if ext is None:
-        pytest.skip("oracle/_ref/slice_acq_cuda.so not built")
+    ext = _reference_extension()
     vol, mat, psf, shape, res = random_case(seed)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
     empty = torch.empty(0, device=DEV)

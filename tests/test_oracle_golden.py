@@ -69,3 +69,22 @@ def test_full_pipeline(name):
             assert rel_err(st[key], d[gkey]) <= TOL, (key, rel_err(st[key], d[gkey]))
     assert rel_err(out, d["final"]) <= TOL
     assert rel_err(O.scale_intensity(out), d["scaled"]) <= TOL
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[0] at full size
+@pytest.mark.parametrize("name", ["sta30_all_flip", "sta38_noresample"])
+def test_full_size_pipeline_vs_reference(name):
+    """The oracle at 256^3 on the bundled subjects against the unmodified reference (tests/golden/full_*.npz):
+    warped segmentation bit-exact over the whole volume, the image on the stored strided sample, and the
+    per-plane sums of the GMM image and of the result."""
+    from golden_util import SUB, load_full_case
+
+    d, labels, seg_in, p = load_full_case(name)
+    out, seg, st = O.generate_base(labels, seg_in, p)
+    np.testing.assert_array_equal(seg, d["seg_out"])
+    rng = float(d["final_max"] - d["final_min"])
+    assert np.abs(out[SUB].astype(np.float64) - d["final_sub"]).max() / rng <= TOL
+    assert float(out.max()) == pytest.approx(float(d["final_max"]), rel=1e-6)
+    nplane = out.shape[1] * out.shape[2]
+    assert np.abs(out.astype(np.float64).sum(axis=(1, 2)) - d["final_plane_sums"]).max() / nplane / rng <= TOL
+    assert np.abs(st["intensity"].astype(np.float64).sum(axis=(1, 2)) - d["intensity_plane_sums"]).max() / nplane <= 1e-3
