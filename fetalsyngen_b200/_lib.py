@@ -56,12 +56,12 @@ class ZoomJob(C.Structure):
 
 
 class SepAxis(C.Structure):
-    _fields_ = [("q0", _vp), ("w", _vp), ("n_out", _i32), ("width", _i32)]
+    _fields_ = [("q0", _vp), ("w", _vp), ("n_out", _i32), ("width", _i32), ("pos", _vp), ("taps", _vp), ("ntaps", _i32), ("_pad", _i32)]
 
 
 class SepconvJob(C.Structure):
     _fields_ = [("src", _vp), ("dst", _vp), ("tmp1", _vp), ("tmp2", _vp), ("ax", SepAxis * 3), ("noise", _vp), ("rng", Rng),
-                ("noise_std", _f32), ("has_noise", _i32)]
+                ("noise_std", _f32), ("has_noise", _i32), ("cap_dst", _i64), ("cap_tmp1", _i64), ("cap_tmp2", _i64)]
 
 
 class SampleJob(C.Structure):
@@ -87,7 +87,7 @@ class UnpackJob(C.Structure):
 
 
 class SepComposeJob(C.Structure):
-    _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32)]
+    _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32), ("cap_q0", _i32), ("cap_w", _i32)]
 
 
 _STRUCTS = {"fsg_em_job": EmJob, "fsg_unpack_job": UnpackJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,

@@ -10,9 +10,17 @@
 // shrinking the volume at every pass:
 //     x: [sx][sy][sz] -> [n0][sy][sz]     streaming, register sliding window, 4N + 4fN bytes
 //     y: [n0][sy][sz] -> [n0][n1][sz]     streaming, register sliding window
-//     z: [n0][n1][sz] -> [n0][n1][n2]     rows staged in shared memory, + RandNoise epilogue
+//     z: [n0][n1][sz] -> [n0][n1][n2]     + RandNoise epilogue.  sz <= 256 (production): a warp per row, the row in
+//                                         registers (8 samples per lane, halo by shuffles), 13-tap blur with static
+//                                         register indexing, then the coarse samples (sep_zrow_kernel); otherwise
+//                                         rows staged in shared memory with the composed windows (sep_z_kernel)
 // instead of 3 full-resolution blur passes + a gather (24 N + 4(N+n^3) bytes before).
 // With identity positions the same kernels are a plain separable blur (BlurCortex).
+// Noise: Philox block = flat output index / 4, component = index % 4, in every kernel.
+// r02 measurement that shaped this file: a schedule that ran z + y fused on the full-resolution volume and x last
+// (4N(1 + 2f^2 + f^3) bytes instead of 4N(1 + 2f + 2f^2 + f^3)) was 2x SLOWER (0.82 vs 0.43 ms per 8 volumes): the
+// z blur at full resolution costs ~27 instructions per voxel against ~10 for the streaming x pass, which already
+// runs at 5.2 TB/s of its own traffic.  Cheap-first (x, y streaming) and the instruction-heavy axis last wins.
 // Float image path: FMA accumulation, parity is the 1e-4 tolerance (tests/test_gpu_base.py).
 #include "common.cuh"
 
@@ -56,6 +64,20 @@ struct VecT<2> {
     a.y = __fmaf_rn(w, v.y, a.y);
   }
 };
+
+// RandNoise epilogue (synthseg.py:217-235) of the last pass: out = max(0, out + std * N).  Injected draws are
+// indexed by the flat output index; the Philox stream is laid out per output row so that a block of four normals
+// never straddles rows: block = row * ceil(n_out / 4) + K / 4, component K % 4.
+__device__ __forceinline__ float noise_normal(const SepNoise& nz, int jb, int64_t row, int K, int n_out, bool inject) {
+  if (inject) return __ldg(nz.noise[jb] + row * n_out + K);
+  const float4 q = philox_normal4(nz.rng[jb], (uint32_t)row * (uint32_t)((n_out + 3) >> 2) + (uint32_t)(K >> 2));
+  const int comp = K & 3;
+  return comp == 0 ? q.x : (comp == 1 ? q.y : (comp == 2 ? q.z : q.w));
+}
+__device__ __forceinline__ float noise_apply(float v, float std, float n) {
+  v = __fmaf_rn(std, n, v);
+  return v < 0.f ? 0.f : v;
+}
 
 // Streaming pass along a slow axis.  The volume is viewed as [outer][a_in][inner]; a thread owns
 // VEC consecutive inner elements of one `outer` slab and walks the axis once, keeping the last W
@@ -121,9 +143,7 @@ __global__ void __launch_bounds__(SEP_THREADS) sep_stream_kernel(const __grid_co
 // Last pass: rows of the fast axis staged in shared memory.  Thread = one output position K
 // (its W weights live in registers) looping over the block's rows; lanes are consecutive K,
 // so the stores are coalesced and the shared-memory reads stride by ~1/factor.
-// RandNoise epilogue (synthseg.py:217-235): out = max(0, out + std*N).  Philox counter layout of
-// this stream: block = row * ceil(n2/4) + K/4, component K%4; every lane draws one block per
-// four rows and the normals are handed out by shuffles, so no draw is computed twice.
+// RandNoise epilogue (synthseg.py:217-235): out = max(0, out + std*N(flat output index)).
 template <int W, bool INJECT>
 __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_constant__ SepPass p, const __grid_constant__ SepNoise nz, int a_in) {
   const int jb = blockIdx.y;
@@ -159,8 +179,6 @@ __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_consta
   const int g = threadIdx.x / kw;
   const bool has_noise = nz.has[jb] != 0;
   const float nstd = nz.std[jb];
-  const int kgroups = (n_out + 3) >> 2;
-  const int lane = threadIdx.x & 31;
   if (g >= groups) return;  // whole warps only (kw is a multiple of 32)
   for (int kb = threadIdx.x - g * kw; kb < kw; kb += (groups == 1 ? SEPZ_THREADS : kw)) {
     const int K = kb;
@@ -175,10 +193,7 @@ __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_consta
 #pragma unroll
       for (int t = 0; t < W; ++t) wreg[t] = 0.f;
     }
-    const int kbase = K - lane;
-    float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
-    int m = 0;
-    for (int r = g; r < nrow; r += groups, ++m) {
+    for (int r = g; r < nrow; r += groups) {
       float acc = 0.f;
       {
         const float* row = s_rows + r * pitch + W + q0;  // q0 >= -W (dead lanes: q0 = 0, zero weights)
@@ -190,28 +205,170 @@ __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_consta
         }
         acc = __fadd_rn(acc, acc2);
       }
-      if (has_noise) {
-        float nv;
-        if (INJECT) {
-          nv = live ? __ldg(nz.noise[jb] + (size_t)(row0 + r) * n_out + K) : 0.f;
-        } else {
-          if ((m & 3) == 0) {
-            // lane l draws the block of row slot (l>>3) and K-group (l&7) of this warp's 32 outputs
-            const int rr = r + (lane >> 3) * groups;
-            const uint32_t blk = (uint32_t)(row0 + rr) * (uint32_t)kgroups + (uint32_t)((kbase >> 2) + (lane & 7));
-            nrm = philox_normal4(nz.rng[jb], blk);
-          }
-          const int srcl = (m & 3) * 8 + (lane >> 2);
-          const float a = __shfl_sync(0xffffffffu, nrm.x, srcl), b = __shfl_sync(0xffffffffu, nrm.y, srcl);
-          const float c = __shfl_sync(0xffffffffu, nrm.z, srcl), d = __shfl_sync(0xffffffffu, nrm.w, srcl);
-          const int comp = lane & 3;
-          nv = comp == 0 ? a : (comp == 1 ? b : (comp == 2 ? c : d));
-        }
-        acc = __fmaf_rn(nstd, nv, acc);
-        acc = acc < 0.f ? 0.f : acc;
-      }
+      if (has_noise && live) acc = noise_apply(acc, nstd, noise_normal(nz, jb, row0 + r, K, n_out, INJECT));
       if (live) p.dst[jb][(size_t)(row0 + r) * n_out + K] = acc;
     }
+  }
+}
+
+// Last pass for rows of at most 256 samples (the production extents): one warp per row, the row in registers.
+// Lane l holds its 8 consecutive samples (two 16-byte loads, the next row already in flight), fetches the 6 + 6
+// halo samples from its neighbours by shuffles and evaluates the zero-padded 13-tap Gaussian for its 8 positions
+// with statically indexed registers (the reference's conv along z, utils/generation.py:84-110); the blurred row
+// goes to shared memory and the lanes sample it at the coarse positions (w_f*B[f] + w_c*B[c], 0 where the
+// reference's sampler returns 0; utils/generation.py:227-285).  The outputs are transposed through shared memory
+// so that a lane owns four consecutive K: one Philox block and one 16-byte store per group.
+// r02 ncu of sep_z_kernel at these extents: bound by shared-memory wavefronts (W loads per output, 2-way bank
+// conflicts at stride 1/f); here a row costs 2 + 16 shared-memory instructions per lane instead of 16 per output.
+constexpr int ZR_THREADS = 256;
+constexpr int ZR_R = 6;      // blur radius held in registers (13 taps)
+constexpr int ZR_ROW = 256;  // row / coarse row limit (8 samples per lane)
+struct SepZRow {
+  const float* src[FSG_MAX_JOBS];
+  float* dst[FSG_MAX_JOBS];
+  const fsg_tab* pos[FSG_MAX_JOBS];
+  const float* taps[FSG_MAX_JOBS];
+  int ntaps[FSG_MAX_JOBS];
+  int n_out[FSG_MAX_JOBS];
+  int rows[FSG_MAX_JOBS];
+};
+
+__device__ __forceinline__ void zr_load_row(const float* __restrict__ src, int row, int rows, int sz, int lane, float (&v)[8]) {
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = 0.f;
+  if (row < rows && 8 * lane < sz) {
+    const float4* r4 = reinterpret_cast<const float4*>(src + (size_t)row * sz + 8 * lane);
+    const float4 a = __ldcs(r4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    if (8 * lane + 4 < sz) {
+      const float4 b = __ldcs(r4 + 1);
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+  }
+}
+
+template <bool INJECT>
+__global__ void __launch_bounds__(ZR_THREADS, 3) sep_zrow_kernel(const __grid_constant__ SepZRow p, const __grid_constant__ SepNoise nz, int sz) {
+  const int jb = blockIdx.y;
+  const int n2 = p.n_out[jb], rows = p.rows[jb];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ __align__(16) float s_b[ZR_THREADS / 32][ZR_ROW];  // blurred row of each warp
+  __shared__ __align__(16) float s_o[ZR_THREADS / 32][ZR_ROW];  // coarse row of each warp (transposition)
+  float* const my_b = s_b[warp];
+  float* const my_o = s_o[warp];
+  const char* const my_bb = reinterpret_cast<const char*>(my_b);
+
+  float tp[2 * ZR_R + 1];
+  {
+    const int nt = p.taps[jb] ? p.ntaps[jb] : 1, r = nt / 2;
+#pragma unroll
+    for (int s_ = 0; s_ < 2 * ZR_R + 1; ++s_) {
+      const int t = s_ - ZR_R + r;
+      tp[s_] = (t >= 0 && t < nt) ? (p.taps[jb] ? __ldg(p.taps[jb] + t) : 1.0f) : 0.f;
+    }
+  }
+  // coarse positions sampled by this lane: K = lane + 32 e (neighbouring lanes read neighbouring words)
+  int zfc[8];  // byte offsets into the blurred row: f*4 | c*4 << 16, -1 = the sampler returns 0
+  float zwc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int K = lane + 32 * e;
+    zfc[e] = -1;
+    zwc[e] = 0.f;
+    if (K < n2) {
+      if (p.pos[jb]) {
+        const fsg_tab t = p.pos[jb][K];
+        if (t.f >= 0) zfc[e] = ((int)t.f * 4) | (((int)t.c * 4) << 16);
+        zwc[e] = t.wc;
+      } else {
+        zfc[e] = (K * 4) | ((K * 4) << 16);
+      }
+    }
+  }
+  const bool has_noise = nz.has[jb] != 0;
+  const float nstd = nz.std[jb];
+  const uint32_t kgroups = (uint32_t)((n2 + 3) >> 2);
+  const float* __restrict__ src = p.src[jb];
+  float* __restrict__ dst = p.dst[jb];
+  const bool dst16 = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  const int stride = gridDim.x * (ZR_THREADS / 32);
+
+  int row = blockIdx.x * (ZR_THREADS / 32) + warp;
+  float cur[8];
+  zr_load_row(src, row, rows, sz, lane, cur);
+  for (; row < rows; row += stride) {
+    float nxt[8];
+    zr_load_row(src, row + stride, rows, sz, lane, nxt);
+    float w20[8 + 2 * ZR_R];
+#pragma unroll
+    for (int m = 0; m < ZR_R; ++m) {
+      const float l = __shfl_up_sync(0xffffffffu, cur[8 - ZR_R + m], 1), r = __shfl_down_sync(0xffffffffu, cur[m], 1);
+      w20[m] = lane == 0 ? 0.f : l;
+      w20[8 + ZR_R + m] = lane == 31 ? 0.f : r;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) w20[ZR_R + m] = cur[m];
+    float b[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      float acc = 0.f, acc2 = 0.f;
+#pragma unroll
+      for (int s_ = 0; s_ < 2 * ZR_R; s_ += 2) {
+        acc = __fmaf_rn(tp[s_], w20[m + s_], acc);
+        acc2 = __fmaf_rn(tp[s_ + 1], w20[m + s_ + 1], acc2);
+      }
+      b[m] = __fadd_rn(__fmaf_rn(tp[2 * ZR_R], w20[m + 2 * ZR_R], acc), acc2);
+    }
+    __syncwarp();  // the previous row's readers of my_b / my_o are done
+    reinterpret_cast<float4*>(my_b)[2 * lane] = make_float4(b[0], b[1], b[2], b[3]);
+    reinterpret_cast<float4*>(my_b)[2 * lane + 1] = make_float4(b[4], b[5], b[6], b[7]);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+      if (zfc[e] >= 0) {
+        const float lo = *reinterpret_cast<const float*>(my_bb + (zfc[e] & 0xffff)), hi = *reinterpret_cast<const float*>(my_bb + (zfc[e] >> 16));
+        v = __fmaf_rn(__fsub_rn(1.0f, zwc[e]), lo, __fmul_rn(zwc[e], hi));
+      }
+      my_o[lane + 32 * e] = v;
+    }
+    __syncwarp();
+    // ---- lane owns K = 4 lane + 128 h + (0..3): noise + store
+    float* __restrict__ orow = dst + (size_t)row * n2;
+    const bool vec = dst16 && (((size_t)row * n2) & 3) == 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int K0 = 4 * lane + 128 * h;
+      if (K0 < n2) {
+        float4 o = reinterpret_cast<const float4*>(my_o)[lane + 32 * h];
+        if (has_noise) {
+          float4 nq;
+          if (INJECT) {
+            const float* nrow = nz.noise[jb] + (size_t)row * n2 + K0;
+            nq.x = __ldg(nrow);
+            nq.y = K0 + 1 < n2 ? __ldg(nrow + 1) : 0.f;
+            nq.z = K0 + 2 < n2 ? __ldg(nrow + 2) : 0.f;
+            nq.w = K0 + 3 < n2 ? __ldg(nrow + 3) : 0.f;
+          } else {
+            nq = philox_normal4(nz.rng[jb], (uint32_t)row * kgroups + (uint32_t)(K0 >> 2));
+          }
+          o.x = noise_apply(o.x, nstd, nq.x);
+          o.y = noise_apply(o.y, nstd, nq.y);
+          o.z = noise_apply(o.z, nstd, nq.z);
+          o.w = noise_apply(o.w, nstd, nq.w);
+        }
+        if (vec && K0 + 3 < n2) {
+          *reinterpret_cast<float4*>(orow + K0) = o;
+        } else {
+          orow[K0] = o.x;
+          if (K0 + 1 < n2) orow[K0 + 1] = o.y;
+          if (K0 + 2 < n2) orow[K0 + 2] = o.z;
+          if (K0 + 3 < n2) orow[K0 + 3] = o.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) cur[m] = nxt[m];
   }
 }
 
@@ -222,7 +379,6 @@ __global__ void __launch_bounds__(256) sep_generic_kernel(const __grid_constant_
   const int jb = blockIdx.y;
   const int n_out = p.n_out[jb], width = p.width[jb], outer = p.outer[jb];
   const int64_t total = (int64_t)outer * n_out * inner;
-  const int kgroups = (n_out + 3) >> 2;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % inner);
     const int64_t oi = e / inner;
@@ -231,18 +387,7 @@ __global__ void __launch_bounds__(256) sep_generic_kernel(const __grid_constant_
     const float* __restrict__ w = p.w[jb] + I * width;
     float acc = 0.f;
     for (int t = 0; t < width; ++t) acc = __fmaf_rn(__ldg(w + t), __ldg(in + (size_t)t * inner), acc);
-    if (last && nz.has[jb]) {
-      float nv;
-      if (INJECT) {
-        nv = __ldg(nz.noise[jb] + e);
-      } else {
-        const float4 q = philox_normal4(nz.rng[jb], (uint32_t)o * (uint32_t)kgroups + (uint32_t)(I >> 2));
-        const int comp = I & 3;
-        nv = comp == 0 ? q.x : (comp == 1 ? q.y : (comp == 2 ? q.z : q.w));
-      }
-      acc = __fmaf_rn(nz.std[jb], nv, acc);
-      acc = acc < 0.f ? 0.f : acc;
-    }
+    if (last && nz.has[jb]) acc = noise_apply(acc, nz.std[jb], noise_normal(nz, jb, o, I, n_out, INJECT));  // last pass: inner == 1, o = row
     p.dst[jb][e] = acc;
   }
 }
@@ -327,6 +472,8 @@ extern "C" int fsg_sep_compose(const fsg_sepcompose_job* jobs, int njobs, void* 
     FSG_REQUIRE(nt >= 1 && nt % 2 == 1 && nt <= FSG_MAX_TAPS, "fsg_sep_compose: job %d needs an odd tap count <= %d", i, FSG_MAX_TAPS);
     const int need = nt + (j.pos ? 1 : 0);
     FSG_REQUIRE(j.width == (need < j.n_in ? need : j.n_in), "fsg_sep_compose: job %d width must be min(n_in, ntaps + (pos != NULL))", i);
+    FSG_REQUIRE(j.cap_q0 >= j.n_out && (int64_t)j.cap_w >= (int64_t)j.n_out * j.width, "fsg_sep_compose: job %d: tables of %d x %d entries do not fit the workspace (%d / %d)", i, j.n_out,
+                j.width, j.cap_q0, j.cap_w);
     b.j[i] = j;
     if (j.n_out > max_n) max_n = j.n_out;
   }
@@ -345,6 +492,12 @@ extern "C" int fsg_sepconv(const fsg_sepconv_job* jobs, int njobs, int sx, int s
     const fsg_sepconv_job& j = jobs[i];
     FSG_REQUIRE(j.src && j.dst && j.tmp1 && j.tmp2, "fsg_sepconv: job %d has a NULL buffer", i);
     FSG_REQUIRE(j.src != j.dst && j.src != j.tmp1 && j.tmp1 != j.tmp2 && j.tmp2 != j.dst, "fsg_sepconv: job %d: adjacent passes must not alias", i);
+    // an axis may be up-sampled (n_out > n_in: simulated spacing finer than the input resolution), so every pass is checked against its buffer
+    FSG_REQUIRE((int64_t)j.ax[0].n_out * sy * sz <= j.cap_tmp1, "fsg_sepconv: job %d: the x pass result %dx%dx%d does not fit tmp1 (%lld floats)", i, j.ax[0].n_out, sy, sz, (long long)j.cap_tmp1);
+    FSG_REQUIRE((int64_t)j.ax[0].n_out * j.ax[1].n_out * sz <= j.cap_tmp2, "fsg_sepconv: job %d: the y pass result %dx%dx%d does not fit tmp2 (%lld floats)", i, j.ax[0].n_out, j.ax[1].n_out, sz,
+                (long long)j.cap_tmp2);
+    FSG_REQUIRE((int64_t)j.ax[0].n_out * j.ax[1].n_out * j.ax[2].n_out <= j.cap_dst, "fsg_sepconv: job %d: the output %dx%dx%d does not fit dst (%lld floats)", i, j.ax[0].n_out, j.ax[1].n_out,
+                j.ax[2].n_out, (long long)j.cap_dst);
     for (int a = 0; a < 3; ++a) {
       const fsg_sepaxis& ax = j.ax[a];
       FSG_REQUIRE(ax.q0 && ax.w, "fsg_sepconv: job %d axis %d has a NULL table", i, a);
@@ -402,7 +555,32 @@ extern "C" int fsg_sepconv(const fsg_sepconv_job* jobs, int njobs, int sx, int s
         sep_generic_kernel<false><<<dim3((unsigned)(want < 148 * 32 ? want : 148 * 32), njobs), 256, 0, s>>>(p, none, a_in, inner, 0);
       }
     } else {
-      if (maxw <= 8 && a_in >= 8) {
+      // rows of <= 256 samples whose blur fits 13 taps, described by `pos` / `taps`: warp-per-row register kernel
+      bool zrow = sz <= ZR_ROW && (sz & 3) == 0;
+      for (int i = 0; i < njobs && zrow; ++i) {
+        const fsg_sepaxis& z = jobs[i].ax[2];
+        zrow = z.ntaps >= 1 && z.ntaps <= 2 * ZR_R + 1 && (z.ntaps & 1) && z.n_out <= ZR_ROW && (z.pos != nullptr || z.n_out == sz) && (reinterpret_cast<uintptr_t>(p.src[i]) & 15) == 0;
+      }
+      if (zrow) {
+        SepZRow zr;
+        memset(&zr, 0, sizeof(zr));
+        for (int i = 0; i < njobs; ++i) {
+          zr.src[i] = p.src[i];
+          zr.dst[i] = p.dst[i];
+          zr.pos[i] = jobs[i].ax[2].pos;
+          zr.taps[i] = jobs[i].ax[2].taps;
+          zr.ntaps[i] = jobs[i].ax[2].ntaps;
+          zr.n_out[i] = p.n_out[i];
+          zr.rows[i] = p.outer[i];
+        }
+        const int want = (max_outer + ZR_THREADS / 32 - 1) / (ZR_THREADS / 32);
+        const int cap = 148 * 3 * 2;  // 3 resident blocks per SM, two waves
+        const dim3 grid((unsigned)(want < cap ? want : cap), njobs);
+        if (inject)
+          sep_zrow_kernel<true><<<grid, ZR_THREADS, 0, s>>>(zr, nz, sz);
+        else
+          sep_zrow_kernel<false><<<grid, ZR_THREADS, 0, s>>>(zr, nz, sz);
+      } else if (maxw <= 8 && a_in >= 8) {
         launch_z<8>(p, nz, njobs, a_in, max_outer, inject, s);
       } else if (maxw <= 16 && a_in >= 16) {
         launch_z<16>(p, nz, njobs, a_in, max_outer, inject, s);

@@ -89,13 +89,16 @@ class SynthEngine:
 
     # ------------------------------------------------------------------ memory
     def scratch(self, name: str, batch: int, dtype=torch.float32, numel=None) -> torch.Tensor:
+        """[batch, numel] scratch rows (grown on demand, never shrunk).  The row pitch is a multiple of 256 bytes so
+        that every row is aligned for the vector kernels whatever the volume extents."""
         numel = self.nvox if numel is None else numel
         key = (name, dtype)
         t = self._scratch.get(key)
         if t is None or t.shape[0] < batch or t.shape[1] < numel:
-            t = torch.empty((batch, numel), dtype=dtype, device=self.device)
+            pitch = (numel + 63) // 64 * 64
+            t = torch.empty((batch, pitch), dtype=dtype, device=self.device)
             self._scratch[key] = t
-        return t
+        return t[:, :numel] if t.shape[1] != numel else t
 
     RING_SLOTS, RING_FLOATS = 8, 1 << 19
 
@@ -331,10 +334,24 @@ class SynthEngine:
         self._call("fsg_blur3d", jobs, B, sx, sy, sz)
 
     # ------------------------------------------------------------------ K4ab (fused)
+    def sep_extents(self, p, positions=True):
+        """Coarse extents of one sample's blur + down-sampling (``positions=False``: plain blur)."""
+        if not positions:
+            return tuple(self.shape)
+        return tuple(resample_size(self.shape[a], self.resolution[a], p.spacing[a]) for a in range(3))
+
+    def sep_capacity(self, p, positions=True):
+        """Floats ``sepconv`` needs behind (dst, tmp1, tmp2) for this sample.  They exceed the volume when an
+        axis is up-sampled (simulated spacing finer than the input resolution, synthseg.py:80-84)."""
+        n = self.sep_extents(p, positions)
+        sx, sy, sz = self.shape
+        return n[0] * n[1] * n[2], n[0] * sy * sz, n[0] * n[1] * sz
+
     def sepconv(self, plans, src, dst, tmp1, tmp2, positions=True):
         """Fused blur + trilinear down-sampling (+noise): plan.stds gives the blur, plan.spacing the
         coarse grid (positions=False: plain blur at full resolution).  tmp1 may alias dst.
-        Returns per-sample (coarse shape, factors) like ``resample``."""
+        Returns per-sample (coarse shape, factors) like ``resample``.  Every buffer must hold what
+        ``sep_capacity`` reports for its sample (checked here and again by the library)."""
         B = len(plans)
         sx, sy, sz = self.shape
         tap_arrays, tap_slot, maxw = [], [], 2
@@ -352,8 +369,14 @@ class SynthEngine:
                     slots.append(None)
             tap_slot.append(slots)
         taps_dev = self.upload(tap_arrays) if tap_arrays else []
-        # workspace per job and axis: float w[nmax][maxw] then int16 q0[nmax]
-        nmax = max(self.shape)
+        extents = [self.sep_extents(p, positions) for p in plans]
+        for b, p in enumerate(plans):
+            need = self.sep_capacity(p, positions)
+            for name, t, n in (("dst", dst[b], need[0]), ("tmp1", tmp1[b], need[1]), ("tmp2", tmp2[b], need[2])):
+                if t.numel() < n:
+                    raise ValueError(f"sepconv: sample {b}: {name} holds {t.numel()} floats, {n} are needed (coarse grid {extents[b]})")
+        # workspace per job and axis: float w[nmax][maxw] then int16 q0[nmax]; an up-sampled axis has more rows than the volume
+        nmax = max(max(self.shape), max(max(n) for n in extents))
         maxw = max(32, (maxw + 3) // 4 * 4)
         per_axis = (nmax * maxw + (nmax + 1) // 2 + 3) // 4 * 4
         ws = self.scratch("sep_tables", B, torch.float32, 3 * per_axis)
@@ -368,7 +391,7 @@ class SynthEngine:
                 n_in = self.shape[a]
                 if positions:
                     t, fac = self.tables.resample(n_in, self.resolution[a], p.spacing[a])
-                    n_out = resample_size(n_in, self.resolution[a], p.spacing[a])
+                    n_out = extents[b][a]
                     cj.pos = t.data_ptr()
                 else:
                     n_out, fac = n_in, 1.0
@@ -381,10 +404,14 @@ class SynthEngine:
                 q_ptr = w_ptr + 4 * nmax * maxw
                 cj.q0_out, cj.w_out = q_ptr, w_ptr
                 cj.ntaps, cj.n_in, cj.n_out, cj.width = ntaps, n_in, n_out, width
-                j.ax[a].q0, j.ax[a].w, j.ax[a].n_out, j.ax[a].width = q_ptr, w_ptr, n_out, width
+                cj.cap_q0, cj.cap_w = nmax, nmax * maxw
+                ax = j.ax[a]
+                ax.q0, ax.w, ax.n_out, ax.width = q_ptr, w_ptr, n_out, width
+                ax.pos, ax.taps, ax.ntaps = cj.pos, cj.taps, ntaps
                 n.append(n_out)
                 factors.append(fac)
             j.src, j.dst, j.tmp1, j.tmp2 = src[b].data_ptr(), dst[b].data_ptr(), tmp1[b].data_ptr(), tmp2[b].data_ptr()
+            j.cap_dst, j.cap_tmp1, j.cap_tmp2 = dst[b].numel(), tmp1[b].numel(), tmp2[b].numel()
             if p.noise_std is not None and positions:
                 j.has_noise, j.noise_std = 1, float(np.float32(p.noise_std))
                 j.noise = _ptr(None if p.noise is None else _check(p.noise, torch.float32, self.device, "noise"))
@@ -541,8 +568,14 @@ class SynthEngine:
         if rs:
             sub = [plans[b] for b in rs]
             # x pass -> buf2, y pass -> buf0 (the GMM image is dead), z pass (+noise) -> buf2
-            info = self.sepconv(sub, [buf1[b] for b in rs], [buf2[b] for b in rs], [buf2[b] for b in rs], [buf0[b] for b in rs])
-            self.zoom([buf2[b] for b in rs], [i[0] for i in info], [1 / i[1] for i in info], [out_img[b].view(-1) for b in rs], post=2 if scale else 1)
+            low, tmp = [buf2[b] for b in rs], [buf0[b] for b in rs]
+            need = [self.sep_capacity(p) for p in sub]
+            if max(max(nd) for nd in need) > self.nvox:  # an up-sampled axis (spacing < resolution): the coarse grid outgrows the volume
+                big_a = self.scratch("sep_big_a", len(rs), numel=max(max(nd[0], nd[1]) for nd in need))
+                big_b = self.scratch("sep_big_b", len(rs), numel=max(nd[2] for nd in need))
+                low, tmp = [big_a[k] for k in range(len(rs))], [big_b[k] for k in range(len(rs))]
+            info = self.sepconv(sub, [buf1[b] for b in rs], low, low, tmp)
+            self.zoom(low, [i[0] for i in info], [1 / i[1] for i in info], [out_img[b].view(-1) for b in rs], post=2 if scale else 1)
         nz = [b for b in no_rs if plans[b].noise_std is not None]
         if nz:
             self.add_noise([plans[b] for b in nz], [buf1[b] for b in nz], [out_img[b].view(-1) for b in nz])

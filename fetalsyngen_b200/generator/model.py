@@ -165,8 +165,9 @@ class FetalSynthGen:
     def _run_augment_tail(self, eng, plan, x):
         """blur + down-sample (+noise) + up-sample (/max), or full-resolution noise."""
         if plan.spacing is not None:
-            low = eng.scratch("buf1", 1)
-            tmp = eng.scratch("buf0", 1)
+            need = eng.sep_capacity(plan)  # exceeds the volume when the spacing is finer than the resolution
+            low = eng.scratch("buf1", 1, numel=max(eng.nvox, need[0], need[1]))
+            tmp = eng.scratch("buf0", 1, numel=max(eng.nvox, need[2]))
             info = eng.sepconv([plan], x, low, low, tmp)
             out = torch.empty_like(x)
             eng.zoom([low[0]], [info[0][0]], [1 / info[0][1]], out, post=1)

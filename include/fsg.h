@@ -128,13 +128,23 @@ int fsg_blur3d(const fsg_blur_job* jobs_host, int njobs, int sx, int sy, int sz,
  * interpolation weights compose into one banded matrix whose rows the host supplies
  * (window start q0 and `width` weights per output; zero weights = zero padding / positions the
  * reference's sampler maps to 0).  With identity positions it is a plain separable blur.
- * Requirements: q0 non-decreasing, 0 <= q0, q0 + width <= n_in.  Passes run x, y, z through
- * tmp1 (>= n_out[0]*sy*sz floats) and tmp2 (>= n_out[0]*n_out[1]*sz floats). */
+ * Requirements: q0 non-decreasing, 0 <= q0, q0 + width <= n_in.
+ * Passes run x, y, z: x  src -> tmp1 [n_out0][sy][sz],  y  tmp1 -> tmp2 [n_out0][n_out1][sz],  z  tmp2 -> dst
+ * (+ noise).  When the z axis is also given uncomposed (`pos` / `taps`, <= 13 taps) and sz <= 256, the last pass
+ * blurs and samples rows in registers instead of applying the composed windows from shared memory; results agree
+ * to the float tolerance.  Philox noise: block = row * ceil(n_out2 / 4) + K / 4 of output row (I, J), component K % 4.
+ * cap_* are the capacities of the buffers in floats: the call fails instead of writing past them (an axis
+ * may be up-sampled, n_out > n_in, when the simulated spacing is finer than the input resolution). */
 typedef struct fsg_sepaxis {
   const int16_t* q0; /* [n_out] first source index of each output's window */
   const float* w;    /* [n_out][width] window weights */
   int32_t n_out;
   int32_t width;
+  /* the same axis before composition (what fsg_sep_compose was given); used by the fused schedule for z */
+  const fsg_tab* pos; /* [n_out] sampling table, NULL = identity positions */
+  const float* taps;  /* [ntaps] Gaussian taps, NULL = no blur */
+  int32_t ntaps;
+  int32_t _pad;
 } fsg_sepaxis;
 typedef struct fsg_sepconv_job {
   const float* src;  /* [sx][sy][sz] */
@@ -146,6 +156,7 @@ typedef struct fsg_sepconv_job {
   fsg_rng rng;
   float noise_std;
   int32_t has_noise;
+  int64_t cap_dst, cap_tmp1, cap_tmp2; /* floats available behind dst / tmp1 / tmp2 */
 } fsg_sepconv_job;
 int fsg_sepconv(const fsg_sepconv_job* jobs_host, int njobs, int sx, int sy, int sz, void* stream);
 
@@ -160,6 +171,7 @@ typedef struct fsg_sepcompose_job {
   int16_t* q0_out; /* [n_out] */
   float* w_out;    /* [n_out][width] */
   int32_t ntaps, n_in, n_out, width;
+  int32_t cap_q0, cap_w; /* entries available behind q0_out / w_out (>= n_out, >= n_out*width) */
 } fsg_sepcompose_job;
 int fsg_sep_compose(const fsg_sepcompose_job* jobs_host, int njobs, void* stream);
 

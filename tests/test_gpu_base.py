@@ -269,6 +269,43 @@ def test_base_pipeline_vs_oracle_random(shape, seed):
     assert rel_err(img[0], want_img) <= TOL
 
 
+@pytest.mark.parametrize("shape,res,spacing", [((48, 40, 56), 1.0, 0.6), ((33, 47, 29), 1.0, 0.75), ((64, 64, 64), 0.8, 0.5)])
+def test_resolution_simulation_with_spacing_finer_than_the_resolution(shape, res, spacing):
+    """spacing < resolution: the reference zeroes the blur and UP-samples (synthseg.py:78-84), so the coarse grid
+    outgrows the volume (n_out > n_in on every axis).  Both schedules (z+y fused: extents divisible by 4; generic:
+    odd extents) against the oracle, in a batch next to an ordinary down-sampling sample whose buffers follow
+    directly behind (an overrun of the scratch rows would corrupt it)."""
+    from fetalsyngen_b200.tables import resample_size, resample_stds
+
+    rs = np.random.RandomState(int(spacing * 100))
+    seg, seeds = _phantom(rs, shape)
+    eng = engine_for(DEV, shape, (res, res, res))
+    plans, want = [], []
+    for sp in (spacing, 1.7 * res):
+        p = _random_plan(rs, shape, DEV)
+        p.spacing = np.array([sp] * 3)
+        p.stds = resample_stds(p.spacing, [res] * 3, rs.rand())
+        n = [resample_size(v, res, sp) for v in shape]
+        assert (sp >= res) or all(n[a] > shape[a] for a in range(3))
+        p.noise = torch.from_numpy(rs.randn(int(np.prod(n))).astype(np.float32)).to(DEV)
+        q = _plan_to_oracle(p)
+        q["resolution"] = np.array([res] * 3)
+        q["noise"] = p.noise.cpu().numpy().reshape(n)
+        q["gmm_noise"] = q["gmm_noise"].reshape(shape)
+        plans.append(p)
+        want.append(O.generate_base(sum(s_.astype(np.int64) for s_ in seeds), seg, q)[:2])
+    dseeds = [torch.from_numpy(s_).to(DEV).view(-1) for s_ in seeds]
+    dseg = torch.from_numpy(seg).to(DEV).view(-1)
+    img, sg = eng.run_base(plans, [dseeds] * 2, [dseg] * 2)
+    for b in range(2):
+        np.testing.assert_array_equal(sg[b].cpu().numpy(), want[b][1])
+        assert rel_err(img[b], want[b][0]) <= TOL
+    # the per-sample API (FetalSynthGen.augment's tail) sizes its own scratch
+    too_small = torch.empty((1, eng.nvox), dtype=torch.float32, device=DEV)
+    with pytest.raises((ValueError, Exception)):
+        eng.sepconv([plans[0]], too_small.clone(), too_small, too_small, too_small.clone())
+
+
 def test_batched_launch_equals_single_launches():
     shape = (48, 40, 56)
     rs = np.random.RandomState(5)
