@@ -28,7 +28,7 @@ class Rng(C.Structure):
 
 class GmmJob(C.Structure):
     _fields_ = [("seed", _vp * 4), ("mus", _vp), ("sigmas", _vp), ("noise", _vp), ("out", _vp), ("labels_out", _vp),
-                ("rng", Rng), ("nlabels", _i32), ("row_len", _i32), ("out_pairs", _vp), ("pairs_float", _i32), ("_pad", _i32)]
+                ("rng", Rng), ("nlabels", _i32), ("row_len", _i32), ("out_pairs", _vp), ("pairs_float", _i32), ("word_bytes", _i32), ("words", _vp), ("shift", _i32 * 4), ("mask", _i32 * 4)]
 
 
 class WarpJob(C.Structure):

@@ -10,7 +10,15 @@ namespace fsg {
 constexpr int GMM_THREADS = 256;
 constexpr int GMM_MAX_LABELS = 256;
 
-// NSEED = number of leading non-NULL seed pointers (the host entry compacts them).
+// Label of one packed seed word (fsg_unpack_job): tab[m] = shift | mask << 8 | base << 16, selected by the 3-bit meta field.
+__device__ __forceinline__ uint32_t decode_word(uint32_t w, const uint32_t (&tab)[5]) {
+  const uint32_t m = w & 7u;
+  const uint32_t t = m == 1 ? tab[1] : (m == 2 ? tab[2] : (m == 3 ? tab[3] : (m == 4 ? tab[4] : 0u)));
+  return (t >> 16) + ((w >> (t & 0xffu)) & ((t >> 8) & 0xffu));
+}
+
+// NSEED = number of leading non-NULL seed pointers (the host entry compacts them); NSEED == 0: packed mode, the
+// labels are decoded from job.words (uint16 when job.word_bytes == 2, else uint32).
 template <bool INJECT, int NSEED>
 __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant__ Batch<fsg_gmm_job> batch, int64_t nvox) {
   const fsg_gmm_job& job = batch.j[blockIdx.y];
@@ -23,6 +31,18 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
   __shared__ float s_first[2][GMM_THREADS];  // first value of every thread's group (pairs output), double-buffered
 
   const int8_t* __restrict__ sp[4] = {job.seed[0], job.seed[1], job.seed[2], job.seed[3]};
+  uint32_t wtab[5] = {0, 0, 0, 0, 0};
+  if (NSEED == 0) {
+#pragma unroll
+    for (int m = 1; m <= 4; ++m) wtab[m] = (uint32_t)job.shift[m - 1] | ((uint32_t)job.mask[m - 1] << 8) | ((uint32_t)(10 * m) << 16);
+  }
+  const bool w16 = job.word_bytes == 2;
+  auto label_at = [&](int64_t v) -> int {  // scalar path (block tails)
+    if (NSEED == 0) return (int)decode_word(w16 ? (uint32_t)static_cast<const uint16_t*>(job.words)[v] : static_cast<const uint32_t*>(job.words)[v], wtab);
+    int l = 0;
+    for (int m = 0; m < NSEED; ++m) l += sp[m][v];
+    return l;
+  };
   const float* __restrict__ noise = job.noise;
   float* __restrict__ out = job.out;
   uint8_t* __restrict__ lab_out = job.labels_out;
@@ -41,6 +61,15 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
     const int64_t v0 = g * 4;
     // labels of the seed volumes are disjoint small non-negative codes: one byte-wise SIMD add sums 4 voxels
     uint32_t lab4 = 0;
+    if (NSEED == 0) {
+      if (w16) {
+        const uint2 q = __ldcs(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(job.words) + v0));
+        lab4 = decode_word(q.x & 0xffffu, wtab) | (decode_word(q.x >> 16, wtab) << 8) | (decode_word(q.y & 0xffffu, wtab) << 16) | (decode_word(q.y >> 16, wtab) << 24);
+      } else {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(job.words) + v0));
+        lab4 = decode_word(q.x, wtab) | (decode_word(q.y, wtab) << 8) | (decode_word(q.z, wtab) << 16) | (decode_word(q.w, wtab) << 24);
+      }
+    }
 #pragma unroll
     for (int m = 0; m < NSEED; ++m) lab4 = __vadd4(lab4, __ldcs(reinterpret_cast<const uint32_t*>(sp[m] + v0)));
     float4 n;
@@ -70,8 +99,7 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
           if (threadIdx.x + 1 < GMM_THREADS) {
             nxt = s_first[it][threadIdx.x + 1];
           } else {
-            int l = 0;
-            for (int m = 0; m < NSEED; ++m) l += sp[m][v4];
+            const int l = label_at(v4);
             const float nz = INJECT ? noise[v4] : philox_normal4(rng, (uint32_t)(g + 1)).x;
             const float2 ms = s_ms[l & (GMM_MAX_LABELS - 1)];
             nxt = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
@@ -103,8 +131,7 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
       nn[0] = q.x; nn[1] = q.y; nn[2] = q.z; nn[3] = q.w;
     }
     for (int e = 0; v0 + e < nvox; ++e) {
-      int l = 0;
-      for (int m = 0; m < NSEED; ++m) l += sp[m][v0 + e];
+      const int l = label_at(v0 + e);
       const float nz = INJECT ? noise[v0 + e] : nn[e];
       const float2 ms = s_ms[l & (GMM_MAX_LABELS - 1)];
       if (out) out[v0 + e] = fmaxf(add_rn(ms.x, mul_rn(ms.y, nz)), 0.f);
@@ -198,6 +225,7 @@ extern "C" int fsg_draw_grids(const fsg_grid_job* jobs, int njobs, void* stream)
 template <bool INJECT>
 static void launch_gmm(const Batch<fsg_gmm_job>& b, int nseed, dim3 grid, int64_t nvox, cudaStream_t s) {
   switch (nseed) {
+    case 0: gmm_kernel<INJECT, 0><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
     case 1: gmm_kernel<INJECT, 1><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
     case 2: gmm_kernel<INJECT, 2><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
     case 3: gmm_kernel<INJECT, 3><<<grid, GMM_THREADS, 0, s>>>(b, nvox); break;
@@ -222,13 +250,21 @@ extern "C" int fsg_gmm(const fsg_gmm_job* jobs, int njobs, int64_t nvox, void* s
     FSG_REQUIRE((j.noise != nullptr) == inject, "fsg_gmm: jobs mix injected and Philox noise");
     // compact the seed pointers of the launch copy to the front
     int n = 0;
-    for (int m = 0; m < 4; ++m)
-      if (j.seed[m]) b.j[i].seed[n++] = j.seed[m];
-    for (int m = n; m < 4; ++m) b.j[i].seed[m] = nullptr;
-    FSG_REQUIRE(n >= 1, "fsg_gmm: job %d has no seed volume", i);
-    FSG_REQUIRE(nseed < 0 || nseed == n, "fsg_gmm: jobs of one launch must have the same number of seed volumes");
+    if (j.words) {  // packed mode: labels decoded from the subject's seed words
+      FSG_REQUIRE(j.word_bytes == 2 || j.word_bytes == 4, "fsg_gmm: job %d: word_bytes must be 2 or 4", i);
+      FSG_REQUIRE((reinterpret_cast<uintptr_t>(j.words) & 15) == 0, "fsg_gmm: job %d: words must be 16-byte aligned", i);
+      for (int m = 0; m < 4; ++m)
+        FSG_REQUIRE(j.shift[m] >= 0 && j.shift[m] < 8 * j.word_bytes && j.mask[m] >= 0 && j.mask[m] <= 15, "fsg_gmm: job %d: bad field for meta-label %d", i, m + 1);
+      for (int m = 0; m < 4; ++m) b.j[i].seed[m] = nullptr;
+    } else {
+      for (int m = 0; m < 4; ++m)
+        if (j.seed[m]) b.j[i].seed[n++] = j.seed[m];
+      for (int m = n; m < 4; ++m) b.j[i].seed[m] = nullptr;
+      FSG_REQUIRE(n >= 1, "fsg_gmm: job %d has no seed volume", i);
+    }
+    FSG_REQUIRE(nseed < 0 || nseed == n, "fsg_gmm: jobs of one launch must have the same number of seed volumes (or all be packed)");
     nseed = n;
-    for (int m = 0; m < 4; ++m) FSG_REQUIRE((reinterpret_cast<uintptr_t>(j.seed[m]) & 3) == 0, "fsg_gmm: seed pointers must be 4-byte aligned");
+    for (int m = 0; m < 4 && !j.words; ++m) FSG_REQUIRE((reinterpret_cast<uintptr_t>(j.seed[m]) & 3) == 0, "fsg_gmm: seed pointers must be 4-byte aligned");
     FSG_REQUIRE((reinterpret_cast<uintptr_t>(j.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.noise) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.labels_out) & 3) == 0,
                 "fsg_gmm: out/noise must be 16-byte aligned");
   }

@@ -21,6 +21,7 @@ import torch
 
 from ..generator.model import FetalSynthGen
 from ..utils.image_reading import SimpleITKReader
+from ..utils.lru import ByteLRU
 
 
 class BidsIndex:
@@ -131,13 +132,46 @@ class FetalSynthDataset(FetalDataset):
         self.load_image = load_image
         self.generator = generator
         self.image_as_intensity = image_as_intensity
-        self._seg_cache: dict = {}
         self.packed_cache = Path(packed_cache) if packed_cache is not None else None
-        self._packed: dict = {}
+        self._init_caches()
         if not self.image_as_intensity and isinstance(self.seed_path, Path):
             if not self.seed_path.exists():
                 raise FileNotFoundError(f"Provided seed path {self.seed_path} does not exist.")
             self._load_seed_path()
+
+    @classmethod
+    def from_packed(cls, packed_cache: str, generator: FetalSynthGen, sub_list: list[str] | None = None) -> "FetalSynthDataset":
+        """Dataset over a directory of bit-packed subject files alone (``<subject>[_<session>].fsgpack.npz``, written by
+        ``tools/pack_dataset.py`` or on first use of ``packed_cache=``): no BIDS tree and no NIfTI decoding at all —
+        what a training job ships to its nodes.  ``sample`` / ``sample_batch`` / ``DeviceBatchLoader`` work as usual."""
+        self = cls.__new__(cls)
+        self.bids_path, self.seed_path = None, Path(packed_cache)
+        self.packed_cache = Path(packed_cache)
+        files = sorted(self.packed_cache.glob("*.fsgpack.npz"))
+        names = [f.name[: -len(".fsgpack.npz")] for f in files]
+        if sub_list is not None:
+            names = [n for n in names if n.split("_ses-")[0] in set(sub_list)]
+        if not names:
+            raise FileNotFoundError(f"No *.fsgpack.npz subject files under {packed_cache}")
+        self.sub_ses = [tuple(n.split("_", 1)) if "_ses-" in n else (n, None) for n in names]
+        self.subjects = sorted({sub for sub, _ in self.sub_ses})
+        self.loader = SimpleITKReader()
+        self.img_paths = [None] * len(self.sub_ses)
+        self.segm_paths = [None] * len(self.sub_ses)
+        self.seed_paths = {}
+        self.load_image = self.image_as_intensity = self._needs_images = False
+        self.generator = generator
+        self._init_caches()
+        return self
+
+    def _init_caches(self, budget_gb: float | None = None):
+        """Device-resident subject caches (uint8 segmentation: 16 MiB, packed seed words: 32 MiB per 256^3 subject),
+        least recently used subjects dropped beyond ``FSG_SUBJECT_CACHE_GB`` (default 32) per process."""
+        import os
+
+        gb = float(os.environ.get("FSG_SUBJECT_CACHE_GB", "32")) if budget_gb is None else budget_gb
+        self._seg_cache = ByteLRU(int(gb * 2**30 / 3))
+        self._packed = ByteLRU(int(gb * 2**30 * 2 / 3))
 
     def _load_seed_path(self):
         """{sub_ses: {n_subclasses: {meta_label: path}}} (datasets.py:246-270)."""
@@ -166,10 +200,12 @@ class FetalSynthDataset(FetalDataset):
             name = self._sub_ses_string(*self.sub_ses[idx])
             f = self.packed_cache / f"{name}.fsgpack.npz"
             if not f.exists():
+                if self.segm_paths[idx] is None:
+                    raise FileNotFoundError(f"{f} is missing and there is no BIDS tree to convert it from")
                 pack_subject(self.segm_paths[idx], self.seed_paths[name], f)
             seg, seeds, _ = load_packed(f)
             hit = (seg, seeds)
-            self._packed[idx] = hit
+            self._packed.put(idx, hit, seg.nbytes + int(np.prod(seeds.shape)) * seeds.word_bytes)
         return hit
 
     def _seeds(self, idx):
@@ -184,11 +220,13 @@ class FetalSynthDataset(FetalDataset):
         if seg is None and self.packed_cache is not None and not self.image_as_intensity and self.seed_path is not None:
             raw = torch.from_numpy(self._packed_subject(idx)[0])
             seg = raw.to(self.generator.engine(tuple(raw.shape)).device).contiguous()
-            self._seg_cache[idx] = seg
+            self._seg_cache.put(idx, seg, seg.numel())
         if seg is None:
-            raw = self.loader(self.segm_paths[idx])
+            raw = torch.nan_to_num(self.loader(self.segm_paths[idx]).float())
+            if raw.numel() and (float(raw.min()) < 0 or float(raw.max()) > 255 or not torch.equal(raw, raw.round())):
+                raise ValueError(f"{self.segm_paths[idx]}: labels are not integers in 0..255 (uint8 label maps only)")
             seg = raw.to(torch.uint8).to(self.generator.engine(tuple(raw.shape)).device).contiguous()
-            self._seg_cache[idx] = seg
+            self._seg_cache.put(idx, seg, seg.numel())
         return seg
 
     # ------------------------------------------------------------------ reference API
@@ -245,15 +283,26 @@ class FetalSynthDataset(FetalDataset):
         return data
 
     # ------------------------------------------------------------------ device fast path
-    def sample_batch(self, indices, scale: bool = True):
+    def sample_batch(self, indices, scale: bool = True, out_img=None, out_seg=None, sample_ids=None, base_seed: int | None = None):
         """Generate ``len(indices)`` samples with batched launches.  Returns
         ``{"image": (B,1,H,W,D) float32, "label": (B,1,H,W,D) uint8, "name": [...]}`` on the
-        generator's device plus the list of per-sample parameter dictionaries."""
+        generator's device plus the list of per-sample parameter dictionaries.
+
+        All parameters of the batch are drawn at once (``batch_draw.py``) as a function of (base seed, sample id).
+        Without ``sample_ids`` the dataset numbers its samples itself and takes the base seed from numpy's global
+        generator on first use, so ``np.random.seed(s)`` before the first call still fixes the whole stream."""
         if self.image_as_intensity or self.seed_path is None:
             raise ValueError("sample_batch needs seed-based intensity generation")
+        if sample_ids is None:
+            if getattr(self, "_batch_seed", None) is None:
+                self._batch_seed, self._batch_next = int(np.random.randint(0, 2**31 - 1)), 0
+            sample_ids = list(range(self._batch_next, self._batch_next + len(indices)))
+            self._batch_next += len(indices)
+            base_seed = self._batch_seed
         segs = [self._segmentation(i) for i in indices]
         names = [self._sub_ses_string(*self.sub_ses[i]) for i in indices]
-        img, seg, params = self.generator.sample_batch(segs, [self._seeds(i) for i in indices], scale=scale)
+        img, seg, params = self.generator.sample_batch(segs, [self._seeds(i) for i in indices], scale=scale, out_img=out_img, out_seg=out_seg, sample_ids=sample_ids,
+                                                       base_seed=int(base_seed or 0))
         return {"image": img.unsqueeze(1), "label": seg.unsqueeze(1), "name": names}, params
 
 
@@ -280,6 +329,7 @@ class DeviceBatchLoader:
         self.num_batches = num_batches if num_batches is not None else max(1, len(dataset) // self.B)
         self.shuffle, self.labels_int64 = shuffle, labels_int64
         self.base_seed, self.rank, self.world = base_seed, rank, world
+        self.epoch = 0  # advanced by every ``__iter__`` (or ``set_epoch``): epochs draw different samples
         gen = dataset.generator
         self.shape = tuple(gen.shape)
         self.eng = gen.engine(self.shape)
@@ -298,16 +348,24 @@ class DeviceBatchLoader:
         n = len(self.ds)
         return [int(v) for v in (rs.randint(0, n, self.B) if self.shuffle else [(step * self.B + k) % n for k in range(self.B)])]
 
-    def _produce(self, step, slot, rs):
+    def set_epoch(self, epoch: int):
+        """Reproducibility contract with ``base_seed``: sample k of step s of epoch e has id
+        ``(e * num_batches + s) * B * world + k * world + rank`` and every draw is a function of (base_seed, id), so a
+        run is reproducible, independent of the sharding, and no two epochs repeat a sample.  The subject indices of
+        an epoch come from ``RandomState((base_seed, rank, epoch))``."""
+        self.epoch = int(epoch)
+
+    def _produce(self, step, slot, rs, epoch):
         from ..sharding import step_ids
 
         idx = self._indices(step, rs)
-        segs = [self.ds._segmentation(i) for i in idx]
         names = [self.ds._sub_ses_string(*self.ds.sub_ses[i]) for i in idx]
         kw = {}
         if self.base_seed is not None:  # reproducible, sharding-independent sample streams
-            kw = {"sample_ids": step_ids(step, self.B, self.rank, self.world), "base_seed": self.base_seed}
+            kw = {"sample_ids": step_ids(epoch * self.num_batches + step, self.B, self.rank, self.world), "base_seed": self.base_seed}
         with torch.cuda.stream(self.stream):
+            # first-use uploads of a subject (segmentation, packed words) are enqueued on the producer stream too
+            segs = [self.ds._segmentation(i) for i in idx]
             if self._released[slot] is not None:
                 self.stream.wait_event(self._released[slot])
             _, _, params = self.ds.generator.sample_batch(segs, [self.ds._seeds(i) for i in idx], scale=True, out_img=self._img[slot], out_seg=self._seg[slot], **kw)
@@ -318,13 +376,15 @@ class DeviceBatchLoader:
         return done, names, params
 
     def __iter__(self):
-        rs = np.random.RandomState(None if self.base_seed is None else self.base_seed + 7919 * self.rank)
-        pending = self._produce(0, 0, rs)
+        epoch = self.epoch
+        self.epoch += 1
+        rs = np.random.RandomState(None if self.base_seed is None else [self.base_seed & 0xFFFFFFFF, self.rank, epoch])
+        pending = self._produce(0, 0, rs, epoch)
         for step in range(self.num_batches):
             slot = step % self.depth
             done, names, params = pending
             if step + 1 < self.num_batches:
-                pending = self._produce(step + 1, (step + 1) % self.depth, rs)
+                pending = self._produce(step + 1, (step + 1) % self.depth, rs, epoch)
             cur = torch.cuda.current_stream()
             cur.wait_event(done)
             label = self._lab[slot] if self._lab is not None else self._seg[slot]

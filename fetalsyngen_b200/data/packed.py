@@ -183,13 +183,13 @@ def load_packed(path):
 def pack_subject(seg_path, seed_paths: dict, out_file, verify: bool = True):
     """One-time converter for one subject: ``seed_paths[n][m]`` NIfTI paths + the segmentation ->
     ``out_file`` (.npz).  ``verify`` re-derives every seed volume from the packed words before writing."""
-    from ..utils.nifti import read_nifti
+    from ..utils.nifti import read_nifti, to_ras
 
-    seg, affine = read_nifti(seg_path, with_affine=True)
+    seg, affine = to_ras(*read_nifti(seg_path, with_affine=True))  # the cache holds RAS-oriented volumes, like the reference feeds its generator
     seg_f = np.nan_to_num(np.asarray(seg, dtype=np.float32))
     if seg_f.min() < 0 or seg_f.max() > 255 or not np.array_equal(seg_f, np.round(seg_f)):
         raise ValueError(f"{seg_path}: labels are not integers in 0..255")
-    vols = {int(n): {int(m): read_nifti(p) for m, p in per.items()} for n, per in seed_paths.items()}
+    vols = {int(n): {int(m): to_ras(*read_nifti(p, with_affine=True))[0] for m, p in per.items()} for n, per in seed_paths.items()}
     words, counts = pack_seed_volumes(vols)
     if words.shape != seg_f.shape:
         raise ValueError(f"{seg_path}: segmentation {seg_f.shape} and seeds {words.shape} differ in shape")

@@ -116,9 +116,11 @@ class SynthEngine:
         if events[slot] is not None:
             events[slot].synchronize()
         self._batch = {"slot": slot, "used": 0, "calls": [], "keep": []}
+        self.tables.hold = True
 
     def flush(self):
         b, self._batch = self._batch, None
+        self.tables.hold = False
         hring, dring, events, _ = self._ring
         stream = _stream()
         if b["used"]:
@@ -194,23 +196,40 @@ class SynthEngine:
 
     # ------------------------------------------------------------------ K1
     def gmm(self, plans, seeds, out: torch.Tensor, labels_out=None, pairs=None):
-        """seeds[b]: list of 1..4 int8/uint8 device volumes summed into the label map.  pairs[b] True:
-        sample b is written in the fixed-point pairs format of the warp fast path (same 4 bytes per
-        voxel, into the same buffer) instead of float32."""
+        """seeds[b]: list of 1..4 int8/uint8 device volumes summed into the label map, or ``(PackedSeeds,
+        mlabel2subclusters)``: the labels are decoded in the kernel from the subject's bit-packed seed words
+        (2 bytes per voxel, no unpack pass).  pairs[b] True: sample b is written in the fixed-point pairs format
+        of the warp fast path (same 4 bytes per voxel, into the same buffer) instead of float32."""
         B = len(plans)
         nvox = int(out.shape[-1]) if torch.is_tensor(out) else self.nvox  # a list mixes [N] outputs and [2N] float-pair outputs
         small = self.upload([p.mus for p in plans] + [p.sigmas for p in plans])
         jobs = (_lib.GmmJob * B)()
+        kinds = []
         for b, p in enumerate(plans):
             j = jobs[b]
-            vols = list(seeds[b])
-            if not 1 <= len(vols) <= 4:
-                raise ValueError("each sample needs 1..4 seed volumes")
-            for m, v in enumerate(vols):
-                if v.dtype not in (torch.int8, torch.uint8) or v.numel() != nvox:
-                    raise TypeError("seed volumes must be int8/uint8 tensors with one label per output voxel")
-                _check(v, v.dtype, self.device, "seed volume")
-                j.seed[m] = v.data_ptr()
+            sd = seeds[b]
+            if isinstance(sd, tuple):  # (PackedSeeds, mlabel2subclusters)
+                ps, m2s = sd
+                if int(np.prod(ps.shape)) != nvox:
+                    raise ValueError("packed seed words must hold one word per output voxel")
+                words = ps.on(self.device)
+                for m in range(1, 5):
+                    n = int(m2s[m])
+                    if n not in ps.layout:
+                        raise KeyError(f"no seeds with {n} sub-classes in this cache (available: {ps.counts})")
+                    j.shift[m - 1], j.mask[m - 1] = ps.layout[n]
+                j.words, j.word_bytes = words.data_ptr(), ps.word_bytes
+                kinds.append(0)
+            else:
+                vols = list(sd)
+                if not 1 <= len(vols) <= 4:
+                    raise ValueError("each sample needs 1..4 seed volumes")
+                for m, v in enumerate(vols):
+                    if v.dtype not in (torch.int8, torch.uint8) or v.numel() != nvox:
+                        raise TypeError("seed volumes must be int8/uint8 tensors with one label per output voxel")
+                    _check(v, v.dtype, self.device, "seed volume")
+                    j.seed[m] = v.data_ptr()
+                kinds.append(len(vols))
             j.mus, j.sigmas = small[b].data_ptr(), small[B + b].data_ptr()
             j.nlabels = int(p.mus.size)
             j.noise = _ptr(None if p.gmm_noise is None else _check(p.gmm_noise, torch.float32, self.device, "gmm_noise"))
@@ -221,7 +240,16 @@ class SynthEngine:
                 j.out = out[b].data_ptr()
             j.labels_out = None if labels_out is None else labels_out[b].data_ptr()
             j.rng = _lib.Rng(p.rng_seed & (2**64 - 1), p.sample_id, STAGE_GMM, 0)
-        self._call("fsg_gmm", jobs, B, nvox)
+        # one launch per kind of label source and noise source (a launch needs them uniform); production batches have one
+        groups: dict = {}
+        for b, k in enumerate(kinds):
+            groups.setdefault((k, plans[b].gmm_noise is not None), []).append(b)
+        if len(groups) == 1:
+            self._call("fsg_gmm", jobs, B, nvox)
+        else:
+            for idx in groups.values():
+                sub = (_lib.GmmJob * len(idx))(*[jobs[b] for b in idx])
+                self._call("fsg_gmm", sub, len(idx), nvox)
         self._keep = (small,)
 
     # ------------------------------------------------------------------ K2
@@ -542,6 +570,7 @@ class SynthEngine:
             self._run_base(plans, seeds, segs, out_img, out_seg, scale, buf0, buf1, buf2)
         except BaseException:
             self._batch = None
+            self.tables.hold = False
             raise
         self.flush()
         return out_img, out_seg
@@ -589,11 +618,15 @@ _ENGINES: dict = {}
 
 
 def engine_for(device, shape, resolution=(1.0, 1.0, 1.0)) -> SynthEngine:
-    """Process-wide engine cache keyed by (device, shape, resolution)."""
+    """Process-wide engine cache keyed by (device, shape, resolution, current CUDA stream).  An engine's scratch
+    volumes, workspace and parameter ring are ordered by stream order alone, so every stream that generates
+    (a ``DeviceBatchLoader``'s producer stream next to the consumer's default stream, a second loader, ...) gets
+    its own engine: nothing is shared across streams, no cross-stream events are needed."""
     dev = torch.device(device)
     if dev.type == "cuda" and dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
-    key = (str(dev), tuple(int(s) for s in shape), tuple(float(r) for r in resolution))
+    stream = torch.cuda.current_stream(dev).cuda_stream if (dev.type == "cuda" and torch.cuda.is_available()) else 0
+    key = (str(dev), tuple(int(s) for s in shape), tuple(float(r) for r in resolution), int(stream))
     eng = _ENGINES.get(key)
     if eng is None:
         eng = SynthEngine(shape, resolution, dev)

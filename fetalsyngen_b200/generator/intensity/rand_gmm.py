@@ -4,13 +4,15 @@ signatures as the reference's ``ImageFromSeeds``
 ``fsg_gmm`` kernel (seed sum + label->(mu,sigma) lookup + noise + clamp in one pass)."""
 from __future__ import annotations
 
+import os
 from pathlib import Path
 from typing import Iterable
 
 import numpy as np
 import torch
 
-from ...utils.nifti import read_nifti
+from ...utils.lru import ByteLRU
+from ...utils.nifti import read_nifti, to_ras
 
 
 class ImageFromSeeds:
@@ -32,7 +34,9 @@ class ImageFromSeeds:
         self.seed_labels = seed_labels
         self.generation_classes = generation_classes
         self.meta_labels = meta_labels
-        self._cache: dict = {}  # (path, device) -> int8 device volume
+        # (path, device) -> int8 device volume; least recently used volumes are dropped beyond the byte budget
+        # (24 volumes = 384 MiB per 256^3 subject; the bit-packed subject cache needs 32 MiB instead)
+        self._cache = ByteLRU(int(float(os.environ.get("FSG_SEED_CACHE_GB", "16")) * 2**30))
 
     # ------------------------------------------------------------------ host draws
     def draw_subclusters(self, mlabel2subclusters=None, genparams: dict = {}) -> dict:
@@ -72,13 +76,13 @@ class ImageFromSeeds:
         key = (str(path), str(device))
         vol = self._cache.get(key)
         if vol is None:
-            arr = read_nifti(path)
+            arr, _ = to_ras(*read_nifti(path, with_affine=True))  # rand_gmm.py:91-96: seeds are reoriented to RAS too
             if arr.dtype != np.int8:
                 if arr.min() < -128 or arr.max() > 127:
                     raise ValueError(f"{path}: seed labels do not fit int8")
                 arr = arr.astype(np.int8)
             vol = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
-            self._cache[key] = vol
+            self._cache.put(key, vol, vol.numel() * vol.element_size())
         return vol
 
     def select_seeds(self, seeds, mlabel2subclusters: dict, device) -> list[torch.Tensor]:

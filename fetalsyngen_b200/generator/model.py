@@ -265,7 +265,10 @@ class FetalSynthGen:
             for b, sd in enumerate(seeds):
                 if isinstance(sd, (dict, PackedSeeds)):
                     m2s = {m: int(out[2][b, m - 1]) for m in range(1, self.intensity_generator.meta_labels + 1)}
-                    vols.append([v.view(-1) for v in self.intensity_generator.select_seeds(sd, m2s, eng.device)])
+                    if isinstance(sd, PackedSeeds):
+                        vols.append((sd, m2s))  # labels decoded inside fsg_gmm from the packed words
+                    else:
+                        vols.append([v.view(-1) for v in self.intensity_generator.select_seeds(sd, m2s, eng.device)])
                     params[b]["selected_seeds"] = {"mlabel2subclusters": m2s}
                 else:
                     vols.append([v.view(-1) for v in sd])

@@ -19,17 +19,18 @@ import torch
 
 
 class _Slot:
-    def __init__(self, batch, shape, dev, word_dtype=None):
+    def __init__(self, batch, shape, dev, word_dtype=None, inputs: bool = True):
         shp = (batch, *shape)
-        self.h_seg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
-        if word_dtype is None:
-            self.h_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, pin_memory=True)
-        else:  # bit-packed seed words of the subject cache (data/packed.py): one word per voxel instead of 4 bytes
-            self.h_seeds = torch.empty(shp, dtype=word_dtype, pin_memory=True)
+        if inputs:
+            self.h_seg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
+            if word_dtype is None:
+                self.h_seeds = torch.empty((batch, 4, *shape), dtype=torch.int8, pin_memory=True)
+            else:  # bit-packed seed words of the subject cache (data/packed.py): one word per voxel instead of 4 bytes
+                self.h_seeds = torch.empty(shp, dtype=word_dtype, pin_memory=True)
+            self.d_seg = torch.empty(shp, dtype=torch.uint8, device=dev)
+            self.d_seeds = torch.empty(self.h_seeds.shape, dtype=self.h_seeds.dtype, device=dev)
         self.h_img = torch.empty(shp, dtype=torch.float32, pin_memory=True)
         self.h_oseg = torch.empty(shp, dtype=torch.uint8, pin_memory=True)
-        self.d_seg = torch.empty(shp, dtype=torch.uint8, device=dev)
-        self.d_seeds = torch.empty(self.h_seeds.shape, dtype=self.h_seeds.dtype, device=dev)
         self.d_img = torch.empty(shp, dtype=torch.float32, device=dev)
         self.d_oseg = torch.empty(shp, dtype=torch.uint8, device=dev)
         self.in_free = None    # compute of the previous use has consumed d_seg / d_seeds
@@ -151,6 +152,67 @@ class HostPipeline:
                 if on_result is not None:
                     on_result(*r)
             self.submit(scale, **kw)
+        while self._inflight:
+            r = self.collect()
+            if on_result is not None:
+                on_result(*r)
+
+
+class DatasetPipeline:
+    """``FetalSynthDataset.sample_batch(indices)`` with host tensors out — the reference's entry point takes a
+    subject *index* (``fetalsyngen/data/datasets.py:256``) and returns ``.cpu()`` tensors (``:315-317``).  The
+    subject cache (uint8 segmentation + bit-packed seed words) stays resident on the device, so a step moves
+    only its indices host->device and its image + segmentation (80 MiB per 256^3 volume) device->host; generation
+    of step k+1 overlaps the read-back of step k through ``depth`` rotating buffer sets."""
+
+    def __init__(self, dataset, batch: int, depth: int = 2):
+        self.ds, self.B = dataset, batch
+        gen = dataset.generator
+        self.shape = tuple(gen.shape)
+        dev = gen.engine(self.shape).device
+        self.slots = [_Slot(batch, self.shape, dev, inputs=False) for _ in range(max(1, depth))]
+        self.s_out = torch.cuda.Stream(device=dev)
+        self.h2d_bytes = 8 * batch  # the indices
+        self.d2h_bytes = self.slots[0].h_img.numel() * 4 + self.slots[0].h_oseg.numel()
+        self._next = 0
+        self._inflight: deque = deque()
+
+    def submit(self, indices, scale: bool = True, **kw):
+        if len(self._inflight) == len(self.slots):
+            raise RuntimeError("DatasetPipeline: every slot is in flight; call collect() first")
+        if len(indices) != self.B:
+            raise ValueError(f"expected {self.B} indices")
+        s = self.slots[self._next % len(self.slots)]
+        self._next += 1
+        cur = torch.cuda.current_stream()
+        if s.out_done is not None:
+            cur.wait_event(s.out_done)  # d_img / d_oseg of this slot are being read by the last D2H
+        out, s.params = self.ds.sample_batch(indices, scale=scale, out_img=s.d_img, out_seg=s.d_oseg, **kw)
+        s.names = out["name"]
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            s.h_img.copy_(s.d_img, non_blocking=True)
+            s.h_oseg.copy_(s.d_oseg, non_blocking=True)
+            s.out_done = torch.cuda.Event()
+            s.out_done.record(self.s_out)
+        self._inflight.append(s)
+
+    def collect(self):
+        """Block until the oldest submitted step is in host memory: (image, segmentation, params) — views of
+        that slot's pinned buffers, valid until the slot is submitted again."""
+        s = self._inflight.popleft()
+        s.out_done.synchronize()
+        return s.h_img, s.h_oseg, s.params
+
+    def run(self, index_batches, scale: bool = True, on_result=None, **kw):
+        for indices in index_batches:
+            if len(self._inflight) == len(self.slots):
+                r = self.collect()
+                if on_result is not None:
+                    on_result(*r)
+            self.submit(indices, scale, **kw)
         while self._inflight:
             r = self.collect()
             if on_result is not None:

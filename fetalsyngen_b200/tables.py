@@ -110,17 +110,22 @@ class DeviceTables:
     """Per-device cache of uploaded tables / tap arrays (built lazily, keyed by their integer
     extents so a continuous random spacing still hits the cache)."""
 
+    MAX_ENTRIES = 65536  # tiny arrays (<= a few KB each); the continuous blur width keys the tap arrays
+
     def __init__(self, device):
         self.device = torch.device(device)
         self._cache: dict = {}
+        self.hold = False  # set by the engine while a launch batch is open: queued calls hold raw pointers into the cache
 
     def _put(self, key, make) -> torch.Tensor:
         t = self._cache.get(key)
         if t is None:
             arr = make()
             t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy()).to(self.device)
-            if len(self._cache) > 8192:
-                self._cache.clear()
+            if len(self._cache) > self.MAX_ENTRIES and not self.hold:
+                # drop the tap arrays only (keyed by a continuous sigma); the integer-keyed tables are bounded by the extents
+                for k in [k for k in self._cache if k[0] == "taps"]:
+                    del self._cache[k]
             self._cache[key] = t
         return t
 

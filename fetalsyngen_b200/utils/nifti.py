@@ -62,13 +62,56 @@ def read_nifti(path, with_affine: bool = False):
     if not with_affine:
         return arr
     aff = np.eye(4)
-    sform_code = struct.unpack(endian + "h", raw[254:256])[0]
+    qform_code, sform_code = struct.unpack(endian + "2h", raw[252:256])
+    pix = struct.unpack(endian + "8f", raw[76:108])
     if sform_code > 0:
         aff[:3] = np.array(struct.unpack(endian + "12f", raw[280:328]), dtype=np.float64).reshape(3, 4)
+    elif qform_code > 0:  # quaternion form (NIfTI-1 standard, method 2)
+        b, c, d, qx, qy, qz = struct.unpack(endian + "6f", raw[256:280])
+        a = np.sqrt(max(0.0, 1.0 - (b * b + c * c + d * d)))
+        rot = np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                        [2 * (b * c + a * d), a * a + c * c - b * b - d * d, 2 * (c * d - a * b)],
+                        [2 * (b * d - a * c), 2 * (c * d + a * b), a * a + d * d - b * b - c * c]])
+        qfac = -1.0 if pix[0] < 0 else 1.0
+        aff[:3, :3] = rot * np.array([pix[1], pix[2], pix[3] * qfac])[None, :]
+        aff[:3, 3] = (qx, qy, qz)
     else:
-        pix = struct.unpack(endian + "8f", raw[76:108])
         aff[0, 0], aff[1, 1], aff[2, 2] = pix[1:4]
     return arr, aff
+
+
+def ras_axes(affine) -> tuple[tuple[int, int, int], tuple[bool, bool, bool]]:
+    """(perm, flip): output axis w of the RAS-oriented array is input axis perm[w], reversed when flip[w] — the
+    closest axis permutation to the affine's rotation (what monai's ``Orientation("RAS")`` / nibabel's
+    ``io_orientation`` compute; the reference applies it to every volume it loads, datasets.py:284-286,
+    rand_gmm.py:91-96)."""
+    from scipy.optimize import linear_sum_assignment
+
+    r = np.asarray(affine, dtype=np.float64)[:3, :3]
+    norm = np.sqrt((r**2).sum(0))
+    norm[norm == 0] = 1.0
+    rn = r / norm
+    world, vox = linear_sum_assignment(-np.abs(rn))  # world axis w <-> voxel axis vox[w]
+    perm = tuple(int(v) for v in vox[np.argsort(world)])
+    flip = tuple(bool(rn[w, perm[w]] < 0) for w in range(3))
+    return perm, flip
+
+
+def to_ras(arr: np.ndarray, affine) -> tuple[np.ndarray, np.ndarray]:
+    """Reorient ``arr[x, y, z]`` to RAS storage order; returns (array, updated affine).  Identity (no copy) for
+    volumes that are stored RAS already, like the reference's bundled data."""
+    perm, flip = ras_axes(affine)
+    aff = np.asarray(affine, dtype=np.float64).copy()
+    if perm == (0, 1, 2) and not any(flip):
+        return arr, aff
+    out = np.transpose(arr, perm)
+    aff[:3, :3] = aff[:3, :3][:, list(perm)]
+    for w in range(3):
+        if flip[w]:
+            out = np.flip(out, axis=w)
+            aff[:3, 3] = aff[:3, 3] + aff[:3, w] * (out.shape[w] - 1)
+            aff[:3, w] = -aff[:3, w]
+    return np.ascontiguousarray(out), aff
 
 
 def write_nifti(path, arr: np.ndarray, affine: np.ndarray | None = None) -> None:

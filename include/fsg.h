@@ -67,7 +67,13 @@ typedef struct fsg_gmm_job {
                           * quantisation <= 1/256 intensity unit, ~1e-5 of the intensity range) */
   int32_t pairs_float;   /* != 0: out_pairs is a float2 volume [nvox][2] = (I[v], I[v+1]) instead — lossless,
                           * one 8-byte gather per (x, y) row in fsg_warp; twice the bytes written here */
-  int32_t _pad;
+  int32_t word_bytes;    /* packed mode (words != NULL): 2 or 4 */
+  /* packed mode: the sample's labels come straight from a subject's bit-packed seed words (see fsg_unpack_job:
+   * L = meta ? 10 * meta + ((word >> shift[meta-1]) & mask[meta-1]) : 0) instead of the sum of seed volumes, so
+   * the dataset-cache path reads 2 bytes per voxel and needs no fsg_unpack_seeds pass.  seed[] is ignored. */
+  const void* words;     /* [nvox] uint16 / uint32 (device), 16-byte aligned, or NULL */
+  int32_t shift[4];
+  int32_t mask[4];
 } fsg_gmm_job;
 int fsg_gmm(const fsg_gmm_job* jobs_host, int njobs, int64_t nvox, void* stream);
 

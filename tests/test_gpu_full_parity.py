@@ -121,3 +121,26 @@ def test_batched_base_path_vs_oracle_every_voxel_at_256():
     torch.cuda.synchronize()
     for b in range(len(cases)):
         _compare(img[b], sg[b], *want[b])
+
+
+def test_gmm_reads_packed_seed_words_directly():
+    """fsg_gmm's packed mode (labels decoded in the kernel from the subject's bit-packed words: what the dataset
+    cache path runs) against the unpack-then-sum route: label volume and Philox intensities bit-identical."""
+    from fetalsyngen_b200.engine import SamplePlan
+
+    rs = np.random.RandomState(9)
+    seg, words, counts = load_subject("sub-sta21")
+    ps = PackedSeeds(words, counts, device=DEV)
+    eng = engine_for(DEV, tuple(seg.shape), RES)
+    plans, sel = [], []
+    for b in range(3):
+        plans.append(SamplePlan(mus=(25 + 200 * rs.rand(50)).astype(np.float32), sigmas=(5 + 20 * rs.rand(50)).astype(np.float32), rng_seed=5, sample_id=b))
+        sel.append({m: int(rs.randint(1, 7)) for m in range(1, 5)})
+    out_a = torch.empty((3, eng.nvox), dtype=torch.float32, device=DEV)
+    lab_a = torch.empty((3, eng.nvox), dtype=torch.uint8, device=DEV)
+    eng.gmm(plans, [(ps, m2s) for m2s in sel], out_a, labels_out=lab_a)
+    out_b, lab_b = torch.empty_like(out_a), torch.empty_like(lab_a)
+    eng.gmm(plans, [[ps.labels(m2s, DEV).view(-1)] for m2s in sel], out_b, labels_out=lab_b)
+    for b in range(3):
+        assert np.array_equal(lab_a[b].cpu().numpy().reshape(seg.shape), unpack_numpy(words, counts, sel[b]))
+    assert torch.equal(lab_a, lab_b) and torch.equal(out_a, out_b)

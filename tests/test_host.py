@@ -327,3 +327,75 @@ def test_pack_dataset_tool_writes_one_cache_file_per_subject(tmp_path):
         lab = unpack_numpy(ps._host, ps.counts, {1: 2, 2: 1, 3: 2, 4: 1})
         for m in range(1, 5):
             assert (lab[m : m + 1] == 10 * m).all()
+
+
+def test_volumes_are_reoriented_to_ras(tmp_path):
+    """The reference applies monai Orientation('RAS') to every volume it loads (datasets.py:284-286,
+    rand_gmm.py:91-96): LPS / permuted exports must come back in the same storage order as their RAS twin."""
+    from fetalsyngen_b200.utils.image_reading import SimpleITKReader
+    from fetalsyngen_b200.utils.nifti import ras_axes, to_ras, write_nifti
+
+    rs = np.random.RandomState(0)
+    ras = rs.randint(0, 8, size=(5, 6, 7)).astype(np.float32)
+    aff = np.diag([0.5, 0.5, 0.5, 1.0])
+    aff[:3, 3] = (-10, -20, -30)
+    assert ras_axes(aff) == ((0, 1, 2), (False, False, False))
+    assert to_ras(ras, aff)[0] is ras  # stored RAS already: no copy
+    # the same volume exported LPS (x and y reversed) ...
+    lps, aff_lps = ras[::-1, ::-1, :].copy(), aff.copy()
+    aff_lps[:3, 0], aff_lps[:3, 1] = -aff[:3, 0], -aff[:3, 1]
+    aff_lps[:3, 3] = aff[:3, 3] + aff[:3, 0] * 4 + aff[:3, 1] * 5
+    # ... and with its axes stored as (S, R, A)
+    sra, aff_sra = np.ascontiguousarray(ras.transpose(2, 0, 1)), aff.copy()
+    aff_sra[:3, :3] = aff[:3, :3][:, [2, 0, 1]]
+    reader = SimpleITKReader()
+    for name, vol, a in (("lps", lps, aff_lps), ("sra", sra, aff_sra)):
+        f = tmp_path / f"{name}.nii.gz"
+        write_nifti(f, vol, a)
+        got = reader(f)
+        assert tuple(got.shape) == ras.shape and np.array_equal(got.numpy(), ras), name
+        np.testing.assert_allclose(got.affine.numpy(), aff, atol=1e-5)
+
+
+def test_byte_lru_evicts_least_recently_used():
+    from fetalsyngen_b200.utils.lru import ByteLRU
+
+    c = ByteLRU(100)
+    c.put("a", 1, 40)
+    c.put("b", 2, 40)
+    assert c.get("a") == 1  # a is now the most recently used
+    c.put("c", 3, 40)       # 120 bytes > 100: b goes
+    assert "b" not in c and c.get("a") == 1 and c.get("c") == 3 and c.bytes == 80
+    c.put("huge", 4, 1000)  # the newest entry always stays
+    assert c.get("huge") == 4 and len(c) == 1
+
+
+def test_packed_only_dataset_discovers_subjects(tmp_path):
+    """FetalSynthDataset.from_packed: subject files alone, no BIDS tree (names with and without a session)."""
+    from fetalsyngen_b200.data.datasets import FetalSynthDataset
+    from fetalsyngen_b200.data.packed import save_packed
+
+    seg = np.zeros((4, 4, 4), np.uint8)
+    for name in ("sub-b_ses-02", "sub-a", "sub-b_ses-01"):
+        save_packed(tmp_path / f"{name}.fsgpack.npz", seg, np.zeros((4, 4, 4), np.uint16), [1, 2, 3, 4, 5, 6])
+    ds = FetalSynthDataset.from_packed(tmp_path, generator=None)
+    assert ds.sub_ses == [("sub-a", None), ("sub-b", "ses-01"), ("sub-b", "ses-02")] and len(ds) == 2
+    assert [ds._sub_ses_idx(i) for i in range(3)] == ["sub-a", "sub-b_ses-01", "sub-b_ses-02"]
+    assert FetalSynthDataset.from_packed(tmp_path, None, sub_list=["sub-a"]).sub_ses == [("sub-a", None)]
+    with pytest.raises(FileNotFoundError):
+        FetalSynthDataset.from_packed(tmp_path / "nowhere", None)
+
+
+def test_device_loader_epochs_do_not_repeat_sample_ids():
+    """with base_seed every epoch replayed the same ids.  Ids of (epoch, step) are disjoint."""
+    from fetalsyngen_b200.sharding import step_ids
+
+    num_batches, B, world = 5, 4, 2
+    seen = set()
+    for epoch in range(3):
+        for step in range(num_batches):
+            for rank in range(world):
+                ids = step_ids(epoch * num_batches + step, B, rank, world)
+                assert not (seen & set(ids))
+                seen |= set(ids)
+    assert seen == set(range(3 * num_batches * B * world))

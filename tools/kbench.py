@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 from fetalsyngen_b200 import _lib  # noqa: E402
 from fetalsyngen_b200.sharding import step_ids  # noqa: E402
-from fetalsyngen_b200.utils.phantom import label_phantom  # noqa: E402
+from fetalsyngen_b200.data.packed import PackedSeeds  # noqa: E402
 
 
 def main():
@@ -27,15 +27,14 @@ def main():
     a = ap.parse_args()
     shape = (a.shape,) * 3
     dev = "cuda:0"
-    seg_h, seeds_h = label_phantom(shape)
     gen = bench.build_generator(shape, dev)
-    seg_d = torch.from_numpy(seg_h).to(dev)
-    seeds_d = [torch.from_numpy(s).to(dev) for s in seeds_h]
+    subj = [(torch.from_numpy(seg).to(dev), PackedSeeds(words, counts, device=dev)) for _, seg, words, counts in bench.load_subjects(shape)]
     out_img = torch.empty((a.batch, *shape), dtype=torch.float32, device=dev)
     out_seg = torch.empty((a.batch, *shape), dtype=torch.uint8, device=dev)
 
     def step(k):
-        gen.sample_batch([seg_d] * a.batch, [seeds_d] * a.batch, scale=True, out_img=out_img, out_seg=out_seg, sample_ids=step_ids(k, a.batch, 0, 1), base_seed=1234)
+        ids = step_ids(k, a.batch, 0, 1)
+        gen.sample_batch([subj[i % 3][0] for i in ids], [subj[i % 3][1] for i in ids], scale=True, out_img=out_img, out_seg=out_seg, sample_ids=ids, base_seed=1234)
 
     for k in range(3):
         step(k)
