@@ -617,6 +617,13 @@ def run_ours(args, shape):
     _lib.stats.timing = False
     per_call = _lib.stats.elapsed_ms()
     f3 = float(np.mean(f3s))
+    # ---- host cost of a step: wall time to ISSUE 20 steps (the launch queue holds them; no synchronisation inside)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step()
+    host_ms = 1000 * (time.perf_counter() - t0) / 20
+    torch.cuda.synchronize()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -778,7 +785,7 @@ def run_ours(args, shape):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "steps_timed": steps_timed, "warmup": warmup,
-        "ms_per_step": ms / steps_timed, "timed_region_s": ms / 1000, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": ms / steps_timed, "timed_region_s": ms / 1000, "host_ms_per_step": host_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[1]: batch of {B} volumes/GPU/step, {shape[0]}^3 @0.5mm, label maps of the reference's bundled sub-sta21 / sub-sta30 / sub-sta38 (sample id k: subject k mod 3, own sub-class counts), deformation+GMM+gamma+bias+blur+resample+noise, all stage probs=1, Philox noise, ScaleIntensity fused",
                    "shape": list(shape), "batch_per_gpu": B, "coarse_fraction_f3": round(f3, 4),
                    "l2": f"every volume of a step has its own label map and intermediates ({B * nvox * 4 / 2**20:.0f} MiB per float buffer per step > 126 MB L2); the 3 subjects' packed inputs (48 MiB each) are shared across samples",

@@ -29,6 +29,13 @@ class ByteLRU:
             _, (_, nb) = self._d.popitem(last=False)
             self.bytes -= nb
 
+    def __setitem__(self, key, value):
+        """Dictionary-style insert; the size is taken from the tensor / array when it has one."""
+        nbytes = getattr(value, "nbytes", None)
+        if nbytes is None and hasattr(value, "numel"):
+            nbytes = value.numel() * value.element_size()
+        self.put(key, value, int(nbytes or 0))
+
     def __len__(self):
         return len(self._d)
 
