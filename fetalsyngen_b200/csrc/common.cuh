@@ -25,7 +25,8 @@ int check_launch(const char* what);
 // A/B switches of DESIGN.md section 4, read from the environment ONCE when the library is loaded (core.cu);
 // launch wrappers only look at this struct.
 struct Config {
-  bool warp_tile;         // FSG_WARP_TILE=1: TMA-staged tile kernel for the warp
+  bool warp_tile;         // FSG_WARP_TILE=1: r01 TMA-staged 16^3 tile kernel for the warp (single buffered)
+  bool warp_pipe;         // FSG_WARP_PIPE=0/1: pipelined TMA kernel (persistent, producer / consumer warps)
   int fwd_warp_min_taps;  // FSG_FWD_WARP_MIN_TAPS: PSF size from which the acquisition splits taps over lanes
   bool fwd_lean;          // FSG_FWD_LEAN=1: nested-lerp accumulation in the acquisition
   bool adj_lean;          // FSG_ADJ_LEAN=0: reference operation order in the PSF reconstruction

@@ -19,6 +19,7 @@ static Config read_config() {
   };
   Config c;
   c.warp_tile = flag("FSG_WARP_TILE", false);
+  c.warp_pipe = flag("FSG_WARP_PIPE", false);
   // r01: 215 taps 2.5 ms (thread) vs 3.9 ms (warp); 729 taps 12.7 vs 9.3 ms
   c.fwd_warp_min_taps = num("FSG_FWD_WARP_MIN_TAPS", 400);
   // opt-in: measured with the xy-quad volume 1.59 vs 1.27 ms (215 taps), 4.46 vs 4.62 ms (729 taps), 0.49 vs

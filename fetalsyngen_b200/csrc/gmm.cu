@@ -29,6 +29,13 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
   }
   __syncthreads();
   __shared__ float s_first[2][GMM_THREADS];  // first value of every thread's group (pairs output), double-buffered
+  __shared__ uint2 s_dec[8];                  // packed mode: (shift, mask | base << 8) per 3-bit meta field (0, 5..7: label 0)
+  if (NSEED == 0 && threadIdx.x < 8) {
+    const int m = threadIdx.x;
+    s_dec[m] = (m >= 1 && m <= 4) ? make_uint2((uint32_t)job.shift[m - 1], (uint32_t)job.mask[m - 1] | ((uint32_t)(10 * m) << 8)) : make_uint2(0u, 0u);
+    // visibility: the __syncthreads above ran before; a second one follows below for packed launches
+  }
+  if (NSEED == 0) __syncthreads();
 
   const int8_t* __restrict__ sp[4] = {job.seed[0], job.seed[1], job.seed[2], job.seed[3]};
   uint32_t wtab[5] = {0, 0, 0, 0, 0};
@@ -64,7 +71,11 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
     if (NSEED == 0) {
       if (w16) {
         const uint2 q = __ldcs(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(job.words) + v0));
-        lab4 = decode_word(q.x & 0xffffu, wtab) | (decode_word(q.x >> 16, wtab) << 8) | (decode_word(q.y & 0xffffu, wtab) << 16) | (decode_word(q.y >> 16, wtab) << 24);
+        auto dec = [&](uint32_t w) -> uint32_t {  // meta ? 10 meta + ((w >> shift) & mask) : 0, tables in shared memory
+          const uint2 t = s_dec[w & 7u];
+          return (t.y >> 8) + ((w >> t.x) & (t.y & 0xffu));
+        };
+        lab4 = dec(q.x & 0xffffu) | (dec(q.x >> 16) << 8) | (dec(q.y & 0xffffu) << 16) | (dec(q.y >> 16) << 24);
       } else {
         const uint4 q = __ldcs(reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(job.words) + v0));
         lab4 = decode_word(q.x, wtab) | (decode_word(q.y, wtab) << 8) | (decode_word(q.z, wtab) << 16) | (decode_word(q.w, wtab) << 24);

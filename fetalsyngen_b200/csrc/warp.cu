@@ -31,6 +31,8 @@ namespace fsg {
 
 // warp_tile.cu: TMA-staged variant; returns 0 when it launched, -1 when the batch is not eligible
 int launch_warp_tile(const fsg_warp_job* jobs, int njobs, bool epi, int sx, int sy, int sz, cudaStream_t stream);
+// warp_pipe.cu: pipelined TMA variant (persistent blocks, producer / consumer warps); same return convention
+int launch_warp_pipe(const fsg_warp_job* jobs, int njobs, bool epi, int sx, int sy, int sz, cudaStream_t stream);
 
 // Exact control-grid value at voxel (i,j,k): x-, y-, z-blend in myzoom_torch's order.  Used by
 // the edge pre-pass only (the main kernel stages the x/y blends in shared memory).
@@ -672,6 +674,11 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
     // but measured 2.4x slower than the full-z kernel at 256^3 (r01e: 2.17 ms vs 0.90 ms per 8
     // volumes; one 163 KB block per SM, no overlap of the box load with the gathers), so it is
     // opt-in until it is double-buffered.
+    if (config().warp_pipe && g < 2) {
+      const int rc = launch_warp_pipe(part[g], cnt[g], g == 0, sx, sy, sz, s);
+      if (rc == 0) continue;
+      if (rc > 0) return rc;
+    }
     if (config().warp_tile && g < 2) {
       const int rc = launch_warp_tile(part[g], cnt[g], g == 0, sx, sy, sz, s);
       if (rc == 0) continue;

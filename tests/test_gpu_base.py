@@ -354,6 +354,12 @@ def test_warp_kernel_variants_agree(monkeypatch):
     assert "tile (" not in res.stdout  # no box-bound violations reported by the debug check
     err = float(res.stdout.split("ERR")[1])
     assert err <= TOL
+    # the pipelined TMA kernel (persistent blocks, producer / consumer warps): staged boxes, then every tile forced
+    # through its global-memory fallback (FSG_TILE_DEBUG=1)
+    for extra in ({}, {"FSG_TILE_DEBUG": "1"}):
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, FSG_WARP_PIPE="1", FSG_WARP_TILE="0", **extra), timeout=300)
+        assert res.returncode == 0, res.stderr[-1500:]
+        assert float(res.stdout.split("ERR")[1]) <= TOL
 
 
 def test_sample_batch_streams_do_not_depend_on_the_sharding():
