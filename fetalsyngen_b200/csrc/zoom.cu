@@ -245,15 +245,20 @@ __global__ void __launch_bounds__(ZW_THREADS, 2) zoom_walk_kernel(const __grid_c
   int2* s_tx = s_ty + RJ;
 
   const int k4 = tid % SZ4, jrow0 = tid / SZ4;
-  // z table of this thread's four columns: byte offsets into a coarse row + weights
-  int zf[4], zc[4];
-  float zwc[4];
+  // z stage mapping: thread = one output column k (lanes = consecutive k: neighbouring lanes read the same or the
+  // neighbouring coarse word, no bank conflicts; r02a ncu of the float4-per-thread mapping: 2-way conflicts on every
+  // gather, 11 M conflict wavefronts per launch), walking the chunk's coarse rows
+  constexpr int NKZ = SZ > ZW_THREADS ? SZ / ZW_THREADS : 1, ZROWS = SZ < ZW_THREADS ? ZW_THREADS / SZ : 1;
+  const int zk = tid % SZ, zr0 = tid / SZ;  // SZ >= 256: zk = tid, zr0 = 0
+  int zf[NKZ], zc[NKZ];
+  float zwc[NKZ], zwf[NKZ];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const fsg_tab t = job.tab[2][4 * k4 + e];
+  for (int e = 0; e < NKZ; ++e) {
+    const fsg_tab t = job.tab[2][zk + e * ZW_THREADS];
     zf[e] = (int)t.f * 4;
     zc[e] = (int)t.c * 4;
     zwc[e] = t.wc;
+    zwf[e] = sub_rn(1.0f, t.wc);
   }
   for (int j = tid; j < RJ; j += ZW_THREADS) {
     const fsg_tab t = job.tab[1][min(j0 + j, sy - 1)];
@@ -302,17 +307,15 @@ __global__ void __launch_bounds__(ZW_THREADS, 2) zoom_walk_kernel(const __grid_c
   for (int X = x_first; X <= x_last; ++X, b ^= 1) {
     cp_async_commit_wait_all();
     __syncthreads();  // plane X's coarse rows are in s_c[b]; the y stage of plane X-1 is done with s_tz
-    // ---- z stage: s_tz[r][4 k4 .. 4 k4 + 3] for the rows r = jrow0, jrow0 + RSTEP, ...
+    // ---- z stage: s_tz[r][zk] for the rows r = zr0, zr0 + ZROWS, ...
     {
       const char* cb = reinterpret_cast<const char*>(s_c + (size_t)b * cap * n2max);
-      for (int r = jrow0; r < nr; r += RSTEP) {
+#pragma unroll 2
+      for (int r = zr0; r < nr; r += ZROWS) {
         const char* row = cb + (size_t)r * n2 * 4;
-        float4 o;
-        o.x = __fmaf_rn(sub_rn(1.0f, zwc[0]), *reinterpret_cast<const float*>(row + zf[0]), __fmul_rn(zwc[0], *reinterpret_cast<const float*>(row + zc[0])));
-        o.y = __fmaf_rn(sub_rn(1.0f, zwc[1]), *reinterpret_cast<const float*>(row + zf[1]), __fmul_rn(zwc[1], *reinterpret_cast<const float*>(row + zc[1])));
-        o.z = __fmaf_rn(sub_rn(1.0f, zwc[2]), *reinterpret_cast<const float*>(row + zf[2]), __fmul_rn(zwc[2], *reinterpret_cast<const float*>(row + zc[2])));
-        o.w = __fmaf_rn(sub_rn(1.0f, zwc[3]), *reinterpret_cast<const float*>(row + zf[3]), __fmul_rn(zwc[3], *reinterpret_cast<const float*>(row + zc[3])));
-        reinterpret_cast<float4*>(s_tz + (size_t)r * SZ)[k4] = o;
+#pragma unroll
+        for (int e = 0; e < NKZ; ++e)
+          s_tz[(size_t)r * SZ + zk + e * ZW_THREADS] = __fmaf_rn(zwf[e], *reinterpret_cast<const float*>(row + zf[e]), __fmul_rn(zwc[e], *reinterpret_cast<const float*>(row + zc[e])));
       }
     }
     __syncthreads();
