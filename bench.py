@@ -575,12 +575,13 @@ def run_ours(args, shape):
         step()
     barrier()
     # ---- length of the timed region: at least --steps and at least MIN_TIMED_S (estimated from 3 more steps)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(10):
         step()
     torch.cuda.synchronize()
-    est = (time.perf_counter() - t0) / 3
-    steps_timed = max(args.steps, int(math.ceil(MIN_TIMED_S / max(est, 1e-6))))
+    est = (time.perf_counter() - t0) / 10
+    steps_timed = max(args.steps, int(math.ceil(1.15 * MIN_TIMED_S / max(est, 1e-6))))
     if world > 1:
         t = torch.tensor([steps_timed], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
