@@ -353,3 +353,42 @@ def test_dataset_with_packed_cache_gives_identical_samples(tmp_path):
     ia, sa, _ = gen.sample_batch([plain._segmentation(i) for i in (0, 1)], [plain._seeds(i) for i in (0, 1)], sample_ids=[4, 9], base_seed=77)
     ib, sb, _ = gen.sample_batch([packed._segmentation(i) for i in (0, 1)], [packed._seeds(i) for i in (0, 1)], sample_ids=[4, 9], base_seed=77)
     assert torch.equal(ia, ib) and torch.equal(sa, sb)
+
+
+def test_packed_only_dataset_and_dataset_pipeline_on_the_bundled_subjects():
+    """FetalSynthDataset.from_packed over the committed 256^3 subject files (no BIDS tree, no NIfTI): the index-based
+    batched entry point, its host-output pipeline (what bench.py's e2e_dataset_cache leg times) and the
+    reference-shaped per-sample call all run from the device-resident subject cache."""
+    from fetalsyngen_b200.data.datasets import FetalSynthDataset
+    from fetalsyngen_b200.host_pipeline import DatasetPipeline
+    from golden_util import SUBJECTS
+
+    shape = (256, 256, 256)
+    gen = _gen(shape)
+    ds = FetalSynthDataset.from_packed(SUBJECTS, gen)
+    assert [ds._sub_ses_idx(i) for i in range(3)] == ["sub-sta21", "sub-sta30", "sub-sta38"]
+    out, params = ds.sample_batch([0, 1, 2], scale=True, sample_ids=[10, 11, 12], base_seed=3)
+    img, lab = out["image"][:, 0].clone(), out["label"][:, 0].clone()
+    assert img.shape == (3, *shape) and float(img.max()) == 1.0 and float(img.min()) == 0.0 and out["name"] == ["sub-sta21", "sub-sta30", "sub-sta38"]
+    # same ids through the generator directly: identical volumes (every draw is a function of (base_seed, id))
+    segs = [ds._segmentation(i) for i in range(3)]
+    img2, lab2, _ = gen.sample_batch(segs, [ds._seeds(i) for i in range(3)], scale=True, sample_ids=[10, 11, 12], base_seed=3)
+    assert torch.equal(img, img2) and torch.equal(lab, lab2)
+    # warped labels stay inside the subject's label set and cover a plausible part of the volume
+    for b in range(3):
+        assert set(torch.unique(lab[b]).tolist()) <= set(torch.unique(segs[b]).tolist())
+        assert 0.3 < float((lab[b] > 0).float().mean()) / float((segs[b] > 0).float().mean()) < 3.0
+    # host-output pipeline: two pipelined steps, results equal to the device path and in submission order
+    dp = DatasetPipeline(ds, 3, depth=2)
+    got = []
+    dp.run([[0, 1, 2], [2, 0, 1]], on_result=lambda hi, hs, pr: got.append((hi.clone(), hs.clone())), sample_ids=None)
+    assert len(got) == 2 and got[0][0].shape == (3, *shape) and got[0][0].dtype == torch.float32 and got[0][1].dtype == torch.uint8
+    dp2 = DatasetPipeline(ds, 3, depth=2)
+    dp2.submit([0, 1, 2], True, sample_ids=[10, 11, 12], base_seed=3)
+    hi, hs, _ = dp2.collect()
+    assert torch.equal(hi, img.cpu()) and torch.equal(hs, lab.cpu())
+    # the reference's per-sample entry point on the same cache
+    np.random.seed(0)
+    torch.manual_seed(0)
+    data, gp = ds.sample(1)
+    assert data["image"].shape == (1, *shape) and data["label"].dtype == torch.int64 and data["name"] == "sub-sta30" and "generation_time" in gp

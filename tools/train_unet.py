@@ -124,6 +124,9 @@ def main():
     per = max(1, B // TB)
     losses = []
     generate(0)
+    with torch.cuda.stream(gstream):  # engines are per stream: build the producer stream's engine (scratch, tables) before the clock starts
+        gstream.wait_stream(torch.cuda.current_stream())
+        generate(1)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     nsteps = 0
