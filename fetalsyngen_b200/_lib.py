@@ -132,6 +132,10 @@ SIGNATURES = {
     "fsg_volume_xyquads": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp]),
     "fsg_volume_xpairs": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fsg_slice_acq_adjoint": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _f32, _vp, _vp, _vp, _vp, _vp] + [C.c_int] * 6 + [_f32, C.c_int, _vp]),
+    "fsg_slice_acq_forward_ex": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _f32, _vp, _vp] + [C.c_int] * 6 + [_f32, C.c_int, _vp]),
+    "fsg_slice_acq_adjoint_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _f32, _vp, _vp, _vp, _vp, _vp] + [C.c_int] * 6 + [_f32, C.c_int, C.c_int, _vp]),
+    "fsg_axisangle2mat": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "fsg_mat2axisangle": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "fsg_slice_sums": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "fsg_slice_gamma": (C.c_int, [_vp, _i64, _f32, _vp, _vp]),
     "fsg_slice_rician": (C.c_int, [_vp, _i64, _f32, _f32, _vp, _vp, Rng, _vp]),

@@ -333,6 +333,26 @@ int fsg_slice_acq_adjoint(const float* transforms, const float* psf, int dp, int
                           void* stream);
 /* workspace: 2*D*H*W device floats, 8-byte aligned (interleaved value/weight accumulator: one 64-bit
  * reduction per tap); vol_weight may be NULL. */
+
+/* The pybind module's FULL contract (any option the generator does not use): optional byte masks over the volume
+ * ([D][H][W], non-zero = inside) and over the slices ([n][h][w]), the per-pixel weight output (need_weight), both PSF
+ * modes in both directions, optional equalisation.
+ *   fsg_slice_acq_forward_ex  = slice_acq_cuda.forward(transforms, vol, vol_mask, slices_mask, psf, (h, w), res_slice,
+ *                               need_weight = (slices_weight != NULL), interp_psf)      (slice_acq_cuda.cpp:61-79)
+ *   fsg_slice_acq_adjoint_ex  = slice_acq_cuda.adjoint_forward(transforms, psf, slices, slices_mask, vol_mask,
+ *                               (D, H, W), res_slice, interp_psf, equalize)             (slice_acq_cuda.cpp:105-124)
+ * psf: the dense [dp][hp][wp] grid (read when interp_psf != 0); taps / radius as above.  Outputs are zero-filled by
+ * the call; masks and slices_weight may be NULL; vol_weight may be NULL unless equalize != 0. */
+int fsg_slice_acq_forward_ex(const float* transforms, const float* vol, const uint8_t* vol_mask, const uint8_t* slices_mask, const float* psf, int dp, int hp, int wp,
+                             const float* taps, int ntaps, float radius, float* slices, float* slices_weight, int n, int h, int w, int D, int H, int W, float res_slice,
+                             int interp_psf, void* stream);
+int fsg_slice_acq_adjoint_ex(const float* transforms, const float* psf, int dp, int hp, int wp, const float* taps, int ntaps, float radius, const float* slices,
+                             const uint8_t* slices_mask, const uint8_t* vol_mask, float* vol, float* vol_weight, int n, int h, int w, int D, int H, int W, float res_slice,
+                             int interp_psf, int equalize, void* stream);
+/* Rigid-transform conversions of the reference's second pybind module (transform_convert_cuda.cpp:27-51,
+ * kernels transform_convert_cuda_kernel.cu:14-65,190-264): (n, 6) axis-angle (radians) + translation <-> (n, 3, 4). */
+int fsg_axisangle2mat(const float* axisangle, float* mat, int n, void* stream);
+int fsg_mat2axisangle(const float* mat, float* axisangle, int n, void* stream);
 /* slice_idx (device, [n], may be NULL): slice in of the launch reads slices[slice_idx[in]] — the
  * "stacks[kept_idx]" gather of PSFReconstructor (simulate_reco.py:766-767) without a copy.
  *

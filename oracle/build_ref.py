@@ -17,6 +17,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 REF = Path(os.environ.get("FSG_REFERENCE_ROOT", "/root/reference")) / "fetalsyngen/generator/artifacts/svort/slice_acquisition"
+REF_T = REF.parent / "transform"  # transform_convert_cuda{.cpp,_kernel.cu}: the reference's second pybind module
 OUT = ROOT / "_ref"
 
 
@@ -28,19 +29,24 @@ def build(verbose: bool = False):
     from torch.utils.cpp_extension import load
 
     OUT.mkdir(exist_ok=True)
-    return load("slice_acq_cuda", [str(REF / "slice_acq_cuda.cpp"), str(REF / "slice_acq_cuda_kernel.cu")], build_directory=str(OUT), verbose=verbose, is_python_module=True)
+    mod = load("slice_acq_cuda", [str(REF / "slice_acq_cuda.cpp"), str(REF / "slice_acq_cuda_kernel.cu")], build_directory=str(OUT), verbose=verbose, is_python_module=True)
+    if (REF_T / "transform_convert_cuda.cpp").exists():
+        (OUT / "tc").mkdir(exist_ok=True)
+        load("transform_convert_cuda", [str(REF_T / "transform_convert_cuda.cpp"), str(REF_T / "transform_convert_cuda_kernel.cu")], build_directory=str(OUT / "tc"), verbose=verbose,
+             is_python_module=True)
+    return mod
 
 
-def load_built():
-    """Import the pre-built module from oracle/_ref (no compiler needed)."""
-    so = OUT / "slice_acq_cuda.so"
+def load_built(name: str = "slice_acq_cuda"):
+    """Import a pre-built module from oracle/_ref (no compiler needed): ``slice_acq_cuda`` or ``transform_convert_cuda``."""
+    so = (OUT / "slice_acq_cuda.so") if name == "slice_acq_cuda" else (OUT / "tc" / f"{name}.so")
     if not so.exists():
         return None
     import importlib.util
 
     import torch  # noqa: F401  (the extension links against libtorch)
 
-    spec = importlib.util.spec_from_file_location("slice_acq_cuda", so)
+    spec = importlib.util.spec_from_file_location(name, so)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod

@@ -288,3 +288,83 @@ def test_xyquads_acquisition_is_bit_identical():
     a = SR.slice_acquisition(mat, vol, psf, (64, 64), 1.2)
     b = SR.slice_acquisition(mat, vol, psf, (64, 64), 1.2, pairs=SR.volume_xyquads(vol))
     assert torch.equal(a, b) and float(a.abs().max()) > 0
+
+
+# ------------------------------------------------------------------ the pybind modules' full contract (native_compat)
+def _compat_case(seed):
+    vol, mat, psf, shape, res = random_case(seed, D=36, n=6, hw=40)
+    rs = np.random.RandomState(100 + seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    vol_mask = rs.rand(*vol.shape) > 0.2
+    slices_mask = rs.rand(mat.shape[0], 1, *shape) > 0.3
+    return t(vol)[None, None].contiguous(), t(mat), t(psf), shape, float(res), t(vol_mask)[None, None].contiguous(), t(slices_mask).contiguous()
+
+
+@pytest.mark.parametrize("interp_psf", [False, True])
+@pytest.mark.parametrize("need_weight", [False, True])
+@pytest.mark.parametrize("masks", ["none", "vol", "slices", "both"])
+def test_forward_full_contract_vs_reference_extension(interp_psf, need_weight, masks):
+    """slice_acq_cuda.forward with every option (volume / slice masks, weight output, both PSF modes): the drop-in
+    module over libfsg against the reference's own extension, same argument list."""
+    from fetalsyngen_b200.generator.artifacts.native_compat import slice_acq_cuda as ours
+
+    ext = _reference_extension()
+    vol, mat, psf, shape, res, vmask, smask = _compat_case(3)
+    empty_b = torch.empty(0, dtype=torch.bool, device=DEV)
+    vm = vmask if masks in ("vol", "both") else empty_b
+    sm = smask if masks in ("slices", "both") else empty_b
+    want = ext.forward(mat, vol, vm, sm, psf, list(shape), res, need_weight, interp_psf)
+    got = ours.forward(mat, vol, vm, sm, psf, list(shape), res, need_weight, interp_psf)
+    assert len(got) == len(want) == (2 if need_weight else 1)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        close(rel(g, w.cpu().numpy()))
+        assert ((g == 0) == (w == 0)).float().mean() > 0.999  # the same pixels stay unwritten
+    if masks in ("slices", "both"):
+        assert float(got[0][~smask].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("interp_psf", [False, True])
+@pytest.mark.parametrize("equalize", [False, True])
+@pytest.mark.parametrize("masks", ["none", "vol", "slices", "both"])
+def test_adjoint_full_contract_vs_reference_extension(interp_psf, equalize, masks):
+    from fetalsyngen_b200.generator.artifacts.native_compat import slice_acq_cuda as ours
+
+    ext = _reference_extension()
+    vol, mat, psf, shape, res, vmask, smask = _compat_case(4)
+    empty_b, empty_f = torch.empty(0, dtype=torch.bool, device=DEV), torch.empty(0, device=DEV)
+    slices = ext.forward(mat, vol, empty_f, empty_f, psf, list(shape), res, False, False)[0]
+    vm = vmask if masks in ("vol", "both") else empty_b
+    sm = smask if masks in ("slices", "both") else empty_b
+    want = ext.adjoint_forward(mat, psf, slices, sm, vm, list(vol.shape[-3:]), res, interp_psf, equalize)
+    got = ours.adjoint_forward(mat, psf, slices, sm, vm, list(vol.shape[-3:]), res, interp_psf, equalize)
+    close(rel(got[0], want[0].cpu().numpy()), cap=0.25, frac=2e-3)
+    if equalize:
+        close(rel(got[1], want[1].cpu().numpy()), cap=0.25, frac=2e-3)
+    if masks in ("vol", "both"):
+        assert float(got[0][~vmask].abs().max()) == 0.0
+
+
+def test_transform_conversions_vs_reference_extension_and_oracle():
+    """transform_convert_cuda.axisangle2mat_forward / mat2axisangle_forward: small and large angles, the
+    first-order branch below 1e-6, all four quaternion branches, against the reference's module and the oracle."""
+    from fetalsyngen_b200.generator.artifacts.native_compat import transform_convert_cuda as ours
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+
+    rs = np.random.RandomState(8)
+    ax = np.concatenate([rs.randn(200, 3) * 1.5, rs.randn(200, 3) * 20], 1).astype(np.float32)
+    ax[:10, :3] *= 1e-4                      # first-order branch
+    ax[10:40, :3] *= 3.14159 / np.linalg.norm(ax[10:40, :3], axis=1, keepdims=True)  # rotations by ~pi: the three trace-negative branches
+    axd = torch.from_numpy(ax).to(DEV)
+    mat = ours.axisangle2mat_forward(axd)[0]
+    assert np.abs(mat.cpu().numpy() - M.axisangle2mat(ax)).max() <= 2e-6
+    back = ours.mat2axisangle_forward(mat)[0]
+    assert np.abs(back.cpu().numpy() - M.mat2axisangle(mat.cpu().numpy())).max() <= 2e-4  # atan2 / sqrt near pi amplify an ulp of the matrix
+    mat2 = ours.axisangle2mat_forward(back)[0]
+    assert float((mat2 - mat).abs().max()) <= 5e-4  # same rotation after the round trip
+    ext = build_ref.load_built("transform_convert_cuda")
+    assert ext is not None, "oracle/_ref/tc/transform_convert_cuda.so is missing: run __graft_entry__.build() in the build container"
+    assert float((ext.axisangle2mat_forward(axd)[0] - mat).abs().max()) <= 2e-6
+    assert float((ext.mat2axisangle_forward(mat)[0] - back).abs().max()) <= 2e-4
