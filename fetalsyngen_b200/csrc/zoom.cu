@@ -217,7 +217,13 @@ __global__ void __launch_bounds__(ZM_THREADS) zoom_plane_kernel(const __grid_con
 //   y stage: cur[m] = w_f * s_tz[f_j] + w_c * s_tz[c_j]   (float4, registers)
 //   x stage: every output plane i with c_i == X: out = w_f * prev + w_c * cur (+ /max, ScaleIntensity | min/max)
 constexpr int ZW_THREADS = 256;
-constexpr int ZW_M = 8;
+#ifndef FSG_ZW_M
+#define FSG_ZW_M 8
+#endif
+#ifndef FSG_ZW_MINB
+#define FSG_ZW_MINB 2
+#endif
+constexpr int ZW_M = FSG_ZW_M;  // float4 slots per thread and plane (A/B: -DFSG_ZW_M=4 -DFSG_ZW_MINB=3)
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -225,7 +231,7 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 template <bool REDUCE, int SZ4>
-__global__ void __launch_bounds__(ZW_THREADS, 2) zoom_walk_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int sx, int sy, int cap, int n2max, int xsegs) {
+__global__ void __launch_bounds__(ZW_THREADS, FSG_ZW_MINB) zoom_walk_kernel(const __grid_constant__ Batch<fsg_zoom_job> batch, int sx, int sy, int cap, int n2max, int xsegs) {
   constexpr int SZ = 4 * SZ4, RJ = ZW_THREADS * ZW_M / SZ4, RSTEP = ZW_THREADS / SZ4;  // rows per chunk, row step between a thread's slots
   const fsg_zoom_job& job = batch.j[blockIdx.y];
   const int n0 = job.n[0], n1 = job.n[1], n2 = job.n[2];
@@ -441,7 +447,7 @@ static bool launch_zoom_walk(const Batch<fsg_zoom_job>& b, const fsg_zoom_job* j
     if (REDUCE == false && (reinterpret_cast<uintptr_t>(jobs[i].dst) & 15)) return false;
   }
   const size_t smem = ((((size_t)2 * cap * max_n2 + 3) & ~(size_t)3) + (size_t)cap * 4 * SZ4 + 2 * (size_t)RJ + 2 * (size_t)sx) * sizeof(float);
-  if (smem > 110 * 1024) return false;  // two blocks per SM
+  if (smem > (FSG_ZW_MINB >= 3 ? 72 : 110) * 1024) return false;  // FSG_ZW_MINB blocks per SM
   const int nchunk = (sy + RJ - 1) / RJ;
   // segments of output planes: enough blocks for >= 2 waves of 2 blocks per SM, each segment at least 8 planes long
   int xsegs = (148 * 4 + nchunk * njobs - 1) / (nchunk * njobs);

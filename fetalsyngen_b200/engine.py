@@ -398,11 +398,11 @@ class SynthEngine:
             tap_slot.append(slots)
         taps_dev = self.upload(tap_arrays) if tap_arrays else []
         extents = [self.sep_extents(p, positions) for p in plans]
-        for b, p in enumerate(plans):
-            need = self.sep_capacity(p, positions)
-            for name, t, n in (("dst", dst[b], need[0]), ("tmp1", tmp1[b], need[1]), ("tmp2", tmp2[b], need[2])):
-                if t.numel() < n:
-                    raise ValueError(f"sepconv: sample {b}: {name} holds {t.numel()} floats, {n} are needed (coarse grid {extents[b]})")
+        for b, n in enumerate(extents):
+            need = (n[0] * n[1] * n[2], n[0] * sy * sz, n[0] * n[1] * sz)
+            for name, t, cnt in (("dst", dst[b], need[0]), ("tmp1", tmp1[b], need[1]), ("tmp2", tmp2[b], need[2])):
+                if t.shape[-1] < cnt:
+                    raise ValueError(f"sepconv: sample {b}: {name} holds {t.shape[-1]} floats, {cnt} are needed (coarse grid {n})")
         # workspace per job and axis: float w[nmax][maxw] then int16 q0[nmax]; an up-sampled axis has more rows than the volume
         nmax = max(max(self.shape), max(max(n) for n in extents))
         maxw = max(32, (maxw + 3) // 4 * 4)
@@ -598,8 +598,10 @@ class SynthEngine:
             sub = [plans[b] for b in rs]
             # x pass -> buf2, y pass -> buf0 (the GMM image is dead), z pass (+noise) -> buf2
             low, tmp = [buf2[b] for b in rs], [buf0[b] for b in rs]
-            need = [self.sep_capacity(p) for p in sub]
-            if max(max(nd) for nd in need) > self.nvox:  # an up-sampled axis (spacing < resolution): the coarse grid outgrows the volume
+            need = None
+            if any(p.spacing[a] < self.resolution[a] for p in sub for a in range(3)):
+                need = [self.sep_capacity(p) for p in sub]
+            if need is not None and max(max(nd) for nd in need) > self.nvox:  # an up-sampled axis (spacing < resolution): the coarse grid outgrows the volume
                 big_a = self.scratch("sep_big_a", len(rs), numel=max(max(nd[0], nd[1]) for nd in need))
                 big_b = self.scratch("sep_big_b", len(rs), numel=max(nd[2] for nd in need))
                 low, tmp = [big_a[k] for k in range(len(rs))], [big_b[k] for k in range(len(rs))]
