@@ -557,3 +557,23 @@ def test_zoom_minmax_equals_extrema_of_zoomed_volume(shape, coarse, kind):
     torch.cuda.synchronize()
     got = tuple(float(v) for v in mm[0].cpu())
     assert got == want, (got, want)
+
+
+@pytest.mark.parametrize("shape,coarses", [((40, 72, 128), [(17, 31, 50), (40, 72, 128)]), ((33, 47, 256), [(12, 16, 86), (30, 40, 201)]), ((24, 20, 512), [(9, 7, 170), (24, 20, 300)]),
+                                            ((31, 45, 38), [(11, 15, 13), (31, 45, 38)])])
+def test_zoom_kernels_vs_oracle_in_mixed_batches(shape, coarses):
+    """myzoom_torch (utils/generation.py:310-397) through both up-sampling kernels — the walk kernel (sz in {128, 256,
+    512}: axes blended z, y, x) and the generic plane kernel — on non-cubic volumes, two jobs with different coarse
+    grids per launch, against the oracle's x, y, z order (they differ by rounding only)."""
+    eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+    rs = np.random.RandomState(shape[2])
+    srcs, want = [], []
+    for c in coarses:
+        x = (rs.rand(*c) * 300).astype(np.float32)
+        srcs.append(torch.from_numpy(x).to(DEV).contiguous())
+        want.append(O.zoom_linear(x, np.asarray(shape, dtype=np.float64) / np.asarray(c, dtype=np.float64)))
+    dst = torch.empty((len(coarses), int(np.prod(shape))), dtype=torch.float32, device=DEV)
+    eng.zoom(srcs, coarses, [[s / c for s, c in zip(shape, cc)] for cc in coarses], dst, post=0)
+    for b in range(len(coarses)):
+        assert want[b].shape == tuple(shape)
+        assert rel_err(dst[b].view(shape), want[b]) <= 1e-6
