@@ -28,14 +28,20 @@ class Rng(C.Structure):
 
 class GmmJob(C.Structure):
     _fields_ = [("seed", _vp * 4), ("mus", _vp), ("sigmas", _vp), ("noise", _vp), ("out", _vp), ("labels_out", _vp),
-                ("rng", Rng), ("nlabels", _i32), ("row_len", _i32), ("out_pairs", _vp), ("pairs_float", _i32), ("word_bytes", _i32), ("words", _vp), ("shift", _i32 * 4), ("mask", _i32 * 4)]
+                ("rng", Rng), ("nlabels", _i32), ("row_len", _i32), ("out_pairs", _vp), ("pairs_float", _i32), ("word_bytes", _i32), ("words", _vp), ("shift", _i32 * 4), ("mask", _i32 * 4),
+                ("out_surf", C.c_uint64), ("surf_ny", _i32), ("_pad2", _i32)]
 
 
 class WarpJob(C.Structure):
     _fields_ = [("src_img", _vp), ("src_pairs", _vp), ("src_seg", _vp), ("src_img2", _vp), ("dst_img", _vp), ("dst_seg", _vp), ("dst_img2", _vp),
                 ("fsmall", _vp), ("ftab", _vp * 3), ("bf_low", _vp), ("btab", _vp * 3), ("shift", _vp),
                 ("A", _f32 * 9), ("c2", _f32 * 3), ("center", _f32 * 3), ("gamma", _f32),
-                ("fs", _i32 * 3), ("bs", _i32 * 3), ("mode", _i32), ("flip", _i32), ("has_gamma", _i32), ("pairs_float", _i32)]
+                ("fs", _i32 * 3), ("bs", _i32 * 3), ("mode", _i32), ("flip", _i32), ("has_gamma", _i32), ("pairs_float", _i32),
+                ("src_tex", C.c_uint64)]
+
+
+class TexVol(C.Structure):
+    _fields_ = [("array", C.c_uint64), ("tex", C.c_uint64), ("surf", C.c_uint64), ("nx", _i32), ("ny", _i32), ("nz", _i32), ("_pad", _i32)]
 
 
 class BlurJob(C.Structure):
@@ -99,6 +105,9 @@ SIGNATURES = {
     "fsg_last_error": (C.c_char_p, []),
     "fsg_sizeof": (C.c_int, [C.c_char_p]),
     "fsg_gmm": (C.c_int, [C.POINTER(GmmJob), C.c_int, _i64, _vp]),
+    "fsg_texvol_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(TexVol)]),
+    "fsg_texvol_destroy": (C.c_int, [C.POINTER(TexVol)]),
+    "fsg_texvol_copy": (C.c_int, [C.POINTER(TexVol), _vp, C.c_int, _vp]),
     "fsg_warp_shift": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "fsg_warp": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "fsg_warp_coords": (C.c_int, [C.POINTER(WarpJob), C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
@@ -155,7 +164,8 @@ SIGNATURES = {
 
 # kernels one call of an entry point launches on the fused base path (profiles/r01g_launches.csv);
 # entry points not listed launch one
-KERNELS_PER_CALL = {"fsg_warp_shift": 4, "fsg_sepconv": 3, "fsg_zoom_minmax": 3, "fsg_minmax": 3, "fsg_slice_acq_adjoint": 2, "fsg_slice_gamma": 2}
+KERNELS_PER_CALL = {"fsg_warp_shift": 4, "fsg_sepconv": 3, "fsg_zoom_minmax": 3, "fsg_minmax": 3, "fsg_slice_acq_adjoint": 2, "fsg_slice_gamma": 2,
+                    "fsg_texvol_create": 0, "fsg_texvol_destroy": 0, "fsg_texvol_copy": 0}
 
 _lib = None
 

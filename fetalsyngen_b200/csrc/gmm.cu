@@ -56,6 +56,11 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
   const fsg_rng rng = job.rng;
   uint32_t* __restrict__ pairs = job.out_pairs;
   const int row_len = job.row_len;
+  // block-linear output (fsg_texvol): group g = 4 voxels of row (x, y) at column 4 * z4
+  const unsigned long long surf = job.out_surf;
+  const uint32_t rq = surf ? (uint32_t)row_len >> 2 : 1u, sny = surf ? (uint32_t)job.surf_ny : 1u;
+  const bool pow2 = ((rq & (rq - 1)) | (sny & (sny - 1))) == 0;
+  const int rq_sh = __ffs(rq) - 1, ny_sh = __ffs(sny) - 1;
 
   const int64_t ngroups = nvox >> 2;  // whole groups of 4 voxels; the tail is handled below
   const int64_t stride = (int64_t)gridDim.x * GMM_THREADS;
@@ -93,7 +98,18 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
     o.y = fmaxf(add_rn(m1.x, mul_rn(m1.y, n.y)), 0.f);
     o.z = fmaxf(add_rn(m2.x, mul_rn(m2.y, n.z)), 0.f);
     o.w = fmaxf(add_rn(m3.x, mul_rn(m3.y, n.w)), 0.f);
-    if (out) *reinterpret_cast<float4*>(out + v0) = o;
+    if (surf) {
+      const uint32_t gg = (uint32_t)g;
+      uint32_t row, z4, x, y;
+      if (pow2) {
+        row = gg >> rq_sh, z4 = gg & (rq - 1), x = row >> ny_sh, y = row & (sny - 1);
+      } else {
+        row = gg / rq, z4 = gg - row * rq, x = row / sny, y = row - x * sny;
+      }
+      surf2DLayeredwrite<float4>(o, (cudaSurfaceObject_t)surf, (int)(z4 * 16u), (int)y, (int)x);
+    } else if (out) {
+      *reinterpret_cast<float4*>(out + v0) = o;
+    }
     if (lab_out) *reinterpret_cast<uint32_t*>(lab_out + v0) = lab4;
     }
     if (pairs) {  // block-uniform
@@ -253,7 +269,10 @@ extern "C" int fsg_gmm(const fsg_gmm_job* jobs, int njobs, int64_t nvox, void* s
   int nseed = -1;
   for (int i = 0; i < njobs; ++i) {
     const fsg_gmm_job& j = jobs[i];
-    FSG_REQUIRE((j.out || j.out_pairs) && j.mus && j.sigmas, "fsg_gmm: job %d has a NULL out/mus/sigmas", i);
+    FSG_REQUIRE((j.out || j.out_pairs || j.out_surf) && j.mus && j.sigmas, "fsg_gmm: job %d has a NULL out/mus/sigmas", i);
+    if (j.out_surf)
+      FSG_REQUIRE(!j.out && !j.out_pairs && j.row_len >= 4 && j.row_len % 4 == 0 && j.surf_ny >= 1 && nvox % ((int64_t)j.row_len * j.surf_ny) == 0,
+                  "fsg_gmm: job %d: out_surf needs row_len (nz, a multiple of 4) and surf_ny with nz * ny dividing nvox, and no other output", i);
     if (j.out_pairs)
       FSG_REQUIRE(j.row_len >= 1 && nvox % j.row_len == 0 && nvox % 4 == 0 && (reinterpret_cast<uintptr_t>(j.out_pairs) & 15) == 0,
                   "fsg_gmm: job %d: out_pairs needs row_len dividing nvox, nvox %% 4 == 0 and a 16-byte aligned buffer", i);

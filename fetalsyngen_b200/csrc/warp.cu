@@ -362,14 +362,48 @@ __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(const __grid_constan
 //   * gamma and bias share one exponential: v' = 2^(gamma*lg2 v + (1-gamma) lg2 300 + bf*lg2 e).
 // Coordinates (and therefore the nearest-neighbour segmentation) stay bit-exact: the chain of
 // separately rounded mul/add is unchanged.
+// FSG_WARP_PIN: loop invariants kept in ordinary registers through an opaque asm (ptxas otherwise re-derives them
+// from the constant bank inside the inner loop): bit 0 the affine (12 registers), bit 1 the strides / texture
+// handle, bit 2 the clamp bounds.  r02, texture variant: inner loop of two voxels 238 -> 208 instructions with 6.
+#ifndef FSG_WARP_PIN
+#define FSG_WARP_PIN 6
+#endif
 #ifndef FSG_WARP_MINBLOCKS
 #define FSG_WARP_MINBLOCKS 3  // <= 85 registers: 3 blocks of 256 threads per SM
+#endif
+// The texture variant is bound by texture latency and issue slots together: 4 resident blocks (64 registers, no
+// spills with FSG_WARP_PIN=6) measured 0.655 ms against 0.70 ms with 3 (r02, 8 volumes of 256^3); the linear
+// variants spill at 64 registers and stay at 3.
+#ifndef FSG_WARP_MINBLOCKS_TEX
+#define FSG_WARP_MINBLOCKS_TEX 4
 #endif
 // PAIRS: the source image is fsg_gmm's out_pairs volume — 16-bit fixed point (I[z] | I[z+1] << 16), so
 // ONE 32-bit gather brings both z corners of an (x, y) row: four gather instructions per voxel instead
 // of eight (the kernel is bound by L1 wavefronts per gather, not by bytes).
+// PAIRS == 3: the source image is a block-linear fsg_texvol (job.src_tex): the 2x2 (y, z) footprint of each
+// of the two x layers comes from ONE texture gather (tld4), so a voxel costs two texture instructions instead
+// of eight global loads.  The gather returns the raw float32 texels: same values, same blend, same result.
+__device__ __forceinline__ float4 tex_gather_yz(unsigned long long tex, int layer, float u, float v) {
+  float4 r;  // (z0,y1), (z1,y1), (z1,y0), (z0,y0) for the footprint z0 = floor(u - 0.5), y0 = floor(v - 0.5)
+  asm("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%8}];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(tex), "r"(layer), "f"(u), "f"(v), "f"(0.f));
+  return r;
+}
+
+// Trilinear blend of one voxel from its two gathers (x layers l and l+1), in the order of the packed code below
+// (x, then y, then z; every step a fused multiply-add), so the result is bit-identical to it.  The x blend runs
+// as two packed FMAs on the register pairs as the texture unit returns them: (x, y) = row y1 at (z0, z1),
+// (z, w) = row y0 at (z1, z0).
+__device__ __forceinline__ float tex_blend(const float4 g0, const float4 g1, float wx, float wy, float wz) {
+  const P2 w = pk(wx, wx), lo1 = pk(g0.x, g0.y), lo0 = pk(g0.z, g0.w);
+  float c10, c11, c01, c00;
+  upk(fma2(w, sub2(pk(g1.x, g1.y), lo1), lo1), c10, c11);
+  upk(fma2(w, sub2(pk(g1.z, g1.w), lo0), lo0), c01, c00);
+  const float c0_ = __fmaf_rn(wy, __fsub_rn(c10, c00), c00), c1_ = __fmaf_rn(wy, __fsub_rn(c11, c01), c01);
+  return __fmaf_rn(wz, __fsub_rn(c1_, c0_), c0_);
+}
+
 template <bool EPI, int PAIRS>
-__global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
+__global__ void __launch_bounds__(WARP_THREADS, PAIRS == 3 ? FSG_WARP_MINBLOCKS_TEX : FSG_WARP_MINBLOCKS) warp_fast_kernel(const __grid_constant__ Batch<fsg_warp_job> batch, int sx, int sy, int sz) {
   const fsg_warp_job& job = batch.j[blockIdx.z];
   const int tid = threadIdx.x;
   extern __shared__ float4 s_dyn[];
@@ -418,15 +452,38 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
   }
   __syncthreads();
 
-  const Affine aff(job);
+  Affine aff(job);
+#if FSG_WARP_PIN & 1
+  // keep the affine in ordinary registers: ptxas otherwise re-reads the twelve values from the constant bank
+  // (eleven LDCU + the block-index arithmetic) in every iteration of the inner loop
+#pragma unroll
+  for (int q = 0; q < 9; ++q) asm volatile("" : "+f"(aff.a[q]));
+#pragma unroll
+  for (int q = 0; q < 3; ++q) asm volatile("" : "+f"(aff.c[q]));
+#endif
   const float cen_x = job.center[0], cen_y = job.center[1], cen_z = job.center[2];
-  const float mx = (float)(sx - 1), my = (float)(sy - 1), mz = (float)(sz - 1);
+  float mx = (float)(sx - 1), my = (float)(sy - 1), mz = (float)(sz - 1);
   // largest floats below S-1: floor(min(c, that)) <= S-2
-  const float lx = __int_as_float(__float_as_int(mx) - 1), ly = __int_as_float(__float_as_int(my) - 1), lz = __int_as_float(__float_as_int(mz) - 1);
+  float lx = __int_as_float(__float_as_int(mx) - 1), ly = __int_as_float(__float_as_int(my) - 1), lz = __int_as_float(__float_as_int(mz) - 1);
   const int plane = sy * sz;
-  const int xs = job.flip ? -plane : plane;
+  int xs = job.flip ? -plane : plane;
+#if FSG_WARP_PIN & 2
+  asm volatile("" : "+r"(xs));
+#endif
+#if FSG_WARP_PIN & 4
+  asm volatile("" : "+f"(mx), "+f"(my), "+f"(mz), "+f"(lx), "+f"(ly), "+f"(lz));
+#endif
   // index = fx*xs + fy*sz + fz with all three taken as raw float bits of (value + 2^23)
   const unsigned kbias = (unsigned)(job.flip ? (sx - 1) * plane : 0) - 0x4B000000u * (unsigned)(xs + sz + 1);
+  unsigned long long src_tex = job.src_tex;
+  int lay0 = job.flip ? sx - 1 : 0, lstep = job.flip ? -1 : 1;  // texture layer of floor index l: lay0 + lstep * l
+  int fzn = fz_n;
+#if FSG_WARP_PIN & 2
+  asm volatile("" : "+l"(src_tex));
+  asm volatile("" : "+r"(lay0));
+  asm volatile("" : "+r"(lstep));
+  asm volatile("" : "+r"(fzn));
+#endif
   const float* __restrict__ const src_img = PAIRS ? reinterpret_cast<const float*>(job.src_pairs) : job.src_img;
   const uint8_t* __restrict__ const src_seg = job.src_seg;
   float* __restrict__ const dst_img = job.dst_img;
@@ -451,7 +508,7 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
     const float4* pf = s_f + tf.f;
     const float4* pc = s_f + tf.c;
     unsigned o_row = (unsigned)((x0 * sy + y0) * sz + k);
-    int row = 0;
+    int row = 0, roff = 0;  // roff = row * fzn
 #pragma unroll 1
     for (int ry = 0; ry < WY; ++ry, o_row += sz) {
       const float yc = sub_rn((float)(y0 + ry), cen_y);
@@ -459,10 +516,10 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
       P2 xi2 = pk((float)x0, (float)(x0 + 1));
       unsigned o = o_row;
 #pragma unroll 1
-      for (int rx = 0; rx < WX; rx += 2, row += 2, o += 2 * plane, xi2 = add2(xi2, pk(2.0f, 2.0f))) {
+      for (int rx = 0; rx < WX; rx += 2, row += 2, roff += 2 * fzn, o += 2 * plane, xi2 = add2(xi2, pk(2.0f, 2.0f))) {
         // two voxels (i, j, k) and (i+1, j, k): products stay scalar FMULs (separately rounded, ptxas
         // would contract a packed mul feeding a packed add), every add is one packed FADD2
-        const float4 f0a = pf[row * fz_n], f1a = pc[row * fz_n], f0b = pf[(row + 1) * fz_n], f1b = pc[(row + 1) * fz_n];
+        const float4 f0a = pf[roff], f1a = pc[roff], f0b = pf[roff + fzn], f1b = pc[roff + fzn];
         const P2 fx = add2(pk(mul_rn(tf.wf, f0a.x), mul_rn(tf.wf, f0b.x)), pk(mul_rn(tf.wc, f1a.x), mul_rn(tf.wc, f1b.x)));
         const P2 fy = add2(pk(mul_rn(tf.wf, f0a.y), mul_rn(tf.wf, f0b.y)), pk(mul_rn(tf.wc, f1a.y), mul_rn(tf.wc, f1b.y)));
         const P2 fz = add2(pk(mul_rn(tf.wf, f0a.z), mul_rn(tf.wf, f0b.z)), pk(mul_rn(tf.wc, f1a.z), mul_rn(tf.wc, f1b.z)));
@@ -498,7 +555,20 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
         const char* b10 = b00 + by_plane;
         const char* b11 = b10 + by_row;
         P2 c000, c001, c010, c011, c100, c101, c110, c111;
-        if (PAIRS == 2) {  // float2 (I[z], I[z+1]): both z corners of a row in one 8-byte gather, exact
+        float4 tex_a0, tex_a1, tex_b0, tex_b1;
+        if (PAIRS == 3) {
+          // floor indices back from the magic-biased floats: layer = x (mirrored when flipped), texel centre
+          // of the footprint's far corner = floor + 1 (the gather takes floor(u - 0.5) and the next texel)
+          const int la = __float_as_int(txa) - 0x4B000000, lb = __float_as_int(txb) - 0x4B000000;
+          const int la0 = lay0 + lstep * la, lb0 = lay0 + lstep * lb;
+          float ua, ub, va_, vb_;
+          upk(add2(sub2(tz2, magic2), pk(1.0f, 1.0f)), ua, ub);
+          upk(add2(sub2(ty2, magic2), pk(1.0f, 1.0f)), va_, vb_);
+          const float4 ga0 = tex_gather_yz(src_tex, la0, ua, va_), ga1 = tex_gather_yz(src_tex, la0 + lstep, ua, va_);
+          const float4 gb0 = tex_gather_yz(src_tex, lb0, ub, vb_), gb1 = tex_gather_yz(src_tex, lb0 + lstep, ub, vb_);
+          // blended per voxel (below) on the register pairs the gathers return: no repacking across the two voxels
+          tex_a0 = ga0, tex_a1 = ga1, tex_b0 = gb0, tex_b1 = gb1;
+        } else if (PAIRS == 2) {  // float2 (I[z], I[z+1]): both z corners of a row in one 8-byte gather, exact
 #define LD2(p) __ldg(reinterpret_cast<const float2*>(p))
           const float2 qa00 = LD2(a00), qa01 = LD2(a01), qa10 = LD2(a10), qa11 = LD2(a11);
           const float2 qb00 = LD2(b00), qb01 = LD2(b01), qb10 = LD2(b10), qb11 = LD2(b11);
@@ -549,11 +619,20 @@ __global__ void __launch_bounds__(WARP_THREADS, FSG_WARP_MINBLOCKS) warp_fast_ke
         const uint8_t laba = __ldg(src_seg + ((unsigned)__float_as_int(sxa) * (unsigned)xs + (unsigned)__float_as_int(sya) * (unsigned)sz + (unsigned)__float_as_int(sza) + kbias));
         const uint8_t labb = __ldg(src_seg + ((unsigned)__float_as_int(sxb) * (unsigned)xs + (unsigned)__float_as_int(syb) * (unsigned)sz + (unsigned)__float_as_int(szb) + kbias));
         // ---- trilinear blend (image path: fused, packed)
-        const P2 c00 = fma2(wx2, sub2(c100, c000), c000), c01 = fma2(wx2, sub2(c101, c001), c001);
-        const P2 c10 = fma2(wx2, sub2(c110, c010), c010), c11 = fma2(wx2, sub2(c111, c011), c011);
-        const P2 c0_ = fma2(wy2, sub2(c10, c00), c00), c1_ = fma2(wy2, sub2(c11, c01), c01);
         float va, vb;
-        upk(fma2(wz2, sub2(c1_, c0_), c0_), va, vb);
+        if (PAIRS == 3) {
+          float wxa, wxb, wya, wyb, wza, wzb;
+          upk(wx2, wxa, wxb);
+          upk(wy2, wya, wyb);
+          upk(wz2, wza, wzb);
+          va = tex_blend(tex_a0, tex_a1, wxa, wya, wza);
+          vb = tex_blend(tex_b0, tex_b1, wxb, wyb, wzb);
+        } else {
+          const P2 c00 = fma2(wx2, sub2(c100, c000), c000), c01 = fma2(wx2, sub2(c101, c001), c001);
+          const P2 c10 = fma2(wx2, sub2(c110, c010), c010), c11 = fma2(wx2, sub2(c111, c011), c011);
+          const P2 c0_ = fma2(wy2, sub2(c10, c00), c00), c1_ = fma2(wy2, sub2(c11, c01), c01);
+          upk(fma2(wz2, sub2(c1_, c0_), c0_), va, vb);
+        }
         va = fminf(fminf(iia, jja), kka) > 0.f ? va : 0.f;
         vb = fminf(fminf(iib, jjb), kkb) > 0.f ? vb : 0.f;
         if (PAIRS == 1 && !EPI) {
@@ -605,7 +684,8 @@ static int validate(const fsg_warp_job* jobs, int njobs, int sx, int sy, int sz,
     }
     if (need_io) {
       FSG_REQUIRE(j.dst_img || j.dst_seg || j.dst_img2, "%s: job %d has no output", who, n);
-      FSG_REQUIRE(!j.dst_img || j.src_img || j.src_pairs, "%s: job %d dst_img without src_img", who, n);
+      FSG_REQUIRE(!j.dst_img || j.src_img || j.src_pairs || j.src_tex, "%s: job %d dst_img without src_img", who, n);
+      FSG_REQUIRE(!j.src_tex || (!j.src_img && !j.src_pairs), "%s: job %d has both a texture and a linear source image", who, n);
       FSG_REQUIRE(!j.dst_seg || j.src_seg, "%s: job %d dst_seg without src_seg", who, n);
       FSG_REQUIRE(!j.dst_img2 || j.src_img2, "%s: job %d dst_img2 without src_img2", who, n);
       FSG_REQUIRE(j.dst_img != j.src_img || !j.dst_img || (j.mode == 0 && !j.flip), "%s: job %d in-place warp is not allowed", who, n);
@@ -647,7 +727,7 @@ extern "C" int fsg_warp_shift(const fsg_warp_job* jobs, int njobs, int sx, int s
 
 // A job takes the fast kernel when it is the production case; `epi` = it has a gamma or bias epilogue.
 static bool fast_eligible(const fsg_warp_job& j, int sx, int sy, int sz) {
-  return j.mode == 1 && j.fsmall && (j.src_img || j.src_pairs) && j.dst_img && j.src_seg && j.dst_seg && !j.dst_img2 && sx % WX == 0 && sy % WY == 0 && sx >= 2 && sy >= 2 &&
+  return j.mode == 1 && j.fsmall && (j.src_img || j.src_pairs || j.src_tex) && j.dst_img && j.src_seg && j.dst_seg && !j.dst_img2 && sx % WX == 0 && sy % WY == 0 && sx >= 2 && sy >= 2 &&
          sz >= 2 && (!j.bf_low || j.dst_img);
 }
 
@@ -657,18 +737,19 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
   // partition the batch: fast kernel with / without epilogue, generic kernel for everything else
   // groups: 0/1 = fast kernel on a float source with / without epilogue, 2 = generic, 3/4 = fast kernel on
   // the fixed-point pairs source with / without epilogue
-  fsg_warp_job part[7][FSG_MAX_JOBS];  // 5/6: fast kernel on the float2 pairs source with / without epilogue
-  int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+  fsg_warp_job part[9][FSG_MAX_JOBS];  // 5/6: fast kernel on the float2 pairs source, 7/8: on the block-linear texture source
+  int cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int n = 0; n < njobs; ++n) {
     const fsg_warp_job& j = jobs[n];
     const bool fast = fast_eligible(j, sx, sy, sz);
     FSG_REQUIRE(!j.src_pairs || (fast && (reinterpret_cast<uintptr_t>(j.src_pairs) & (j.pairs_float ? 7 : 3)) == 0), "fsg_warp: job %d: src_pairs is only read by the fast path", n);
-    const int g = !fast ? 2 : ((j.src_pairs ? (j.pairs_float ? 5 : 3) : 0) + ((j.has_gamma || j.bf_low) ? 0 : 1));
+    FSG_REQUIRE(!j.src_tex || fast, "fsg_warp: job %d: a texture source (src_tex) is only read by the fast path (deformation with a control grid, tile-aligned extents)", n);
+    const int g = !fast ? 2 : ((j.src_tex ? 7 : (j.src_pairs ? (j.pairs_float ? 5 : 3) : 0)) + ((j.has_gamma || j.bf_low) ? 0 : 1));
     part[g][cnt[g]++] = j;
   }
   cudaStream_t s = as_stream(stream);
   Batch<fsg_warp_job> b;
-  for (int g = 0; g < 7; ++g) {
+  for (int g = 0; g < 9; ++g) {
     if (!cnt[g] || g == 2) continue;
     // FSG_WARP_TILE=1 selects the TMA-staged cubic-tile variant (warp_tile.cu).  It is parity-green
     // but measured 2.4x slower than the full-z kernel at 256^3 (r01e: 2.17 ms vs 0.90 ms per 8
@@ -697,8 +778,12 @@ extern "C" int fsg_warp(const fsg_warp_job* jobs, int njobs, int sx, int sy, int
       warp_fast_kernel<false, 1><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
     else if (g == 5)
       warp_fast_kernel<true, 2><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
-    else
+    else if (g == 6)
       warp_fast_kernel<false, 2><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else if (g == 7)
+      warp_fast_kernel<true, 3><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
+    else
+      warp_fast_kernel<false, 3><<<grid, WARP_THREADS, smem, s>>>(b, sx, sy, sz);
   }
   if (cnt[2]) {
     if (int rc = fill_batch(b, part[2], cnt[2])) return rc;

@@ -24,6 +24,33 @@ STAGE_GMM, STAGE_NOISE, STAGE_FIELD, STAGE_BIAS = 1, 2, 3, 4
 # gather per row in the warp; the GMM kernel writes 8 instead of 4 bytes per voxel.
 _PAIRS_MODE = int(__import__("os").environ.get("FSG_GMM_PAIRS", "0") or 0)
 _PAIRS = _PAIRS_MODE in (1, 2)
+# FSG_WARP_TEX (default 1): samples that take the warp fast path get their GMM image written into a block-linear
+# layered array (fsg_texvol) and gathered with two tld4 texture instructions per voxel instead of eight global
+# loads; results are bit-identical to the linear path (FSG_WARP_TEX=0).
+# The opt-in experiments on the linear source (FSG_GMM_PAIRS, FSG_WARP_TILE, FSG_WARP_PIPE) switch it off.
+_env = __import__("os").environ
+_TEX = (_env.get("FSG_WARP_TEX", "1") or "1") != "0" and not _PAIRS and _env.get("FSG_WARP_TILE", "0") in ("", "0") and _env.get("FSG_WARP_PIPE", "0") in ("", "0")
+
+
+class TexVolume:
+    """One block-linear intensity volume (``fsg_texvol``): CUDA array + texture + surface handles."""
+
+    def __init__(self, shape):
+        self.h = _lib.TexVol()
+        _lib.call("fsg_texvol_create", int(shape[0]), int(shape[1]), int(shape[2]), C.byref(self.h))
+
+    def upload(self, linear: torch.Tensor):
+        _lib.call("fsg_texvol_copy", C.byref(self.h), linear.data_ptr(), 0, _stream())
+
+    def download(self, linear: torch.Tensor):
+        _lib.call("fsg_texvol_copy", C.byref(self.h), linear.data_ptr(), 1, _stream())
+
+    def __del__(self):
+        try:
+            if self.h.array:
+                _lib.call("fsg_texvol_destroy", C.byref(self.h))
+        except Exception:
+            pass
 
 
 @dataclass
@@ -86,6 +113,8 @@ class SynthEngine:
         self.tables = DeviceTables(self.device)
         self._scratch: dict = {}
         self._batch = None
+        self.use_tex = _TEX
+        self._texvols: list = []
 
     # ------------------------------------------------------------------ memory
     def scratch(self, name: str, batch: int, dtype=torch.float32, numel=None) -> torch.Tensor:
@@ -99,6 +128,12 @@ class SynthEngine:
             t = torch.empty((batch, pitch), dtype=dtype, device=self.device)
             self._scratch[key] = t
         return t[:, :numel] if t.shape[1] != numel else t
+
+    def texvol(self, b: int) -> TexVolume:
+        """The b-th block-linear intensity volume of this engine (created on first use)."""
+        while len(self._texvols) <= b:
+            self._texvols.append(TexVolume(self.shape))
+        return self._texvols[b]
 
     RING_SLOTS, RING_FLOATS = 8, 1 << 19
 
@@ -195,11 +230,12 @@ class SynthEngine:
         return views
 
     # ------------------------------------------------------------------ K1
-    def gmm(self, plans, seeds, out: torch.Tensor, labels_out=None, pairs=None):
+    def gmm(self, plans, seeds, out: torch.Tensor, labels_out=None, pairs=None, tex=None):
         """seeds[b]: list of 1..4 int8/uint8 device volumes summed into the label map, or ``(PackedSeeds,
         mlabel2subclusters)``: the labels are decoded in the kernel from the subject's bit-packed seed words
         (2 bytes per voxel, no unpack pass).  pairs[b] True: sample b is written in the fixed-point pairs format
-        of the warp fast path (same 4 bytes per voxel, into the same buffer) instead of float32."""
+        of the warp fast path (same 4 bytes per voxel, into the same buffer) instead of float32.  tex[b] a
+        ``TexVolume``: sample b is written into that block-linear volume instead of out[b]."""
         B = len(plans)
         nvox = int(out.shape[-1]) if torch.is_tensor(out) else self.nvox  # a list mixes [N] outputs and [2N] float-pair outputs
         small = self.upload([p.mus for p in plans] + [p.sigmas for p in plans])
@@ -233,7 +269,9 @@ class SynthEngine:
             j.mus, j.sigmas = small[b].data_ptr(), small[B + b].data_ptr()
             j.nlabels = int(p.mus.size)
             j.noise = _ptr(None if p.gmm_noise is None else _check(p.gmm_noise, torch.float32, self.device, "gmm_noise"))
-            if pairs is not None and pairs[b]:
+            if tex is not None and tex[b] is not None:
+                j.out, j.out_surf, j.row_len, j.surf_ny = None, tex[b].h.surf, int(self.shape[2]), int(self.shape[1])
+            elif pairs is not None and pairs[b]:
                 j.out, j.out_pairs, j.row_len = None, out[b].data_ptr(), int(self.shape[2])
                 j.pairs_float = 1 if _PAIRS_MODE == 2 else 0
             else:
@@ -253,7 +291,7 @@ class SynthEngine:
         self._keep = (small,)
 
     # ------------------------------------------------------------------ K2
-    def _warp_jobs(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True, pairs=None):
+    def _warp_jobs(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True, pairs=None, tex=None):
         B = len(plans)
         sx, sy, sz = self.shape
         arrays, slots, gjobs = [], [], []
@@ -292,7 +330,9 @@ class SynthEngine:
         for b, p in enumerate(plans):
             j = jobs[b]
             j.src_img, j.dst_img = _ptr(None if src_img is None else src_img[b]), _ptr(None if dst_img is None else dst_img[b])
-            if pairs is not None and pairs[b]:
+            if tex is not None and tex[b] is not None:
+                j.src_img, j.src_tex = None, tex[b].h.tex
+            elif pairs is not None and pairs[b]:
                 j.src_img, j.src_pairs = None, _ptr(src_img[b])
                 j.pairs_float = 1 if _PAIRS_MODE == 2 else 0
             j.src_seg, j.dst_seg = _ptr(None if src_seg is None else src_seg[b]), _ptr(None if dst_seg is None else dst_seg[b])
@@ -325,10 +365,10 @@ class SynthEngine:
                     j.btab[a] = self.tables.zoom(bs[a], self.shape[a] / bs[a], self.shape[a]).data_ptr()
         return jobs, keep
 
-    def warp(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True, pairs=None):
+    def warp(self, plans, src_img, src_seg, dst_img, dst_seg, src_img2=None, dst_img2=None, epilogue=True, pairs=None, tex=None):
         B = len(plans)
         sx, sy, sz = self.shape
-        jobs, keep = self._warp_jobs(plans, src_img, src_seg, dst_img, dst_seg, src_img2, dst_img2, epilogue, pairs)
+        jobs, keep = self._warp_jobs(plans, src_img, src_seg, dst_img, dst_seg, src_img2, dst_img2, epilogue, pairs, tex)
         didx = [b for b, p in enumerate(plans) if p.deform]
         if didx:
             dj = (_lib.WarpJob * len(didx))(*[jobs[b] for b in didx])
@@ -581,19 +621,26 @@ class SynthEngine:
         sx, sy, sz = self.shape
         return bool(_PAIRS and p.deform and (p.fsmall is not None or p.fsmall_dev is not None) and sx % 8 == 0 and sy % 4 == 0 and sz % 4 == 0 and min(self.shape) >= 2)
 
+    def tex_eligible(self, p) -> bool:
+        """Same condition as ``pairs_eligible`` (the GMM image is read by the warp fast path only): hand it over
+        in a block-linear texture volume."""
+        sx, sy, sz = self.shape
+        return bool(self.use_tex and p.deform and (p.fsmall is not None or p.fsmall_dev is not None) and sx % 8 == 0 and sy % 4 == 0 and sz % 4 == 0 and min(self.shape) >= 2)
+
     def _run_base(self, plans, seeds, segs, out_img, out_seg, scale, buf0, buf1, buf2):
         B = len(plans)
-        pairs = [self.pairs_eligible(p) for p in plans]
+        tex = [self.texvol(b) if self.tex_eligible(p) else None for b, p in enumerate(plans)]
+        pairs = [tex[b] is None and self.pairs_eligible(p) for b, p in enumerate(plans)]
         gmm_out = buf0
         if _PAIRS_MODE == 2 and any(pairs):  # float2 pairs need 8 bytes per voxel: their own scratch volume
             wide = self.scratch("gmm_fpairs", B, torch.float32, 2 * self.nvox)
             gmm_out = [wide[b] if pairs[b] else buf0[b] for b in range(B)]
-        self.gmm(plans, seeds, gmm_out, pairs=pairs)
+        self.gmm(plans, seeds, gmm_out, pairs=pairs, tex=tex)
         rs = [b for b, p in enumerate(plans) if p.spacing is not None]
         no_rs = [b for b, p in enumerate(plans) if p.spacing is None]
         # warp straight into the output for samples that skip the resolution simulation
         warp_dst = [out_img[b].view(-1) if (plans[b].spacing is None and plans[b].noise_std is None) else buf1[b] for b in range(B)]
-        self.warp(plans, gmm_out, segs, warp_dst, out_seg, pairs=pairs)
+        self.warp(plans, gmm_out, segs, warp_dst, out_seg, pairs=pairs, tex=tex)
         if rs:
             sub = [plans[b] for b in rs]
             # x pass -> buf2, y pass -> buf0 (the GMM image is dead), z pass (+noise) -> buf2

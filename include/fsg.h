@@ -49,6 +49,25 @@ typedef struct fsg_rng {
   uint32_t _pad;
 } fsg_rng;
 
+/* Block-linear intensity volume: a layered 2-D CUDA array (layer = x, row = y, column = z; float32) with a
+ * surface object, through which fsg_gmm writes it, and a point-sampled texture object, through which
+ * fsg_warp's fast path fetches the 2x2 (y, z) footprint of a trilinear sample with ONE texture gather (tld4)
+ * per x layer: two texture instructions per voxel instead of eight global loads, on the texture unit's
+ * tiled addressing instead of the load/store unit's 128-byte lines (the gather of a rotated row crosses
+ * many lines; measured r02: warp 0.91 -> see DESIGN.md).  The texel values are the same float32 bits,
+ * so results are identical to the linear path.  Handles are plain 64-bit integers (cudaArray_t,
+ * cudaTextureObject_t, cudaSurfaceObject_t). */
+typedef struct fsg_texvol {
+  uint64_t array;
+  uint64_t tex;
+  uint64_t surf;
+  int32_t nx, ny, nz, _pad;
+} fsg_texvol;
+int fsg_texvol_create(int nx, int ny, int nz, fsg_texvol* out);
+int fsg_texvol_destroy(fsg_texvol* v);
+/* linear [nx][ny][nz] float32 device volume <-> the array (to_linear != 0: array -> linear); tests and debugging */
+int fsg_texvol_copy(const fsg_texvol* v, float* linear_dev, int to_linear, void* stream);
+
 /* K1 — GMM intensity synthesis. Replaces ImageFromSeeds.sample_intensities' per-voxel part
  * (generator/intensity/rand_gmm.py:146-149) fused with the seed sum of load_seeds
  * (rand_gmm.py:90-97): L = sum(seed[m]); I = max(0, mus[L] + sigmas[L] * N). */
@@ -74,6 +93,10 @@ typedef struct fsg_gmm_job {
   const void* words;     /* [nvox] uint16 / uint32 (device), 16-byte aligned, or NULL */
   int32_t shift[4];
   int32_t mask[4];
+  uint64_t out_surf;     /* fsg_texvol.surf: write the intensities into the block-linear volume instead of `out`
+                          * (row_len = nz, surf_ny = ny; nvox = nx * ny * nz, nz % 4 == 0), or 0 */
+  int32_t surf_ny;
+  int32_t _pad2;
 } fsg_gmm_job;
 int fsg_gmm(const fsg_gmm_job* jobs_host, int njobs, int64_t nvox, void* stream);
 
@@ -107,6 +130,7 @@ typedef struct fsg_warp_job {
   int32_t flip;
   int32_t has_gamma;
   int32_t pairs_float;    /* src_pairs holds fsg_gmm's float2 pairs (pairs_float there) instead of fixed point */
+  uint64_t src_tex;       /* fsg_texvol.tex of the source image instead of src_img (fast path only), or 0 */
 } fsg_warp_job;
 /* Pre-pass: writes floor(min over the volume of the clamped coordinate) per axis into
  * job.shift (affine_nonrigid.py:350-358).  No volume traffic; coordinates are recomputed. */

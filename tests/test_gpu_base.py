@@ -360,6 +360,44 @@ def test_warp_kernel_variants_agree(monkeypatch):
         res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, FSG_WARP_PIPE="1", FSG_WARP_TILE="0", **extra), timeout=300)
         assert res.returncode == 0, res.stderr[-1500:]
         assert float(res.stdout.split("ERR")[1]) <= TOL
+    # the linear float32 hand-over (FSG_WARP_TEX=0; the default gathers from a block-linear texture volume)
+    assert eng.use_tex and eng.tex_eligible(plan)
+    eng.use_tex = False
+    try:
+        img1, sg1 = eng.run_base([plan], [seeds_from_golden(d)], [seg], scale=False)
+    finally:
+        eng.use_tex = True
+    assert torch.equal(img0, img1) and torch.equal(sg0, sg1)
+
+
+def test_texture_volume_round_trip_and_non_power_of_two_extents():
+    """fsg_texvol: linear -> array -> linear is the identity; fsg_gmm's surface output equals its linear output
+    on extents whose row and plane counts are not powers of two (the kernel's division path)."""
+    from fetalsyngen_b200.engine import TexVolume
+
+    rs = np.random.RandomState(4)
+    for shape in [(40, 36, 44), (8, 4, 4), (16, 100, 12)]:
+        n = int(np.prod(shape))
+        x = torch.from_numpy(rs.randn(n).astype(np.float32)).to(DEV)
+        tv = TexVolume(shape)
+        tv.upload(x)
+        y = torch.empty_like(x)
+        tv.download(y)
+        torch.cuda.synchronize()
+        assert torch.equal(x, y)
+        seg, seeds = _phantom(rs, shape)
+        p = _random_plan(rs, shape, DEV)
+        eng = engine_for(DEV, shape, (0.5, 0.5, 0.5))
+        sd = [[torch.from_numpy(v).to(DEV).view(-1) for v in seeds]]
+        lin = torch.empty((1, n), dtype=torch.float32, device=DEV)
+        for philox in (False, True):
+            if philox:
+                p.gmm_noise, p.rng_seed, p.sample_id = None, 3, 1
+            eng.gmm([p], sd, lin)
+            eng.gmm([p], sd, [None], tex=[tv])
+            tv.download(y)
+            torch.cuda.synchronize()
+            assert torch.equal(lin[0], y), (shape, philox)
 
 
 def test_sample_batch_streams_do_not_depend_on_the_sharding():

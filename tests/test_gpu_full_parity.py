@@ -144,3 +144,42 @@ def test_gmm_reads_packed_seed_words_directly():
     for b in range(3):
         assert np.array_equal(lab_a[b].cpu().numpy().reshape(seg.shape), unpack_numpy(words, counts, sel[b]))
     assert torch.equal(lab_a, lab_b) and torch.equal(out_a, out_b)
+
+
+def test_texture_gather_hand_over_is_bit_identical_at_256():
+    """The default GMM -> warp hand-over (block-linear fsg_texvol written through a surface, gathered with tld4)
+    against the linear float32 hand-over (FSG_WARP_TEX=0): image and segmentation bit for bit, for flipped and
+    unflipped samples with Philox noise in one batched launch; the GMM kernel's surface output equals its linear
+    output."""
+    from fetalsyngen_b200.engine import SamplePlan, TexVolume
+
+    rs = np.random.RandomState(77)
+    eng = engine_for(DEV, (256, 256, 256), RES)
+    assert eng.use_tex, "the texture hand-over is the default"
+    plans, seeds, segs = [], [], []
+    for b, (subject, flip, resample) in enumerate([("sub-sta21", True, True), ("sub-sta30", False, True), ("sub-sta38", True, False)]):
+        seg, words, counts = load_subject(subject)
+        q = _random_params(rs, tuple(seg.shape), flip, resample)
+        p = _plan_from_params(q)
+        p.gmm_noise, p.noise, p.rng_seed, p.sample_id = None, None, 123, b
+        assert eng.tex_eligible(p)
+        plans.append(p)
+        seeds.append((PackedSeeds(words, counts, device=DEV), {m: int(rs.randint(1, 7)) for m in range(1, 5)}))
+        segs.append(torch.from_numpy(seg).to(DEV).view(-1))
+    img_t, seg_t = eng.run_base(plans, seeds, segs)
+    eng.use_tex = False
+    try:
+        img_l, seg_l = eng.run_base(plans, seeds, segs)
+    finally:
+        eng.use_tex = True
+    assert torch.equal(seg_t, seg_l) and torch.equal(img_t, img_l)
+    # the GMM stage alone: surface output read back == linear output
+    lin = torch.empty((3, eng.nvox), dtype=torch.float32, device=DEV)
+    eng.gmm(plans, seeds, lin)
+    vols = [TexVolume(eng.shape) for _ in range(3)]
+    eng.gmm(plans, seeds, [None] * 3, tex=vols)
+    back = torch.empty_like(lin)
+    for b in range(3):
+        vols[b].download(back[b])
+    torch.cuda.synchronize()
+    assert torch.equal(back, lin)
