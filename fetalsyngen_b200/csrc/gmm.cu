@@ -61,13 +61,41 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
   const uint32_t rq = surf ? (uint32_t)row_len >> 2 : 1u, sny = surf ? (uint32_t)job.surf_ny : 1u;
   const bool pow2 = ((rq & (rq - 1)) | (sny & (sny - 1))) == 0;
   const int rq_sh = __ffs(rq) - 1, ny_sh = __ffs(sny) - 1;
+  // Thread -> group mapping of the surface mode: a warp owns one 64-byte x 8-row tile (a GOB of the block-linear
+  // layout: 4 float4 groups along z times 8 rows), so its 32 stores fill one contiguous 512-byte block of the
+  // array (measured on B200: 5.4 TB/s, the same as linear stores; a warp spread along one row writes eight
+  // 64-byte pieces of eight tiles and reaches 3.4 TB/s).  The group index g — Philox counter and voxel offset —
+  // of a voxel does not depend on which thread handles it.
+  const bool gob = surf && (sny & 7u) == 0 && (rq & 3u) == 0;
+  const uint32_t tiles_z = rq >> 2, tiles_y = sny >> 3;
 
   const int64_t ngroups = nvox >> 2;  // whole groups of 4 voxels; the tail is handled below
   const int64_t stride = (int64_t)gridDim.x * GMM_THREADS;
   int it = 0;
   for (int64_t gbase = (int64_t)blockIdx.x * GMM_THREADS; gbase < ngroups; gbase += stride, it ^= 1) {
-    const int64_t g = gbase + threadIdx.x;
+    int64_t g = gbase + threadIdx.x;
     const bool active = g < ngroups;
+    uint32_t sx_ = 0, sy_ = 0, sz4 = 0;  // surface coordinates of the group
+    if (surf && active) {
+      const uint32_t gi = (uint32_t)g;
+      if (gob) {
+        const uint32_t lane = gi & 31u, tile = gi >> 5;
+        uint32_t zc, t2, y8;
+        if (pow2) {
+          zc = tile & (tiles_z - 1), t2 = tile >> (rq_sh - 2), y8 = t2 & (tiles_y - 1), sx_ = t2 >> (ny_sh - 3);
+        } else {
+          t2 = tile / tiles_z, zc = tile - t2 * tiles_z, sx_ = t2 / tiles_y, y8 = t2 - sx_ * tiles_y;
+        }
+        sy_ = y8 * 8u + (lane >> 2), sz4 = zc * 4u + (lane & 3u);
+        g = (int64_t)((sx_ * sny + sy_) * rq + sz4);
+      } else if (pow2) {
+        const uint32_t row = gi >> rq_sh;
+        sz4 = gi & (rq - 1), sx_ = row >> ny_sh, sy_ = row & (sny - 1);
+      } else {
+        const uint32_t row = gi / rq;
+        sz4 = gi - row * rq, sx_ = row / sny, sy_ = row - sx_ * sny;
+      }
+    }
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
     const int64_t v0 = g * 4;
@@ -99,14 +127,7 @@ __global__ void __launch_bounds__(GMM_THREADS) gmm_kernel(const __grid_constant_
     o.z = fmaxf(add_rn(m2.x, mul_rn(m2.y, n.z)), 0.f);
     o.w = fmaxf(add_rn(m3.x, mul_rn(m3.y, n.w)), 0.f);
     if (surf) {
-      const uint32_t gg = (uint32_t)g;
-      uint32_t row, z4, x, y;
-      if (pow2) {
-        row = gg >> rq_sh, z4 = gg & (rq - 1), x = row >> ny_sh, y = row & (sny - 1);
-      } else {
-        row = gg / rq, z4 = gg - row * rq, x = row / sny, y = row - x * sny;
-      }
-      surf2DLayeredwrite<float4>(o, (cudaSurfaceObject_t)surf, (int)(z4 * 16u), (int)y, (int)x);
+      surf2DLayeredwrite<float4>(o, (cudaSurfaceObject_t)surf, (int)(sz4 * 16u), (int)sy_, (int)sx_);
     } else if (out) {
       *reinterpret_cast<float4*>(out + v0) = o;
     }

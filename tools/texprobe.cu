@@ -132,6 +132,16 @@ __global__ void __launch_bounds__(256) k_store_surf(cudaSurfaceObject_t surf, fl
   float b = seed + i;
   surf2DLayeredwrite<float4>(make_float4(b, b + 1, b + 2, b + 3), surf, z4 * 16, y, x);
 }
+// same bytes, but each warp writes one whole 64-byte x 8-row tile (a GOB of the block-linear layout)
+__global__ void __launch_bounds__(256) k_store_surf_gob(cudaSurfaceObject_t surf, float seed) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  int lane = i & 31, tile = i >> 5;
+  int zc = tile % (S / 16), y8 = (tile / (S / 16)) % (S / 8), x = tile / (S / 16 * (S / 8));
+  int y = y8 * 8 + (lane >> 2), z4 = zc * 4 + (lane & 3);
+  int g = (x * S + y) * (S / 4) + z4;  // the float4 index k_store_surf gives this voxel group
+  float b = seed + g;
+  surf2DLayeredwrite<float4>(make_float4(b, b + 1, b + 2, b + 3), surf, z4 * 16, y, x);
+}
 __global__ void __launch_bounds__(256) k_check_surf(cudaTextureObject_t tex, float seed, int* bad) {
   int i = blockIdx.x * 256 + threadIdx.x;
   int z = i % S, y = (i / S) % S, x = i / (S * S);
@@ -291,10 +301,13 @@ int main() {
       ms = time_ms([&] { k_store_surf<<<g4, 256>>>(surf[v++ % NV], 1.f); });
       cudaError_t e = cudaDeviceSynchronize();
       printf("store surface float4 %.4f ms (%.0f GB/s) %s\n", ms, N * 4 / ms * 1e-6, cudaGetErrorString(e));
+      ms = time_ms([&] { k_store_surf_gob<<<g4, 256>>>(surf[v++ % NV], 1.f); });
+      e = cudaDeviceSynchronize();
+      printf("store surface float4, one GOB per warp %.4f ms (%.0f GB/s) %s\n", ms, N * 4 / ms * 1e-6, cudaGetErrorString(e));
       int* bad;
       cudaMalloc(&bad, 4);
       cudaMemset(bad, 0, 4);
-      k_store_surf<<<g4, 256>>>(surf[0], 7.f);
+      k_store_surf_gob<<<g4, 256>>>(surf[0], 7.f);
       k_check_surf<<<grid, 256>>>(texl[0], 7.f, bad);
       int hb = -1;
       cudaMemcpy(&hb, bad, 4, cudaMemcpyDeviceToHost);
