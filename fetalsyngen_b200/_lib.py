@@ -96,6 +96,28 @@ class SepComposeJob(C.Structure):
     _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32), ("cap_q0", _i32), ("cap_w", _i32)]
 
 
+_NP_SCALARS = {_vp: "u8", _f32: "f4", _i32: "i4", _i64: "i8", C.c_uint32: "u4", C.c_uint64: "u8", C.c_double: "f8", C.c_int16: "i2", C.c_uint8: "u1"}
+_np_dtypes: dict = {}
+
+
+def np_dtype(ct):
+    """numpy dtype with the exact layout of a ctypes job struct (explicit offsets and item size), so that an array
+    of jobs can be filled column by column and handed to the library as is."""
+    import numpy as np
+
+    dt = _np_dtypes.get(ct)
+    if dt is None:
+        if isinstance(ct, type) and issubclass(ct, C.Structure):
+            names = [n for n, _ in ct._fields_]
+            dt = np.dtype({"names": names, "formats": [np_dtype(t) for _, t in ct._fields_], "offsets": [getattr(ct, n).offset for n in names], "itemsize": C.sizeof(ct)})
+        elif isinstance(ct, type) and issubclass(ct, C.Array):
+            dt = np.dtype((np_dtype(ct._type_), (ct._length_,)))
+        else:
+            dt = np.dtype(_NP_SCALARS[ct])
+        _np_dtypes[ct] = dt
+    return dt
+
+
 _STRUCTS = {"fsg_em_job": EmJob, "fsg_unpack_job": UnpackJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
 

@@ -56,10 +56,90 @@ def affine_matrices(rot: np.ndarray, sh: np.ndarray, sc: np.ndarray) -> np.ndarr
     return a * sc[:, :, None]
 
 
-def draw_plans(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = False):
-    """Plans + parameter dictionaries for ``len(sample_ids)`` samples of generator ``gen``.
-    Control grids are not drawn here: the plans carry (size, std) and the engine draws them on the
-    device (``fsg_draw_grids``).  Returns (plans, params[, mlabel2subclusters])."""
+class BatchDraw:
+    """Everything ``draw_plans`` draws for the samples of one step, as arrays over the batch (the vectorised
+    launch builder ``batch_step.run_base_batch`` consumes them directly; ``plans()`` / ``params()`` give the
+    per-sample ``SamplePlan`` objects and the reference-shaped parameter dictionaries)."""
+
+    __slots__ = ("B", "base_seed", "sample_ids", "shape", "res", "mus", "sigmas", "deform_on", "flip", "nonlinear", "rot", "shear", "scal", "A", "c2",
+                 "center", "nonlin_scale", "size_f", "nonlin_std", "gamma_on", "gamma", "bias_on", "bf_scale", "bf_size", "bf_std", "res_on", "spacing",
+                 "stds", "noise_on", "noise_std", "m2s")
+
+    def plans(self):
+        out = []
+        for b in range(self.B):
+            p = SamplePlan(mus=self.mus[b], sigmas=self.sigmas[b], rng_seed=int(self.base_seed), sample_id=int(self.sample_ids[b]))
+            if self.deform_on[b]:
+                p.deform, p.flip, p.A, p.c2, p.center = True, bool(self.flip[b]), self.A[b], self.c2[b].astype(np.float64), self.center
+                if self.nonlinear:
+                    p.fsmall_dev = (tuple(int(v) for v in self.size_f[b]), float(self.nonlin_std[b]))
+            if self.gamma_on[b]:
+                p.gamma = float(self.gamma[b])
+            if self.bias_on[b]:
+                p.bf_dev = (tuple(int(v) for v in self.bf_size[b]), float(self.bf_std[b]))
+            if self.res_on[b]:
+                p.spacing = np.array([self.spacing[b]] * 3, dtype=np.float64)
+                p.stds = self.stds[b].copy()
+            if self.noise_on[b]:
+                p.noise_std = float(self.noise_std[b])
+            out.append(p)
+        return out
+
+    def param(self, b: int) -> dict:
+        """Parameter dictionary of sample b in the shape ``FetalSynthGen.sample`` returns (model.py:231-257)."""
+        pr = {"selected_seeds": {}, "seed_intensities": {}}
+        if self.deform_on[b]:
+            non_rigid = {}
+            if self.nonlinear:
+                non_rigid = {"nonlin_scale": np.array([self.nonlin_scale[b]]), "nonlin_std": float(self.nonlin_std[b]),
+                             "size_F_small": self.size_f[b].tolist()}
+            pr["deform_params"] = {"affine": {"rotations": self.rot[b], "shears": self.shear[b], "scalings": self.scal[b]}, "non_rigid": non_rigid, "flip": bool(self.flip[b])}
+        else:
+            pr["deform_params"] = {"affine": None, "non_rigid": None, "flip": False}
+        pr["gamma_params"] = {"gamma": float(self.gamma[b]) if self.gamma_on[b] else None}
+        if self.bias_on[b]:
+            pr["bf_params"] = {"bf_scale": np.array([self.bf_scale[b]]), "bf_std": np.array([self.bf_std[b]]), "bf_size": self.bf_size[b].tolist()}
+        else:
+            pr["bf_params"] = {"bf_scale": None, "bf_std": None, "bf_size": None}
+        pr["resample_params"] = {"spacing": [float(self.spacing[b])] * 3 if self.res_on[b] else None}
+        pr["noise_params"] = {"noise_std": float(self.noise_std[b]) if self.noise_on[b] else None}
+        if self.m2s is not None:
+            pr["selected_seeds"] = {"mlabel2subclusters": {m + 1: int(v) for m, v in enumerate(self.m2s[b])}}
+        return pr
+
+    def params(self):
+        return LazyParams(self)
+
+
+class LazyParams:
+    """List-like view of the per-sample parameter dictionaries, built on access (a training loop that never looks
+    at them does not pay for eight dictionaries per step)."""
+
+    def __init__(self, draw: BatchDraw):
+        self._d, self._cache = draw, {}
+
+    def __len__(self):
+        return self._d.B
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if b < 0:
+            b += self._d.B
+        if not 0 <= b < self._d.B:
+            raise IndexError(b)
+        if b not in self._cache:
+            self._cache[b] = self._d.param(b)
+        return self._cache[b]
+
+    def __iter__(self):
+        return (self[b] for b in range(self._d.B))
+
+
+def draw_batch(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = False) -> BatchDraw:
+    """All parameters of ``len(sample_ids)`` samples of generator ``gen``, a pure function of (base_seed, id).
+    Control grids are not drawn here: the draw carries (size, std) and the engine draws them on the device
+    (``fsg_draw_grids``)."""
     ig, sd, rs_, bf, nz, gm = gen.intensity_generator, gen.spatial_deform, gen.resampled, gen.biasfield, gen.noise, gen.gamma
     B = len(sample_ids)
     shape = tuple(int(v) for v in shape)
@@ -70,6 +150,8 @@ def draw_plans(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = 
     o_s = 2 * nlabels + nsamp  # scalar block
     U = uniforms(base_seed, sample_ids, o_s + 40)
     S = U[:, o_s:]
+    d = BatchDraw()
+    d.B, d.base_seed, d.sample_ids, d.shape = B, int(base_seed), np.asarray(sample_ids, dtype=np.uint64), shape
 
     # ---- GMM tables (rand_gmm.py:120-145)
     mus = (np.float32(25) + np.float32(200) * U[:, o_mus : o_mus + nlabels].astype(np.float32)).astype(np.float32)
@@ -78,66 +160,49 @@ def draw_plans(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = 
         pert = ndtri(U[:, o_pert : o_pert + nsamp]).astype(np.float32)
         t = mus[:, np.asarray(ig.generation_classes)] + np.float32(25) * pert
         mus[:, np.asarray(ig.seed_labels)] = np.clip(t, np.float32(0), np.float32(225))
+    d.mus, d.sigmas = mus, sigmas
 
     # ---- spatial deformation (affine_nonrigid.py:140-145, 249-324)
-    deform_on = S[:, 0] < sd.prob
-    flip = S[:, 1] < sd.flip_prb
-    rot = (2 * sd.max_rotation * S[:, 2:5] - sd.max_rotation) / 180.0 * np.pi
-    shear = 2 * sd.max_shear * S[:, 5:8] - sd.max_shear
-    scal = 1 + (2 * sd.max_scaling * S[:, 8:11] - sd.max_scaling)
-    A = affine_matrices(rot, shear, scal).astype(np.float32)
+    d.deform_on = S[:, 0] < sd.prob
+    d.flip = S[:, 1] < sd.flip_prb
+    d.rot = (2 * sd.max_rotation * S[:, 2:5] - sd.max_rotation) / 180.0 * np.pi
+    d.shear = 2 * sd.max_shear * S[:, 5:8] - sd.max_shear
+    d.scal = 1 + (2 * sd.max_scaling * S[:, 8:11] - sd.max_scaling)
+    d.A = affine_matrices(d.rot, d.shear, d.scal).astype(np.float32)
     centre2, max_shift, center, shp_f = sd._shape_constants(shape)
-    c2 = centre2[None, :] + (2 * (max_shift[None, :] * S[:, 11:14]) - max_shift[None, :])
-    nonlin_scale = sd.nonlin_scale_min + S[:, 14] * (sd.nonlin_scale_max - sd.nonlin_scale_min)
-    size_f = np.round(nonlin_scale[:, None] * shp_f[None, :]).astype(int)
-    nonlin_std = sd.nonlin_std_max * S[:, 15]
+    d.center = center
+    d.c2 = centre2[None, :] + (2 * (max_shift[None, :] * S[:, 11:14]) - max_shift[None, :])
+    d.nonlinear = bool(sd.nonlinear_transform)
+    d.nonlin_scale = sd.nonlin_scale_min + S[:, 14] * (sd.nonlin_scale_max - sd.nonlin_scale_min)
+    d.size_f = np.round(d.nonlin_scale[:, None] * shp_f[None, :]).astype(int)
+    d.nonlin_std = (sd.nonlin_std_max * S[:, 15]).astype(np.float32)  # the kernels take float32 scales
 
     # ---- gamma (synthseg.py:262-275), bias field (:157-176), resolution (:63-80), noise (:217-235)
-    gamma_on = S[:, 16] < gm.prob
-    gamma = np.exp(gm.gamma_std * ndtri(S[:, 17]))
-    bias_on = S[:, 18] < bf.prob
-    bf_scale = bf.scale_min + S[:, 19] * (bf.scale_max - bf.scale_min)
-    bf_size = np.maximum(np.round(bf_scale[:, None] * np.asarray(shape)[None, :]).astype(int), 1)
-    bf_std = bf.std_min + (bf.std_max - bf.std_min) * S[:, 20]
-    res_on = S[:, 21] < rs_.prob
-    spacing = rs_.min_resolution + (rs_.max_resolution - rs_.min_resolution) * S[:, 22]
-    blur_u = S[:, 23]
-    noise_on = S[:, 24] < nz.prob
-    noise_std = nz.std_min + (nz.std_max - nz.std_min) * S[:, 25]
-    m2s = None
+    d.gamma_on = S[:, 16] < gm.prob
+    d.gamma = np.exp(gm.gamma_std * ndtri(S[:, 17]))
+    d.bias_on = S[:, 18] < bf.prob
+    d.bf_scale = bf.scale_min + S[:, 19] * (bf.scale_max - bf.scale_min)
+    d.bf_size = np.maximum(np.round(d.bf_scale[:, None] * np.asarray(shape)[None, :]).astype(int), 1)
+    d.bf_std = (bf.std_min + (bf.std_max - bf.std_min) * S[:, 20]).astype(np.float32)
+    d.res_on = S[:, 21] < rs_.prob
+    d.spacing = rs_.min_resolution + (rs_.max_resolution - rs_.min_resolution) * S[:, 22]
+    d.res = np.asarray(gen.resolution, dtype=np.float64)
+    # blur widths of the resolution simulation (tables.resample_stds, synthseg.py:78-80), all samples at once
+    sp3 = np.repeat(d.spacing[:, None], 3, axis=1)
+    d.stds = (0.85 + 0.3 * S[:, 23:24]) * np.log(5) / np.pi * sp3 / d.res[None, :]
+    d.stds[sp3 <= d.res[None, :]] = 0.0
+    d.noise_on = S[:, 24] < nz.prob
+    d.noise_std = (nz.std_min + (nz.std_max - nz.std_min) * S[:, 25]).astype(np.float32)
+    d.m2s = None
     if with_subclusters:  # rand_gmm.py:81-85: randint(min, max + 1) per meta label
         k = ig.max_subclusters - ig.min_subclusters + 1
-        m2s = ig.min_subclusters + np.minimum((S[:, 26 : 26 + ig.meta_labels] * k).astype(int), k - 1)
+        d.m2s = ig.min_subclusters + np.minimum((S[:, 26 : 26 + ig.meta_labels] * k).astype(int), k - 1)
+    return d
 
-    res = np.asarray(gen.resolution, dtype=np.float64)
-    plans, params = [], []
-    for b in range(B):
-        p = SamplePlan(mus=mus[b], sigmas=sigmas[b], rng_seed=int(base_seed), sample_id=int(sample_ids[b]))
-        pr = {"selected_seeds": {}, "seed_intensities": {}}
-        if deform_on[b]:
-            p.deform, p.flip, p.A, p.c2, p.center = True, bool(flip[b]), A[b], c2[b].astype(np.float64), center
-            non_rigid = {}
-            if sd.nonlinear_transform:
-                p.fsmall_dev = (tuple(int(v) for v in size_f[b]), float(np.float32(nonlin_std[b])))
-                non_rigid = {"nonlin_scale": np.array([nonlin_scale[b]]), "nonlin_std": float(nonlin_std[b]), "size_F_small": size_f[b].tolist()}
-            pr["deform_params"] = {"affine": {"rotations": rot[b], "shears": shear[b], "scalings": scal[b]}, "non_rigid": non_rigid, "flip": bool(flip[b])}
-        else:
-            pr["deform_params"] = {"affine": None, "non_rigid": None, "flip": False}
-        if gamma_on[b]:
-            p.gamma = float(gamma[b])
-        pr["gamma_params"] = {"gamma": p.gamma}
-        if bias_on[b]:
-            p.bf_dev = (tuple(int(v) for v in bf_size[b]), float(np.float32(bf_std[b])))
-            pr["bf_params"] = {"bf_scale": np.array([bf_scale[b]]), "bf_std": np.array([bf_std[b]]), "bf_size": bf_size[b].tolist()}
-        else:
-            pr["bf_params"] = {"bf_scale": None, "bf_std": None, "bf_size": None}
-        if res_on[b]:
-            p.spacing = np.array([spacing[b]] * 3, dtype=np.float64)
-            p.stds = resample_stds(p.spacing, res, float(blur_u[b]))
-        pr["resample_params"] = {"spacing": None if p.spacing is None else p.spacing.tolist()}
-        if noise_on[b]:
-            p.noise_std = float(np.float32(noise_std[b]))
-        pr["noise_params"] = {"noise_std": p.noise_std}
-        plans.append(p)
-        params.append(pr)
-    return (plans, params, m2s) if with_subclusters else (plans, params)
+
+def draw_plans(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = False):
+    """Plans + parameter dictionaries for ``len(sample_ids)`` samples of generator ``gen``.
+    Returns (plans, params[, mlabel2subclusters])."""
+    d = draw_batch(gen, sample_ids, base_seed, shape, with_subclusters)
+    plans, params = d.plans(), [d.param(b) for b in range(d.B)]
+    return (plans, params, d.m2s) if with_subclusters else (plans, params)

@@ -115,6 +115,7 @@ class SynthEngine:
         self._batch = None
         self.use_tex = _TEX
         self._texvols: list = []
+        self._ptrs: dict = {}
 
     # ------------------------------------------------------------------ memory
     def scratch(self, name: str, batch: int, dtype=torch.float32, numel=None) -> torch.Tensor:
@@ -134,6 +135,33 @@ class SynthEngine:
         while len(self._texvols) <= b:
             self._texvols.append(TexVolume(self.shape))
         return self._texvols[b]
+
+    # ---- raw device addresses of the cached tables (batch_step.py): one dictionary lookup per use
+    def zoom_table_ptr(self, n_in: int, axis: int) -> int:
+        """Table that zooms a control grid of extent n_in to the volume extent along `axis`."""
+        key = ("z", n_in, axis)
+        p = self._ptrs.get(key)
+        if p is None:
+            p = self._ptrs[key] = self.tables.zoom(n_in, self.shape[axis] / n_in, self.shape[axis]).data_ptr()
+        return p
+
+    def resample_table_ptr(self, axis: int, spacing: float):
+        """(positions table address, factor) of the down-sampling to `spacing` along `axis`."""
+        n_out = resample_size(self.shape[axis], self.resolution[axis], spacing)
+        key = ("r", axis, n_out)
+        p = self._ptrs.get(key)
+        if p is None:
+            t, fac = self.tables.resample(self.shape[axis], self.resolution[axis], spacing)
+            p = self._ptrs[key] = (t.data_ptr(), fac)
+        return p
+
+    def zoom_back_ptr(self, axis: int, n_coarse: int, factor: float) -> int:
+        """Table of the zoom from the coarse extent back to the volume extent (factor = the down-sampling's)."""
+        key = ("b", axis, n_coarse)
+        p = self._ptrs.get(key)
+        if p is None:
+            p = self._ptrs[key] = self.tables.zoom(n_coarse, float(1 / np.float64(factor)), self.shape[axis]).data_ptr()
+        return p
 
     RING_SLOTS, RING_FLOATS = 8, 1 << 19
 

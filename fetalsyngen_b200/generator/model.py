@@ -30,6 +30,11 @@ from .deformation.affine_nonrigid import SpatialDeformation
 from .intensity.rand_gmm import ImageFromSeeds
 
 
+# FSG_FAST_STEP=0: issue the batched throughput path through the per-sample job builder (engine.run_base) instead of
+# the vectorised one (batch_step.run_base_batch); same launches, same results, more host time.
+_FAST_STEP = (__import__("os").environ.get("FSG_FAST_STEP", "1") or "1") != "0"
+
+
 class FetalSynthGen:
     def __init__(
         self,
@@ -255,25 +260,32 @@ class FetalSynthGen:
         if sample_ids is not None and not genparams:
             # throughput path: every sample of the step drawn at once (batch_draw.py), a pure function of
             # (base_seed, sample id)
-            from ..batch_draw import draw_plans
-
+            from ..batch_draw import draw_batch
+            from ..batch_step import run_base_batch
             from ..data.packed import PackedSeeds
 
             use_dict = any(isinstance(sd, (dict, PackedSeeds)) for sd in seeds)
-            out = draw_plans(self, list(sample_ids), int(base_seed or 0), shape, with_subclusters=use_dict)
-            plans, params = out[0], out[1]
+            d = draw_batch(self, list(sample_ids), int(base_seed or 0), shape, with_subclusters=use_dict)
             for b, sd in enumerate(seeds):
                 if isinstance(sd, (dict, PackedSeeds)):
-                    m2s = {m: int(out[2][b, m - 1]) for m in range(1, self.intensity_generator.meta_labels + 1)}
+                    m2s = {m: int(d.m2s[b, m - 1]) for m in range(1, self.intensity_generator.meta_labels + 1)}
                     if isinstance(sd, PackedSeeds):
                         vols.append((sd, m2s))  # labels decoded inside fsg_gmm from the packed words
                     else:
                         vols.append([v.view(-1) for v in self.intensity_generator.select_seeds(sd, m2s, eng.device)])
-                    params[b]["selected_seeds"] = {"mlabel2subclusters": m2s}
                 else:
                     vols.append([v.view(-1) for v in sd])
-            img, seg = eng.run_base(plans, vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)
-            return img, seg, params
+            B = len(segmentations)
+            shp = (B, *shape)
+            fast_ok = _FAST_STEP and 1 <= B == len(seeds) and all(t is None or (tuple(t.shape) == shp and t.is_contiguous() and t.device == eng.device) for t in (out_img, out_seg))
+            if fast_ok:
+                img = torch.empty(shp, dtype=torch.float32, device=eng.device) if out_img is None else out_img
+                seg = torch.empty(shp, dtype=torch.uint8, device=eng.device) if out_seg is None else out_seg
+                if img.dtype == torch.float32 and seg.dtype == torch.uint8 and run_base_batch(eng, d, vols, segmentations, img, seg, scale):
+                    return img, seg, d.params()
+            # anything the vectorised builder does not take: per-sample plans through the generic path
+            img, seg = eng.run_base(d.plans(), vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)
+            return img, seg, d.params()
         for b in range(len(segmentations)):
             if sample_ids is not None:
                 from ..sharding import sample_seed

@@ -399,3 +399,74 @@ def test_device_loader_epochs_do_not_repeat_sample_ids():
                 assert not (seen & set(ids))
                 seen |= set(ids)
     assert seen == set(range(3 * num_batches * B * world))
+
+
+@pytest.mark.parametrize("prob,packed", [(1.0, True), (0.6, True), (0.6, False)])
+def test_vectorised_job_builder_matches_the_per_sample_builder(prob, packed):
+    """batch_step.run_base_batch (numpy structured job arrays filled column by column) must queue the same C-ABI calls
+    with byte-identical job structs as SynthEngine.run_base (one ctypes struct per sample), for every combination of
+    the per-sample gates.  Runs on a CPU stand-in of the engine that records the calls (tests/host_mock.py)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from fetalsyngen_b200.batch_draw import draw_batch
+    from fetalsyngen_b200.batch_step import run_base_batch
+    from fetalsyngen_b200.generator.augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
+    from fetalsyngen_b200.generator.deformation.affine_nonrigid import SpatialDeformation
+    from fetalsyngen_b200.generator.intensity.rand_gmm import ImageFromSeeds
+    from fetalsyngen_b200.generator.model import FetalSynthGen
+    from host_mock import FakePacked, Recorder, cpu_engine, install
+
+    shape, B = (48, 40, 56), 8
+    labels = [0] + list(range(10, 50))
+    classes = [0] + [10] * 10 + [20] * 10 + [30] * 10 + list(range(40, 50))
+    gen = FetalSynthGen(shape=list(shape), resolution=[0.5, 0.5, 0.5], device="cpu", intensity_generator=ImageFromSeeds(1, 6, labels, classes),
+                        spatial_deform=SpatialDeformation(20, 0.02, 0.1, list(shape), prob, True, 0.03, 0.06, 4, 0.5, "cpu"),
+                        resampler=RandResample(prob, 0.5, 1.5), bias_field=RandBiasField(prob, 0.004, 0.02, 0.01, 0.3), noise=RandNoise(prob, 5, 15), gamma=RandGamma(prob, 0.1))
+    rec = Recorder()
+    restore = install(rec)
+    try:
+        eng = cpu_engine(shape, gen.resolution)
+        nv = eng.nvox
+        segs = [torch.zeros(nv, dtype=torch.uint8) for _ in range(B)]
+        subj = [FakePacked(shape) for _ in range(3)]
+        vols_l = [[torch.zeros(nv, dtype=torch.int8) for _ in range(1 + b % 4)] for b in range(B)]
+        out_img = torch.empty((B, *shape), dtype=torch.float32)
+        out_seg = torch.empty((B, *shape), dtype=torch.uint8)
+        seen_gates = set()
+        for step in range(12):
+            ids = list(range(step * B, (step + 1) * B))
+            d = draw_batch(gen, ids, 77, shape, with_subclusters=True)
+            if packed:
+                seeds = [(subj[b % 3], {m: int(d.m2s[b, m - 1]) for m in range(1, 5)}) for b in range(B)]
+            else:
+                seeds = vols_l
+            for b in range(B):
+                seen_gates.add((bool(d.deform_on[b]), bool(d.bias_on[b]), bool(d.res_on[b]), bool(d.noise_on[b]), bool(d.gamma_on[b])))
+            scale = step % 2 == 0
+            rec.calls.clear()
+            eng._ring[3][0] = 0
+            assert run_base_batch(eng, d, seeds, segs, out_img, out_seg, scale)
+            fast = list(rec.calls)
+            rec.calls.clear()
+            eng._ring[3][0] = 0
+            eng.run_base(d.plans(), seeds, segs, out_img=out_img, out_seg=out_seg, scale=scale)
+            slow = list(rec.calls)
+
+            def canon(calls):  # launches of one entry point may be split per kind of label source in a different order
+                return sorted(calls, key=lambda c: (c[0], -1 if c[1] is None else len(c[1]), b"" if c[1] is None else c[1].tobytes()))
+
+            assert [c[0] for c in canon(fast)] == [c[0] for c in canon(slow)], ([c[0] for c in fast], [c[0] for c in slow])
+            for (name, ja, sa), (_, jb, sb) in zip(canon(fast), canon(slow)):
+                if name in ("fsg_minmax", "fsg_scale_intensity"):  # the last argument is a freshly allocated min/max pair
+                    sa, sb = sa[:-1], sb[:-1]
+                assert sa == sb, (name, sa, sb)
+                if ja is None:
+                    continue
+                assert ja.dtype == jb.dtype and ja.shape == jb.shape, name
+                for f in ja.dtype.names:
+                    if f.startswith("_pad"):
+                        continue
+                    assert np.array_equal(ja[f], jb[f]), (name, f, ja[f], jb[f], step)
+        if prob < 1:
+            assert len(seen_gates) > 8  # the draws really exercised different gate combinations
+    finally:
+        restore()
