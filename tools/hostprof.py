@@ -28,10 +28,14 @@ def main():
     for k in range(5):
         step(k)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for k in range(50):
-        step(k)
-    print(f"host issue time: {(time.perf_counter() - t0) / 50 * 1000:.3f} ms per step")
+    host = 0.0
+    for r in range(12):  # rounds of 4 steps from an idle device: the parameter ring lets the host run 8 steps ahead at most
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(4):
+            step(4 * r + k)
+        host += time.perf_counter() - t0
+    print(f"host issue time: {host / 48 * 1000:.3f} ms per step")
     torch.cuda.synchronize()
     pr = cProfile.Profile()
     pr.enable()
