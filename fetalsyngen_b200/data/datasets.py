@@ -283,10 +283,11 @@ class FetalSynthDataset(FetalDataset):
         return data
 
     # ------------------------------------------------------------------ device fast path
-    def sample_batch(self, indices, scale: bool = True, out_img=None, out_seg=None, sample_ids=None, base_seed: int | None = None):
+    def sample_batch(self, indices, scale: bool = True, out_img=None, out_seg=None, sample_ids=None, base_seed: int | None = None, artifacts: bool = False):
         """Generate ``len(indices)`` samples with batched launches.  Returns
         ``{"image": (B,1,H,W,D) float32, "label": (B,1,H,W,D) uint8, "name": [...]}`` on the
-        generator's device plus the list of per-sample parameter dictionaries.
+        generator's device plus the list of per-sample parameter dictionaries.  ``artifacts=True``: the generator's
+        SR artifacts are applied to every sample like ``__getitem__`` does (ScaleIntensity after them).
 
         All parameters of the batch are drawn at once (``batch_draw.py``) as a function of (base seed, sample id).
         Without ``sample_ids`` the dataset numbers its samples itself and takes the base seed from numpy's global
@@ -302,7 +303,7 @@ class FetalSynthDataset(FetalDataset):
         segs = [self._segmentation(i) for i in indices]
         names = [self._sub_ses_string(*self.sub_ses[i]) for i in indices]
         img, seg, params = self.generator.sample_batch(segs, [self._seeds(i) for i in indices], scale=scale, out_img=out_img, out_seg=out_seg, sample_ids=sample_ids,
-                                                       base_seed=int(base_seed or 0))
+                                                       base_seed=int(base_seed or 0), artifacts=artifacts)
         return {"image": img.unsqueeze(1), "label": seg.unsqueeze(1), "name": names}, params
 
 

@@ -242,18 +242,44 @@ class FetalSynthGen:
         params["artifacts"] = artifacts
         return out, seg_out, None if dst2 is None else dst2.view(shape), params
 
+    def _batch_artifacts(self, img, seg, params, genparams, sample_ids, base_seed, scale):
+        """SR artifacts over the samples of a generated batch, in place (see ``sample_batch``)."""
+        eng = self.engine(tuple(self.shape))
+        for b in range(img.shape[0]):
+            if sample_ids is not None:
+                from ..sharding import sample_seed
+
+                sd32 = sample_seed(base_seed or 0, sample_ids[b])
+                np.random.seed(sd32)
+                torch.manual_seed(sd32)
+            out, meta = self._run_artifacts(img[b], seg[b], genparams)
+            if out.data_ptr() != img[b].data_ptr():
+                img[b].copy_(out.view(img[b].shape))
+            params[b]["artifacts"] = meta
+            if scale:
+                eng.scale_intensity(img[b], img[b])
+        return img, seg, params
+
     # ------------------------------------------------------------------ batched fast path
-    def sample_batch(self, segmentations, seeds, scale: bool = False, out_img=None, out_seg=None, genparams: dict = {}, sample_ids=None, base_seed: int | None = None):
+    def sample_batch(self, segmentations, seeds, scale: bool = False, out_img=None, out_seg=None, genparams: dict = {}, sample_ids=None, base_seed: int | None = None,
+                     artifacts: bool = False):
         """Generate ``len(segmentations)`` independent samples with batched launches.
 
         segmentations[b]: uint8 device volume; seeds[b]: the reference's seed-path dictionary
         ``{n_sub: {mlabel: path}}`` or a list of 1..4 int8 device volumes (already selected).
         Returns (images [B,*shape] float32, segmentations [B,*shape] uint8, [params]); both
-        tensors stay on the device.  SR artifacts are not applied on this path.
+        tensors stay on the device.  ``artifacts=True`` applies the configured SR artifacts (BlurCortex, StructNoise,
+        SimulateMotion, SimulatedBoundaries: model.py:200-229) to every sample of the batch after the batched base
+        path, on the device, with their own probabilities, and ScaleIntensity (when ``scale``) after them like
+        ``FetalSynthDataset.__getitem__`` (datasets.py:311); their draws are reseeded per sample from
+        (base_seed, sample id) when ids are given.
 
         sample_ids + base_seed (multi-GPU streams, ``sharding.py``): every draw of sample b becomes
         a function of (base_seed, sample_ids[b]) — numpy is reseeded per sample and the Philox key
         is (base_seed, sample id) — so the output does not depend on how ids are spread over ranks."""
+        if artifacts and any(a is not None for a in self.artifacts.values()):
+            img, seg, params = self.sample_batch(segmentations, seeds, False, out_img, out_seg, genparams, sample_ids, base_seed)
+            return self._batch_artifacts(img, seg, params, genparams, sample_ids, base_seed, scale)
         shape = tuple(self.shape)
         eng = self.engine(shape)
         plans, params, vols = [], [], []

@@ -392,3 +392,44 @@ def test_packed_only_dataset_and_dataset_pipeline_on_the_bundled_subjects():
     torch.manual_seed(0)
     data, gp = ds.sample(1)
     assert data["image"].shape == (1, *shape) and data["label"].dtype == torch.int64 and data["name"] == "sub-sta30" and "generation_time" in gp
+
+
+def test_batched_path_with_sr_artifacts_equals_the_per_sample_artifact_calls():
+    """sample_batch(..., artifacts=True): the four SR artifacts run on every sample of a generated batch (device-resident,
+    their draws reseeded per sample id), ScaleIntensity after them — equal to applying FetalSynthGen._run_artifacts by hand
+    to the un-scaled batch with the same seeds, and independent of how the ids are batched."""
+    import sys
+
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    import bench
+    from fetalsyngen_b200.sharding import sample_seed
+
+    shape = (96, 96, 96)
+    gen = _gen(shape, artifacts=bench.default_artifacts(1.0))
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    seeds_d = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    ids, base = [5, 6, 7], 11
+    img, seg, params = gen.sample_batch([seg_d] * 3, [seeds_d] * 3, scale=True, sample_ids=ids, base_seed=base, artifacts=True)
+    img, seg = img.clone(), seg.clone()
+    assert float(img.max()) == 1.0 and float(img.min()) == 0.0
+    assert all(set(params[b]["artifacts"]) == {"blur_cortex", "struct_noise", "simulate_motion", "boundaries"} for b in range(3))
+    # by hand: un-scaled base batch, artifacts per sample under the same per-sample seeds, then ScaleIntensity
+    base_img, base_seg, _ = gen.sample_batch([seg_d] * 3, [seeds_d] * 3, scale=False, sample_ids=ids, base_seed=base)
+    base_img = base_img.clone()
+    assert torch.equal(base_seg, seg)
+    eng = gen.engine(shape)
+    for b in range(3):
+        sd = sample_seed(base, ids[b])
+        np.random.seed(sd)
+        torch.manual_seed(sd)
+        out, _ = gen._run_artifacts(base_img[b], base_seg[b], {})
+        want = eng.scale_intensity(out.contiguous()).view(shape)
+        # the PSF reconstruction accumulates with floating-point atomics: two runs agree to rounding, not bit for bit
+        diff = (want - img[b]).abs()
+        assert float(diff.max()) <= 1e-3 and float(diff.mean()) <= 1e-5, (b, float(diff.max()), float(diff.mean()))
+        assert float((base_img[b] / base_img[b].max() - want).abs().mean()) > 1e-3  # the artifacts did change the volume
+    # a different batching of the same ids gives the same volumes
+    one, _, _ = gen.sample_batch([seg_d], [seeds_d], scale=True, sample_ids=[6], base_seed=base, artifacts=True)
+    diff = (one[0] - img[1]).abs()
+    assert float(diff.max()) <= 1e-3 and float(diff.mean()) <= 1e-5, (float(diff.max()), float(diff.mean()))
