@@ -40,6 +40,22 @@ class WarpJob(C.Structure):
                 ("src_tex", C.c_uint64)]
 
 
+class StepSample(C.Structure):  # struct fsg_step_sample
+    _fields_ = [("seg", _vp), ("words", _vp), ("seed", _vp * 4), ("word_bytes", _i32), ("shift", _i32 * 4), ("mask", _i32 * 4),
+                ("deform", _i32), ("flip", _i32), ("gamma_on", _i32), ("bias_on", _i32), ("res_on", _i32), ("noise_on", _i32),
+                ("sample_id", C.c_uint64), ("mus", _vp), ("sigmas", _vp), ("A", _f32 * 9), ("c2", _f32 * 3),
+                ("nonlin_std", _f32), ("bf_std", _f32), ("gamma", _f32), ("noise_std", _f32), ("fs", _i32 * 3), ("bs", _i32 * 3),
+                ("tex", C.c_uint64), ("surf", C.c_uint64), ("ftab", _vp * 3), ("btab", _vp * 3), ("pos", _vp * 3), ("ztab", _vp * 3),
+                ("n_out", _i32 * 3), ("ntaps", _i32 * 3), ("taps", _vp * 3)]
+
+
+class Step(C.Structure):  # struct fsg_step
+    _fields_ = [("B", _i32), ("nlabels", _i32), ("shape", _i32 * 3), ("scale", _i32), ("center", _f32 * 3), ("_pad", _i32), ("seed", C.c_uint64),
+                ("buf", _vp * 3), ("buf_pitch", _i64 * 3), ("out_img", _vp), ("out_seg", _vp), ("grids", _vp), ("grids_pitch", _i64), ("grids_cap", _i64),
+                ("shift", _vp), ("shift_pitch", _i64), ("sep_tables", _vp), ("sep_pitch", _i64), ("sep_cap", _i64), ("minmax", _vp), ("minmax_pitch", _i64),
+                ("ring_host", _vp), ("ring_dev", _vp), ("ring_floats", _i64)]
+
+
 class TexVol(C.Structure):
     _fields_ = [("array", C.c_uint64), ("tex", C.c_uint64), ("surf", C.c_uint64), ("nx", _i32), ("ny", _i32), ("nz", _i32), ("_pad", _i32)]
 
@@ -96,6 +112,13 @@ class SepComposeJob(C.Structure):
     _fields_ = [("pos", _vp), ("taps", _vp), ("q0_out", _vp), ("w_out", _vp), ("ntaps", _i32), ("n_in", _i32), ("n_out", _i32), ("width", _i32), ("cap_q0", _i32), ("cap_w", _i32)]
 
 
+class StepJobs(C.Structure):  # struct fsg_step_jobs
+    _fields_ = [("n_gmm", _i32 * 2), ("n_grid", _i32), ("n_warp", _i32), ("n_shift", _i32), ("n_sep", _i32), ("n_noise", _i32), ("n_scale", _i32),
+                ("ring_used", _i32), ("_pad", _i32), ("gmm", (GmmJob * MAX_JOBS) * 2), ("grid", GridJob * (2 * MAX_JOBS)), ("warp", WarpJob * MAX_JOBS),
+                ("shift", WarpJob * MAX_JOBS), ("compose", SepComposeJob * (3 * MAX_JOBS)), ("sep", SepconvJob * MAX_JOBS), ("zoom", ZoomJob * MAX_JOBS),
+                ("noise", NoiseJob * MAX_JOBS), ("scale_idx", _i32 * MAX_JOBS)]
+
+
 _NP_SCALARS = {_vp: "u8", _f32: "f4", _i32: "i4", _i64: "i8", C.c_uint32: "u4", C.c_uint64: "u8", C.c_double: "f8", C.c_int16: "i2", C.c_uint8: "u1"}
 _np_dtypes: dict = {}
 
@@ -119,7 +142,8 @@ def np_dtype(ct):
 
 
 _STRUCTS = {"fsg_em_job": EmJob, "fsg_unpack_job": UnpackJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
-            "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob}
+            "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob,
+            "fsg_texvol": TexVol, "fsg_step_sample": StepSample, "fsg_step": Step, "fsg_step_jobs": StepJobs}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
 SIGNATURES = {
@@ -127,6 +151,8 @@ SIGNATURES = {
     "fsg_last_error": (C.c_char_p, []),
     "fsg_sizeof": (C.c_int, [C.c_char_p]),
     "fsg_gmm": (C.c_int, [C.POINTER(GmmJob), C.c_int, _i64, _vp]),
+    "fsg_step_build": (C.c_int, [C.POINTER(Step), C.POINTER(StepSample), C.POINTER(StepJobs)]),
+    "fsg_step_run": (C.c_int, [C.POINTER(Step), C.POINTER(StepSample), _vp]),
     "fsg_texvol_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(TexVol)]),
     "fsg_texvol_destroy": (C.c_int, [C.POINTER(TexVol)]),
     "fsg_texvol_copy": (C.c_int, [C.POINTER(TexVol), _vp, C.c_int, _vp]),
@@ -187,7 +213,8 @@ SIGNATURES = {
 # kernels one call of an entry point launches on the fused base path (profiles/r01g_launches.csv);
 # entry points not listed launch one
 KERNELS_PER_CALL = {"fsg_warp_shift": 4, "fsg_sepconv": 3, "fsg_zoom_minmax": 3, "fsg_minmax": 3, "fsg_slice_acq_adjoint": 2, "fsg_slice_gamma": 2,
-                    "fsg_texvol_create": 0, "fsg_texvol_destroy": 0, "fsg_texvol_copy": 0}
+                    "fsg_texvol_create": 0, "fsg_texvol_destroy": 0, "fsg_texvol_copy": 0,
+                    "fsg_step_build": 0, "fsg_step_run": 16}
 
 _lib = None
 

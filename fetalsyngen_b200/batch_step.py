@@ -291,3 +291,156 @@ def _issue(eng, d, seeds, B, idx, rs, deform, tex_on, texv, seg_ptr, b0, b1, b2,
     if scale:
         for b in np.flatnonzero(~res_on):
             eng.scale_intensity(out_img[b], out_img[b])
+
+
+# ---------------------------------------------------------------------------------------------- native builder
+def _lookup(eng, kind, axis, keys, make):
+    """Addresses of cached 1-D tables for an integer key per sample: a dense per-engine array indexed by the key
+    (one fancy-indexing operation per step), filled through `make(key)` on first use."""
+    tab = eng._ptrs.get((kind, axis))
+    if tab is None:
+        tab = eng._ptrs[(kind, axis)] = np.zeros(eng.shape[axis] + 2, dtype=_U64)
+    out = tab.take(keys, mode="clip")
+    if not out.all():
+        keys = np.minimum(np.maximum(keys, 0), tab.size - 1)
+        for k in np.unique(keys[out == 0]):
+            tab[k] = make(int(k))
+        out = tab[keys]
+    return out
+
+
+def fill_step(eng, d, seeds, segs, out_img, out_seg, scale, keep):
+    """(fsg_step, fsg_step_sample[B]) of one batch for fsg_step_run / fsg_step_build, or None when the step is not
+    one the native builder covers.  `keep` receives the host arrays the structs point into."""
+    B = d.B
+    sx, sy, sz = eng.shape
+    nvox = eng.nvox
+    res = eng.resolution
+    if _PAIRS or not eng.use_tex or sx % 8 or sy % 4 or sz % 4 or min(eng.shape) < 2 or B > _lib.MAX_JOBS:
+        return None
+    if d.deform_on.any() and not d.nonlinear:
+        return None
+    rs = np.flatnonzero(d.res_on)
+    if rs.size and (d.spacing[rs, None] < res[None, :]).any():
+        return None
+    for s in segs:
+        if s.numel() != nvox or s.dtype != torch.uint8 or s.device != eng.device or not s.is_contiguous():
+            return None
+    idx = np.arange(B)
+    S = np.zeros(B, dtype=_dt("StepSample"))
+    S["seg"] = np.fromiter((s.data_ptr() for s in segs), dtype=_U64, count=B)
+    for b, sd in enumerate(seeds):
+        if isinstance(sd, tuple):
+            ps, m2s = sd
+            if int(np.prod(ps.shape)) != nvox:
+                raise ValueError("packed seed words must hold one word per output voxel")
+            for m in range(1, 5):
+                n = int(m2s[m])
+                if n not in ps.layout:
+                    raise KeyError(f"no seeds with {n} sub-classes in this cache (available: {ps.counts})")
+                S["shift"][b, m - 1], S["mask"][b, m - 1] = ps.layout[n]
+            S["words"][b], S["word_bytes"][b] = ps.on(eng.device).data_ptr(), ps.word_bytes
+        else:
+            vols = list(sd)
+            if not 1 <= len(vols) <= 4:
+                raise ValueError("each sample needs 1..4 seed volumes")
+            for m, v in enumerate(vols):
+                if v.dtype not in (torch.int8, torch.uint8) or v.numel() != nvox or v.device != eng.device or not v.is_contiguous():
+                    raise TypeError("seed volumes must be contiguous int8/uint8 device tensors with one label per output voxel")
+                S["seed"][b, m] = v.data_ptr()
+    deform, bias = d.deform_on, d.bias_on
+    S["deform"], S["flip"], S["gamma_on"], S["bias_on"], S["res_on"], S["noise_on"] = deform, d.flip, d.gamma_on, bias, d.res_on, d.noise_on
+    S["sample_id"] = d.sample_ids
+    mus, sigmas = np.ascontiguousarray(d.mus, dtype=np.float32), np.ascontiguousarray(d.sigmas, dtype=np.float32)
+    keep.extend([mus, sigmas, S])
+    nl = mus.shape[1]
+    S["mus"] = mus.ctypes.data + 4 * nl * idx
+    S["sigmas"] = sigmas.ctypes.data + 4 * nl * idx
+    S["A"] = d.A.reshape(B, 9)
+    S["c2"] = d.c2.astype(np.float32)
+    S["nonlin_std"], S["bf_std"], S["gamma"], S["noise_std"] = d.nonlin_std, d.bf_std, d.gamma.astype(np.float32), d.noise_std
+    S["fs"], S["bs"] = d.size_f, d.bf_size
+    texv = [eng.texvol(b) if deform[b] else None for b in range(B)]
+    S["tex"] = [0 if t is None else t.h.tex for t in texv]
+    S["surf"] = [0 if t is None else t.h.surf for t in texv]
+    for a in range(3):
+        S["ftab"][:, a] = _lookup(eng, "z", a, d.size_f[:, a], lambda n, a=a: eng.zoom_table_ptr(n, a))
+        S["btab"][:, a] = _lookup(eng, "z", a, d.bf_size[:, a], lambda n, a=a: eng.zoom_table_ptr(n, a))
+    maxw = 2
+    if rs.size:
+        n_out = (np.asarray(eng.shape, dtype=np.float64)[None, :] * res[None, :] / d.spacing[:, None]).astype(np.int64)  # resample_size
+        S["n_out"] = n_out
+        for a in range(3):
+            def make_pos(n, a=a):
+                b = int(np.flatnonzero(n_out[:, a] == n)[0])
+                return eng.resample_table_ptr(a, float(d.spacing[b]))[0]
+
+            def make_back(n, a=a):
+                b = int(np.flatnonzero(n_out[:, a] == n)[0])
+                return eng.zoom_back_ptr(a, n, eng.resample_table_ptr(a, float(d.spacing[b]))[1])
+
+            S["pos"][:, a] = _lookup(eng, "r", a, n_out[:, a], make_pos)
+            S["ztab"][:, a] = _lookup(eng, "b", a, n_out[:, a], make_back)
+        S["ntaps"] = 1
+        for b in rs:  # Gaussian taps: one array per distinct width of a sample (continuous widths: not cached)
+            seen = {}
+            for a in range(3):
+                sdv = float(d.stds[b, a])
+                if sdv > 0:
+                    t = seen.get(sdv)
+                    if t is None:
+                        t = seen[sdv] = gaussian_taps_np(sdv)
+                        keep.append(t)
+                        maxw = max(maxw, t.size + 1)
+                    S["taps"][b, a], S["ntaps"][b, a] = t.ctypes.data, t.size
+    # ---- engine buffers
+    st = _lib.Step()
+    st.B, st.nlabels, st.scale, st.seed = B, nl, int(bool(scale)), d.base_seed & (2**64 - 1)
+    st.shape = (C.c_int32 * 3)(sx, sy, sz)
+    st.center = (C.c_float * 3)(*np.asarray(d.center, dtype=np.float32))
+    for k, name in enumerate(("buf0", "buf1", "buf2")):
+        st.buf[k], st.buf_pitch[k] = _rows(eng, name, B)
+    st.out_img, st.out_seg = out_img.data_ptr(), out_seg.data_ptr()
+    nf = (int((3 * d.size_f.prod(axis=1))[deform].max(initial=0)) + 3) // 4 * 4
+    nb = (int(d.bf_size.prod(axis=1)[bias].max(initial=0)) + 3) // 4 * 4
+    cap = max(nf + nb, 4)
+    st.grids, st.grids_pitch = _rows(eng, "grids", B, torch.float32, cap)
+    st.grids_cap = cap
+    st.shift, st.shift_pitch = _rows(eng, "shift", B, torch.float32, 4)
+    if rs.size:
+        nmax = max(max(eng.shape), int(S["n_out"][rs].max()))
+        mw = max(32, (maxw + 3) // 4 * 4)
+        per_axis = (nmax * mw + (nmax + 1) // 2 + 3) // 4 * 4
+        st.sep_tables, st.sep_pitch = _rows(eng, "sep_tables", int(rs.size), torch.float32, 3 * per_axis)
+        st.sep_cap = 3 * per_axis
+    st.minmax, st.minmax_pitch = _rows(eng, "minmax", B, torch.float32, 2)
+    return st, S
+
+
+def run_base_native(eng, d, seeds, segs, out_img, out_seg, scale) -> bool:
+    """The batched base path through the native builder (`fsg_step_run`): one C-ABI call per step.  Returns False
+    when the step is not covered (the caller falls back to `run_base_batch` / `SynthEngine.run_base`)."""
+    keep = []
+    filled = fill_step(eng, d, seeds, segs, out_img, out_seg, scale, keep)
+    if filled is None:
+        return False
+    st, S = filled
+    eng.begin()
+    b = eng._batch
+    try:
+        hring, dring, events, _ = eng._ring
+        st.ring_host, st.ring_dev, st.ring_floats = hring[b["slot"]].data_ptr(), dring[b["slot"]].data_ptr(), eng.RING_FLOATS
+        lib = _lib.load()
+        rc = lib.fsg_step_run(C.byref(st), C.cast(S.ctypes.data, C.POINTER(_lib.StepSample)), _stream())
+        if rc > 0:
+            raise _lib.FsgError(f"fsg_step_run failed ({rc}): {lib.fsg_last_error().decode()}")
+        if rc == 0:
+            _lib.stats.calls["fsg_step_run"] = _lib.stats.calls.get("fsg_step_run", 0) + 1
+            e = torch.cuda.Event()
+            e.record()
+            events[b["slot"]] = e  # the pinned slot is reusable once this step's fetch has run
+    finally:
+        eng._batch = None
+        eng.tables.hold = False
+    eng._keep_native = keep
+    return rc == 0

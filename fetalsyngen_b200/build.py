@@ -14,7 +14,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libfsg.so"
 OBJ = ROOT / "build" / "obj"
-SOURCES = ["core.cu", "gmm.cu", "warp.cu", "warp_tile.cu", "warp_pipe.cu", "blur.cu", "resample.cu", "sepconv.cu", "zoom.cu", "artifacts.cu", "motion.cu", "motion_ex.cu", "seeds.cu", "plan.cu", "texvol.cu"]
+SOURCES = ["core.cu", "gmm.cu", "warp.cu", "warp_tile.cu", "warp_pipe.cu", "blur.cu", "resample.cu", "sepconv.cu", "zoom.cu", "artifacts.cu", "motion.cu", "motion_ex.cu", "seeds.cu", "plan.cu", "texvol.cu", "step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -144,6 +144,10 @@ int fsg_sizeof(const char* name) {
   FSG_SZ(fsg_grid_job)
   FSG_SZ(fsg_em_job)
   FSG_SZ(fsg_unpack_job)
+  FSG_SZ(fsg_texvol)
+  FSG_SZ(fsg_step_sample)
+  FSG_SZ(fsg_step)
+  FSG_SZ(fsg_step_jobs)
 #undef FSG_SZ
   return -1;
 }

@@ -33,6 +33,9 @@ from .intensity.rand_gmm import ImageFromSeeds
 # FSG_FAST_STEP=0: issue the batched throughput path through the per-sample job builder (engine.run_base) instead of
 # the vectorised one (batch_step.run_base_batch); same launches, same results, more host time.
 _FAST_STEP = (__import__("os").environ.get("FSG_FAST_STEP", "1") or "1") != "0"
+# FSG_NATIVE_STEP=0: build the jobs of a batched step in Python (numpy, batch_step.run_base_batch) instead of in the
+# library (fsg_step_run).
+_NATIVE_STEP = (__import__("os").environ.get("FSG_NATIVE_STEP", "1") or "1") != "0"
 
 
 class FetalSynthGen:
@@ -287,7 +290,8 @@ class FetalSynthGen:
             # throughput path: every sample of the step drawn at once (batch_draw.py), a pure function of
             # (base_seed, sample id)
             from ..batch_draw import draw_batch
-            from ..batch_step import run_base_batch
+            from ..batch_step import run_base_batch, run_base_native
+            from .. import _lib as _L
             from ..data.packed import PackedSeeds
 
             use_dict = any(isinstance(sd, (dict, PackedSeeds)) for sd in seeds)
@@ -307,8 +311,12 @@ class FetalSynthGen:
             if fast_ok:
                 img = torch.empty(shp, dtype=torch.float32, device=eng.device) if out_img is None else out_img
                 seg = torch.empty(shp, dtype=torch.uint8, device=eng.device) if out_seg is None else out_seg
-                if img.dtype == torch.float32 and seg.dtype == torch.uint8 and run_base_batch(eng, d, vols, segmentations, img, seg, scale):
-                    return img, seg, d.params()
+                if img.dtype == torch.float32 and seg.dtype == torch.uint8:
+                    # native builder (one C-ABI call per step) unless the per-entry-point timing of bench.py is on
+                    if _NATIVE_STEP and not _L.stats.timing and run_base_native(eng, d, vols, segmentations, img, seg, scale):
+                        return img, seg, d.params()
+                    if run_base_batch(eng, d, vols, segmentations, img, seg, scale):
+                        return img, seg, d.params()
             # anything the vectorised builder does not take: per-sample plans through the generic path
             img, seg = eng.run_base(d.plans(), vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)
             return img, seg, d.params()

@@ -412,6 +412,80 @@ typedef struct fsg_grid_job {
 } fsg_grid_job;
 int fsg_draw_grids(const fsg_grid_job* jobs_host, int njobs, void* stream);
 
+/* Native launch builder of the batched base path.  One call builds every job struct of a step of B samples from
+ * the per-sample draws and issues the step's launches — what FetalSynthGen.generate / augment (model.py:94-229)
+ * drive for one sample, for a whole batch: fsg_gmm, fsg_draw_grids, fsg_warp_shift, fsg_warp, fsg_sep_compose,
+ * fsg_sepconv, fsg_zoom_minmax, fsg_zoom (samples without the resolution simulation: fsg_add_noise and, with
+ * `scale`, fsg_minmax + fsg_scale_intensity).  The host mirror (batch_step.py / engine.py) builds the same bytes in
+ * Python; fsg_step_build exposes the job arrays so that tests can compare the two without a GPU.
+ * Pointers marked HOST are read during the call; every other pointer is a device address. */
+typedef struct fsg_step_sample {
+  const uint8_t* seg;        /* [nvox] input segmentation */
+  const void* words;         /* bit-packed seed words (see fsg_gmm_job) or NULL */
+  const int8_t* seed[4];     /* label volumes when words == NULL (unused entries NULL) */
+  int32_t word_bytes;
+  int32_t shift[4];
+  int32_t mask[4];
+  int32_t deform, flip, gamma_on, bias_on, res_on, noise_on; /* per-sample gates */
+  uint64_t sample_id;        /* Philox subsequence */
+  const float* mus;          /* HOST [nlabels] */
+  const float* sigmas;       /* HOST [nlabels] */
+  float A[9];
+  float c2[3];
+  float nonlin_std, bf_std, gamma, noise_std;
+  int32_t fs[3];             /* control grid of the deformation */
+  int32_t bs[3];             /* control grid of the bias field */
+  uint64_t tex, surf;        /* fsg_texvol handles of the sample's intensity volume, or 0: linear hand-over in buf[0] */
+  const fsg_tab* ftab[3];    /* zoom tables control grid -> volume, per axis */
+  const fsg_tab* btab[3];
+  /* resolution simulation (res_on): */
+  const fsg_tab* pos[3];     /* down-sampling positions per axis */
+  const fsg_tab* ztab[3];    /* zoom tables coarse grid -> volume */
+  int32_t n_out[3];          /* coarse extents */
+  int32_t ntaps[3];          /* Gaussian taps per axis (1 = no blur) */
+  const float* taps[3];      /* HOST tap arrays, NULL = no blur; equal pointers within a sample share one upload */
+} fsg_step_sample;
+typedef struct fsg_step {
+  int32_t B, nlabels;
+  int32_t shape[3];
+  int32_t scale;             /* ScaleIntensity fused into the last kernel */
+  float center[3];
+  int32_t _pad;
+  uint64_t seed;             /* Philox key */
+  float* buf[3];             /* three scratch volumes per sample: rows at buf_pitch[k] bytes */
+  int64_t buf_pitch[3];
+  float* out_img;            /* [B][nvox] */
+  uint8_t* out_seg;          /* [B][nvox] */
+  float* grids;              /* control grids drawn on the device: rows of grids_cap floats */
+  int64_t grids_pitch, grids_cap;
+  float* shift;              /* [B] rows of >= 3 floats */
+  int64_t shift_pitch;
+  float* sep_tables;         /* composed axis tables: rows of sep_cap floats */
+  int64_t sep_pitch, sep_cap;
+  float* minmax;             /* [B] rows of >= 2 floats */
+  int64_t minmax_pitch;
+  float* ring_host;          /* HOST, pinned and device-mapped: parameter block of this step */
+  float* ring_dev;
+  int64_t ring_floats;
+} fsg_step;
+typedef struct fsg_step_jobs {
+  int32_t n_gmm[2], n_grid, n_warp, n_shift, n_sep, n_noise, n_scale, ring_used, _pad;
+  fsg_gmm_job gmm[2][FSG_MAX_JOBS];   /* [0]: packed seed words, [1]: label volumes */
+  fsg_grid_job grid[2 * FSG_MAX_JOBS];
+  fsg_warp_job warp[FSG_MAX_JOBS];
+  fsg_warp_job shift[FSG_MAX_JOBS];
+  fsg_sepcompose_job compose[3 * FSG_MAX_JOBS];
+  fsg_sepconv_job sep[FSG_MAX_JOBS];
+  fsg_zoom_job zoom[FSG_MAX_JOBS];
+  fsg_noise_job noise[FSG_MAX_JOBS];
+  int32_t scale_idx[FSG_MAX_JOBS];    /* samples that need the stand-alone ScaleIntensity */
+} fsg_step_jobs;
+/* Returns 0, or -1 when the step needs something this builder does not cover (the caller takes the generic
+ * path): more than 31 Gaussian taps, a coarse grid larger than the volume, label-volume samples with different
+ * numbers of volumes. */
+int fsg_step_build(const fsg_step* step, const fsg_step_sample* samples_host, fsg_step_jobs* out);
+int fsg_step_run(const fsg_step* step, const fsg_step_sample* samples_host, void* stream);
+
 /* Bit-packed seed cache.  A subject's seed volumes for every sub-class count
  * share the meta-label support, so one word per voxel holds them all: bits 0-2 the meta-label
  * (0 = background, 1..4), then one field per sub-class count n >= 2 holding the voxel's sub-class

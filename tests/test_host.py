@@ -470,3 +470,84 @@ def test_vectorised_job_builder_matches_the_per_sample_builder(prob, packed):
             assert len(seen_gates) > 8  # the draws really exercised different gate combinations
     finally:
         restore()
+
+
+@pytest.mark.parametrize("prob,packed", [(1.0, True), (0.6, True), (0.6, False)])
+def test_native_step_builder_matches_the_per_sample_builder(prob, packed):
+    """fsg_step_build (the C++ builder behind fsg_step_run: one C-ABI call per step) must produce the job structs and
+    the parameter block that SynthEngine.run_base produces, for every combination of the per-sample gates.  Host code
+    only: runs without a GPU on the CPU stand-in of the engine."""
+    import ctypes as C
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from fetalsyngen_b200 import _lib
+    from fetalsyngen_b200.batch_draw import draw_batch
+    from fetalsyngen_b200.batch_step import fill_step
+    from fetalsyngen_b200.generator.augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
+    from fetalsyngen_b200.generator.deformation.affine_nonrigid import SpatialDeformation
+    from fetalsyngen_b200.generator.intensity.rand_gmm import ImageFromSeeds
+    from fetalsyngen_b200.generator.model import FetalSynthGen
+    from host_mock import FakePacked, Recorder, cpu_engine, install
+
+    shape, B = (48, 40, 56), 8
+    labels = [0] + list(range(10, 50))
+    classes = [0] + [10] * 10 + [20] * 10 + [30] * 10 + list(range(40, 50))
+    gen = FetalSynthGen(shape=list(shape), resolution=[0.5, 0.5, 0.5], device="cpu", intensity_generator=ImageFromSeeds(1, 6, labels, classes),
+                        spatial_deform=SpatialDeformation(20, 0.02, 0.1, list(shape), prob, True, 0.03, 0.06, 4, 0.5, "cpu"),
+                        resampler=RandResample(prob, 0.5, 1.5), bias_field=RandBiasField(prob, 0.004, 0.02, 0.01, 0.3), noise=RandNoise(prob, 5, 15), gamma=RandGamma(prob, 0.1))
+    rec = Recorder()
+    restore = install(rec)
+    try:
+        lib = _lib.load()
+        eng = cpu_engine(shape, gen.resolution)
+        nv = eng.nvox
+        segs = [torch.zeros(nv, dtype=torch.uint8) for _ in range(B)]
+        subj = [FakePacked(shape) for _ in range(3)]
+        vols_l = [[torch.zeros(nv, dtype=torch.int8) for _ in range(3)] for b in range(B)]
+        out_img = torch.empty((B, *shape), dtype=torch.float32)
+        out_seg = torch.empty((B, *shape), dtype=torch.uint8)
+        eng.scratch("minmax", B, torch.float32, 2)  # the native builder keeps B rows (stand-alone ScaleIntensity uses the tail)
+        for step in range(10):
+            ids = list(range(step * B, (step + 1) * B))
+            d = draw_batch(gen, ids, 91, shape, with_subclusters=True)
+            seeds = [(subj[b % 3], {m: int(d.m2s[b, m - 1]) for m in range(1, 5)}) for b in range(B)] if packed else vols_l
+            scale = step % 2 == 0
+            # ---- generic builder (recorded)
+            rec.calls.clear()
+            eng._ring[3][0] = 0
+            eng.run_base(d.plans(), seeds, segs, out_img=out_img, out_seg=out_seg, scale=scale)
+            slow = list(rec.calls)
+            # ---- native builder
+            keep = []
+            st, S = fill_step(eng, d, seeds, segs, out_img, out_seg, scale, keep)
+            st.ring_host, st.ring_dev, st.ring_floats = eng._ring[0][0].data_ptr(), eng._ring[1][0].data_ptr(), eng.RING_FLOATS
+            ring_generic = eng._ring_np[0][:4096].copy()
+            J = _lib.StepJobs()
+            rc = lib.fsg_step_build(C.byref(st), C.cast(S.ctypes.data, C.POINTER(_lib.StepSample)), C.byref(J))
+            assert rc == 0, lib.fsg_last_error().decode()
+            assert np.array_equal(eng._ring_np[0][: J.ring_used], ring_generic[: J.ring_used])  # means, sigmas, taps at the same offsets
+
+            def arr(field, n, struct):
+                return np.frombuffer(bytes(field), dtype=_lib.np_dtype(struct))[:n].copy()
+
+            native = {
+                "fsg_gmm": np.concatenate([arr(J.gmm[0], J.n_gmm[0], _lib.GmmJob), arr(J.gmm[1], J.n_gmm[1], _lib.GmmJob)]),
+                "fsg_draw_grids": arr(J.grid, J.n_grid, _lib.GridJob), "fsg_warp_shift": arr(J.shift, J.n_shift, _lib.WarpJob),
+                "fsg_warp": arr(J.warp, J.n_warp, _lib.WarpJob), "fsg_sep_compose": arr(J.compose, 3 * J.n_sep, _lib.SepComposeJob),
+                "fsg_sepconv": arr(J.sep, J.n_sep, _lib.SepconvJob), "fsg_zoom_minmax": arr(J.zoom, J.n_sep, _lib.ZoomJob),
+                "fsg_zoom": arr(J.zoom, J.n_sep, _lib.ZoomJob), "fsg_add_noise": arr(J.noise, J.n_noise, _lib.NoiseJob),
+            }
+            for name, want in native.items():
+                got = [c[1] for c in slow if c[0] == name]
+                got = np.concatenate(got) if got else want[:0]
+                assert len(got) == len(want), (name, len(got), len(want), step)
+                if name == "fsg_gmm":  # the generic builder launches per kind of label source; order within a kind is kept
+                    got = got[np.argsort(got["mus"], kind="stable")]
+                    want = want[np.argsort(want["mus"], kind="stable")]
+                for f in want.dtype.names:
+                    if not f.startswith("_pad"):
+                        assert np.array_equal(got[f], want[f]), (name, f, got[f], want[f], step)
+            scaled = [c[2][0] for c in slow if c[0] == "fsg_minmax"]
+            assert scaled == [out_img.data_ptr() + 4 * nv * int(J.scale_idx[i]) for i in range(J.n_scale)]
+    finally:
+        restore()
