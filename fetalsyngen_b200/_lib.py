@@ -56,6 +56,31 @@ class Step(C.Structure):  # struct fsg_step
                 ("ring_host", _vp), ("ring_dev", _vp), ("ring_floats", _i64)]
 
 
+_f64, _u8p = C.c_double, C.c_void_p
+
+
+class DrawConfig(C.Structure):  # struct fsg_draw_config
+    _fields_ = [("nlabels", _i32), ("nseed", _i32), ("seed_labels", _vp), ("generation_classes", _vp), ("tied", _i32), ("meta_labels", _i32),
+                ("min_subclusters", _i32), ("max_subclusters", _i32), ("shape", _i32 * 3), ("nonlinear", _i32), ("res", _f64 * 3),
+                ("deform_prob", _f64), ("flip_prb", _f64), ("max_rotation", _f64), ("max_shear", _f64), ("max_scaling", _f64), ("nonlin_scale_min", _f64),
+                ("nonlin_scale_max", _f64), ("nonlin_std_max", _f64), ("centre2", _f64 * 3), ("max_shift", _f64 * 3), ("gamma_prob", _f64), ("gamma_std", _f64),
+                ("bias_prob", _f64), ("bf_scale_min", _f64), ("bf_scale_max", _f64), ("bf_std_min", _f64), ("bf_std_max", _f64),
+                ("res_prob", _f64), ("min_resolution", _f64), ("max_resolution", _f64), ("noise_prob", _f64), ("noise_std_min", _f64), ("noise_std_max", _f64)]
+
+
+class DrawOut(C.Structure):  # struct fsg_draw_out
+    _fields_ = [(n, _vp) for n in ("mus", "sigmas", "deform_on", "flip", "gamma_on", "bias_on", "res_on", "noise_on", "rot", "shear", "scal", "A", "c2",
+                                   "nonlin_scale", "size_f", "nonlin_std", "gamma", "bf_scale", "bf_size", "bf_std", "spacing", "stds", "noise_std", "m2s")]
+
+
+class StepInputs(C.Structure):  # struct fsg_step_inputs
+    _fields_ = [("seg", _vp), ("words", _vp), ("word_bytes", _vp), ("layout", _vp), ("layout_len", _vp), ("seed", _vp), ("tex", _vp), ("surf", _vp),
+                ("zoom_tab", _vp * 3), ("zoom_len", _i32 * 3), ("pos_tab", _vp * 3), ("back_tab", _vp * 3), ("res_len", _i32 * 3), ("taps_host", _vp)]
+
+
+STEP_MAX_TAPS = 64
+
+
 class TexVol(C.Structure):
     _fields_ = [("array", C.c_uint64), ("tex", C.c_uint64), ("surf", C.c_uint64), ("nx", _i32), ("ny", _i32), ("nz", _i32), ("_pad", _i32)]
 
@@ -143,7 +168,7 @@ def np_dtype(ct):
 
 _STRUCTS = {"fsg_em_job": EmJob, "fsg_unpack_job": UnpackJob, "fsg_grid_job": GridJob, "fsg_sample_job": SampleJob, "fsg_perlin_octave": PerlinOctave, "fsg_sepaxis": SepAxis, "fsg_sepconv_job": SepconvJob, "fsg_sepcompose_job": SepComposeJob, "fsg_tab": Tab, "fsg_rng": Rng, "fsg_gmm_job": GmmJob, "fsg_warp_job": WarpJob, "fsg_blur_job": BlurJob,
             "fsg_resample_job": ResampleJob, "fsg_noise_job": NoiseJob, "fsg_zoom_job": ZoomJob,
-            "fsg_texvol": TexVol, "fsg_step_sample": StepSample, "fsg_step": Step, "fsg_step_jobs": StepJobs}
+            "fsg_texvol": TexVol, "fsg_draw_config": DrawConfig, "fsg_draw_out": DrawOut, "fsg_step_inputs": StepInputs, "fsg_step_sample": StepSample, "fsg_step": Step, "fsg_step_jobs": StepJobs}
 
 # name -> (restype, argtypes); every symbol include/fsg.h declares
 SIGNATURES = {
@@ -151,6 +176,9 @@ SIGNATURES = {
     "fsg_last_error": (C.c_char_p, []),
     "fsg_sizeof": (C.c_int, [C.c_char_p]),
     "fsg_gmm": (C.c_int, [C.POINTER(GmmJob), C.c_int, _i64, _vp]),
+    "fsg_draw_batch": (C.c_int, [C.POINTER(DrawConfig), _vp, C.c_int, C.c_uint64, C.POINTER(DrawOut)]),
+    "fsg_gaussian_taps": (C.c_int, [C.c_double, _vp, C.c_int]),
+    "fsg_step_fill": (C.c_int, [C.POINTER(Step), C.POINTER(DrawConfig), C.POINTER(DrawOut), _vp, C.POINTER(StepInputs), C.POINTER(StepSample), _vp]),
     "fsg_step_build": (C.c_int, [C.POINTER(Step), C.POINTER(StepSample), C.POINTER(StepJobs)]),
     "fsg_step_run": (C.c_int, [C.POINTER(Step), C.POINTER(StepSample), _vp]),
     "fsg_texvol_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(TexVol)]),
@@ -214,7 +242,7 @@ SIGNATURES = {
 # entry points not listed launch one
 KERNELS_PER_CALL = {"fsg_warp_shift": 4, "fsg_sepconv": 3, "fsg_zoom_minmax": 3, "fsg_minmax": 3, "fsg_slice_acq_adjoint": 2, "fsg_slice_gamma": 2,
                     "fsg_texvol_create": 0, "fsg_texvol_destroy": 0, "fsg_texvol_copy": 0,
-                    "fsg_step_build": 0, "fsg_step_run": 16}
+                    "fsg_step_build": 0, "fsg_step_run": 16, "fsg_draw_batch": 0, "fsg_gaussian_taps": 0, "fsg_step_fill": 0}
 
 _lib = None
 

@@ -63,7 +63,7 @@ class BatchDraw:
 
     __slots__ = ("B", "base_seed", "sample_ids", "shape", "res", "mus", "sigmas", "deform_on", "flip", "nonlinear", "rot", "shear", "scal", "A", "c2",
                  "center", "nonlin_scale", "size_f", "nonlin_std", "gamma_on", "gamma", "bias_on", "bf_scale", "bf_size", "bf_std", "res_on", "spacing",
-                 "stds", "noise_on", "noise_std", "m2s")
+                 "stds", "noise_on", "noise_std", "m2s", "_c_out")
 
     def plans(self):
         out = []
@@ -136,10 +136,82 @@ class LazyParams:
         return (self[b] for b in range(self._d.B))
 
 
+def _draw_config(gen, shape):
+    """``fsg_draw_config`` of a generator for volumes of `shape` (cached on the generator)."""
+    import ctypes as C
+
+    from . import _lib
+
+    cache = gen.__dict__.setdefault("_draw_cfg", {})
+    hit = cache.get(shape)
+    if hit is not None:
+        return hit
+    ig, sd, rs_, bf, nz, gm = gen.intensity_generator, gen.spatial_deform, gen.resampled, gen.biasfield, gen.noise, gen.gamma
+    c = _lib.DrawConfig()
+    labels = np.ascontiguousarray(ig.seed_labels, dtype=np.int32)
+    classes = np.ascontiguousarray(ig.generation_classes, dtype=np.int32)
+    c.nlabels, c.nseed = int(max(ig.seed_labels)) + 1, len(ig.seed_labels)
+    c.seed_labels, c.generation_classes = labels.ctypes.data, classes.ctypes.data
+    c.tied = int(ig.generation_classes != ig.seed_labels)
+    c.meta_labels, c.min_subclusters, c.max_subclusters = int(ig.meta_labels), int(ig.min_subclusters), int(ig.max_subclusters)
+    c.shape = (C.c_int32 * 3)(*shape)
+    c.nonlinear = int(bool(sd.nonlinear_transform))
+    c.res = (C.c_double * 3)(*[float(v) for v in gen.resolution])
+    c.deform_prob, c.flip_prb, c.max_rotation, c.max_shear, c.max_scaling = float(sd.prob), float(sd.flip_prb), float(sd.max_rotation), float(sd.max_shear), float(sd.max_scaling)
+    c.nonlin_scale_min, c.nonlin_scale_max, c.nonlin_std_max = float(sd.nonlin_scale_min), float(sd.nonlin_scale_max), float(sd.nonlin_std_max)
+    centre2, max_shift, center, _ = sd._shape_constants(shape)
+    c.centre2 = (C.c_double * 3)(*[float(v) for v in centre2])
+    c.max_shift = (C.c_double * 3)(*[float(v) for v in max_shift])
+    c.gamma_prob, c.gamma_std = float(gm.prob), float(gm.gamma_std)
+    c.bias_prob, c.bf_scale_min, c.bf_scale_max, c.bf_std_min, c.bf_std_max = float(bf.prob), float(bf.scale_min), float(bf.scale_max), float(bf.std_min), float(bf.std_max)
+    c.res_prob, c.min_resolution, c.max_resolution = float(rs_.prob), float(rs_.min_resolution), float(rs_.max_resolution)
+    c.noise_prob, c.noise_std_min, c.noise_std_max = float(nz.prob), float(nz.std_min), float(nz.std_max)
+    hit = cache[shape] = (c, center, (labels, classes))
+    return hit
+
+
+_OUT_FIELDS = (("mus", np.float32, "L"), ("sigmas", np.float32, "L"), ("deform_on", np.bool_, 0), ("flip", np.bool_, 0), ("gamma_on", np.bool_, 0), ("bias_on", np.bool_, 0),
+               ("res_on", np.bool_, 0), ("noise_on", np.bool_, 0), ("rot", np.float64, 3), ("shear", np.float64, 3), ("scal", np.float64, 3), ("A", np.float32, 9),
+               ("c2", np.float64, 3), ("nonlin_scale", np.float64, 0), ("size_f", np.int64, 3), ("nonlin_std", np.float32, 0), ("gamma", np.float64, 0),
+               ("bf_scale", np.float64, 0), ("bf_size", np.int64, 3), ("bf_std", np.float32, 0), ("spacing", np.float64, 0), ("stds", np.float64, 3),
+               ("noise_std", np.float32, 0), ("m2s", np.int64, "M"))
+
+
 def draw_batch(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = False) -> BatchDraw:
-    """All parameters of ``len(sample_ids)`` samples of generator ``gen``, a pure function of (base_seed, id).
-    Control grids are not drawn here: the draw carries (size, std) and the engine draws them on the device
+    """All parameters of ``len(sample_ids)`` samples of generator ``gen``, a pure function of (base_seed, id), drawn
+    by the library (``fsg_draw_batch``, csrc/step.cu: the one definition shared by the native step and the per-sample
+    plans).  Control grids are not drawn here: the draw carries (size, std) and the engine draws them on the device
     (``fsg_draw_grids``)."""
+    from . import _lib
+
+    shape = tuple(int(v) for v in shape)
+    cfg, center, _ = _draw_config(gen, shape)
+    B = len(sample_ids)
+    d = BatchDraw()
+    d.B, d.base_seed, d.sample_ids, d.shape = B, int(base_seed), np.ascontiguousarray(sample_ids, dtype=np.uint64), shape
+    d.center, d.nonlinear, d.res = center, bool(cfg.nonlinear), np.asarray(gen.resolution, dtype=np.float64)
+    out = _lib.DrawOut()
+    for name, dt, k in _OUT_FIELDS:
+        if name == "m2s" and not with_subclusters:
+            d.m2s = None
+            continue
+        k = cfg.nlabels if k == "L" else (cfg.meta_labels if k == "M" else k)
+        a = np.empty((B, k) if k else (B,), dtype=dt)
+        setattr(d, name, a)
+        setattr(out, name, a.ctypes.data)
+    import ctypes as C
+
+    rc = _lib.load().fsg_draw_batch(C.byref(cfg), d.sample_ids.ctypes.data, B, int(base_seed) & (2**64 - 1), C.byref(out))
+    if rc:
+        raise _lib.FsgError(f"fsg_draw_batch failed ({rc}): {_lib.load().fsg_last_error().decode()}")
+    d.A = d.A.reshape(B, 3, 3)
+    d._c_out = out  # fsg_draw_out over the arrays above (batch_step.run_step_native hands it to fsg_step_fill)
+    return d
+
+
+def draw_batch_numpy(gen, sample_ids, base_seed: int, shape, with_subclusters: bool = False) -> BatchDraw:
+    """The same draws in numpy (the definition ``fsg_draw_batch`` was written from; kept for the test that compares
+    the two: equal booleans and integers, floats to rounding of cos / sin / exp / ndtri)."""
     ig, sd, rs_, bf, nz, gm = gen.intensity_generator, gen.spatial_deform, gen.resampled, gen.biasfield, gen.noise, gen.gamma
     B = len(sample_ids)
     shape = tuple(int(v) for v in shape)

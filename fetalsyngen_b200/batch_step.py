@@ -417,30 +417,154 @@ def fill_step(eng, d, seeds, segs, out_img, out_seg, scale, keep):
     return st, S
 
 
-def run_base_native(eng, d, seeds, segs, out_img, out_seg, scale) -> bool:
-    """The batched base path through the native builder (`fsg_step_run`): one C-ABI call per step.  Returns False
-    when the step is not covered (the caller falls back to `run_base_batch` / `SynthEngine.run_base`)."""
-    keep = []
-    filled = fill_step(eng, d, seeds, segs, out_img, out_seg, scale, keep)
-    if filled is None:
+# ---------------------------------------------------------------------------------------------- fully native step
+class _NativeState:
+    """Per-engine host arrays of the native step: the inputs struct with its arrays, the dense table-address arrays,
+    the sample structs and the step struct (buffer fields refreshed per call: scratch may have been regrown)."""
+
+    def __init__(self, eng):
+        from .data.packed import PackedSeeds  # noqa: F401  (layout arrays are cached on the PackedSeeds objects)
+
+        M = _lib.MAX_JOBS
+        self.seg = np.zeros(M, dtype=_U64)
+        self.words = np.zeros(M, dtype=_U64)
+        self.word_bytes = np.zeros(M, dtype=np.int32)
+        self.layout = np.zeros(M, dtype=_U64)
+        self.layout_len = np.zeros(M, dtype=np.int32)
+        self.seed = np.zeros((M, 4), dtype=_U64)
+        self.tex = np.zeros(M, dtype=_U64)
+        self.surf = np.zeros(M, dtype=_U64)
+        self.taps = np.zeros((M, 3, _lib.STEP_MAX_TAPS), dtype=np.float32)
+        self.zoom = [np.zeros(eng.shape[a] + 2, dtype=_U64) for a in range(3)]
+        self.pos = [np.zeros(eng.shape[a] + 2, dtype=_U64) for a in range(3)]
+        self.back = [np.zeros(eng.shape[a] + 2, dtype=_U64) for a in range(3)]
+        self.missing = np.zeros(4, dtype=np.int32)
+        self.S = (_lib.StepSample * M)()
+        i = self.inputs = _lib.StepInputs()
+        i.seg, i.words, i.word_bytes, i.layout, i.layout_len, i.seed = (a.ctypes.data for a in (self.seg, self.words, self.word_bytes, self.layout, self.layout_len, self.seed))
+        i.tex, i.surf, i.taps_host = self.tex.ctypes.data, self.surf.ctypes.data, self.taps.ctypes.data
+        for a in range(3):
+            i.zoom_tab[a], i.pos_tab[a], i.back_tab[a] = self.zoom[a].ctypes.data, self.pos[a].ctypes.data, self.back[a].ctypes.data
+            i.zoom_len[a] = i.res_len[a] = eng.shape[a] + 2
+        self.st = _lib.Step()
+        self.st.shape = (C.c_int32 * 3)(*eng.shape)
+        self.ntex = 0
+
+
+def _layout_array(ps):
+    """[nmax + 1][2] int32 (shift, mask) per sub-class count of a packed subject (-1: count absent), cached."""
+    arr = getattr(ps, "_layout_arr", None)
+    if arr is None:
+        nmax = max(ps.layout)
+        arr = np.full((nmax + 1, 2), -1, dtype=np.int32)
+        for n, (sh, mk) in ps.layout.items():
+            arr[n] = (sh, mk)
+        ps._layout_arr = arr
+    return arr
+
+
+def prepare_step_native(eng, gen, d, seeds, segs, out_img, out_seg, scale):
+    """(fsg_step, fsg_step_sample array) of one batch, filled by the library (`fsg_step_fill`) from the draws and the
+    input addresses gathered here; None when the step is not covered by the native path."""
+    from .batch_draw import _draw_config
+    from .data.packed import PackedSeeds
+
+    B = d.B
+    sx, sy, sz = eng.shape
+    nvox = eng.nvox
+    if _PAIRS or not eng.use_tex or sx % 8 or sy % 4 or sz % 4 or min(eng.shape) < 2 or B > _lib.MAX_JOBS or len(seeds) != B or len(segs) != B:
+        return None
+    ns = eng.__dict__.get("_native")
+    if ns is None:
+        ns = eng._native = _NativeState(eng)
+    dev = eng.device
+    for b in range(B):
+        s, sd = segs[b], seeds[b]
+        if s.numel() != nvox or s.dtype != torch.uint8 or s.device != dev or not s.is_contiguous():
+            return None
+        ns.seg[b] = s.data_ptr()
+        if isinstance(sd, PackedSeeds):
+            if int(np.prod(sd.shape)) != nvox or d.m2s is None:
+                return None
+            la = _layout_array(sd)
+            ns.words[b], ns.word_bytes[b], ns.layout[b], ns.layout_len[b] = sd.on(dev).data_ptr(), sd.word_bytes, la.ctypes.data, la.shape[0]
+        elif isinstance(sd, (list, tuple)) and 1 <= len(sd) <= 4 and all(torch.is_tensor(v) for v in sd):
+            ns.words[b] = 0
+            ns.seed[b] = 0
+            for m, v in enumerate(sd):
+                if v.dtype not in (torch.int8, torch.uint8) or v.numel() != nvox or v.device != dev or not v.is_contiguous():
+                    return None
+                ns.seed[b, m] = v.data_ptr()
+        else:
+            return None
+    while ns.ntex < B:  # the engine's block-linear volumes, one per batch slot
+        t = eng.texvol(ns.ntex)
+        ns.tex[ns.ntex], ns.surf[ns.ntex] = t.h.tex, t.h.surf
+        ns.ntex += 1
+    cfg = _draw_config(gen, tuple(eng.shape))[0]
+    st = ns.st
+    st.B, st.nlabels, st.scale, st.seed = B, cfg.nlabels, int(bool(scale)), d.base_seed & (2**64 - 1)
+    st.center = (C.c_float * 3)(*d.center)
+    for k, name in enumerate(("buf0", "buf1", "buf2")):
+        st.buf[k], st.buf_pitch[k] = _rows(eng, name, B)
+    st.out_img, st.out_seg = out_img.data_ptr(), out_seg.data_ptr()
+    caps = eng.__dict__.get("_native_caps")
+    if caps is None:  # worst-case scratch sizes of this generator's ranges
+        shp = np.asarray(eng.shape, dtype=np.float64)
+        nf = 3 * int(np.prod(np.round(cfg.nonlin_scale_max * shp) + 1))
+        nb = int(np.prod(np.maximum(np.round(cfg.bf_scale_max * shp), 1) + 1))
+        nmax, mw = max(eng.shape), _lib.STEP_MAX_TAPS + 4
+        caps = eng._native_caps = ((nf + 3) // 4 * 4 + (nb + 3) // 4 * 4, 3 * ((nmax * mw + (nmax + 1) // 2 + 3) // 4 * 4))
+    st.grids, st.grids_pitch = _rows(eng, "grids", B, torch.float32, caps[0])
+    st.grids_cap = caps[0]
+    st.shift, st.shift_pitch = _rows(eng, "shift", B, torch.float32, 4)
+    st.sep_tables, st.sep_pitch = _rows(eng, "sep_tables", B, torch.float32, caps[1])
+    st.sep_cap = caps[1]
+    st.minmax, st.minmax_pitch = _rows(eng, "minmax", B, torch.float32, 2)
+    lib = _lib.load()
+    out = d._c_out
+    for _ in range(64):
+        rc = lib.fsg_step_fill(C.byref(st), C.byref(cfg), C.byref(out), d.sample_ids.ctypes.data, C.byref(ns.inputs), ns.S, ns.missing.ctypes.data)
+        if rc != -2:
+            break
+        kind, a, key = (int(v) for v in ns.missing[:3])  # build the missing table, then fill again
+        if kind == 0:
+            ns.zoom[a][key] = eng.zoom_table_ptr(key, a)
+        else:
+            b = next(b for b in range(B) if d.res_on[b] and int(eng.shape[a] * eng.resolution[a] / d.spacing[b]) == key)
+            p, fac = eng.resample_table_ptr(a, float(d.spacing[b]))
+            ns.pos[a][key], ns.back[a][key] = p, eng.zoom_back_ptr(a, key, fac)
+    if rc == -1:
+        return None
+    if rc:
+        raise _lib.FsgError(f"fsg_step_fill failed ({rc}): {lib.fsg_last_error().decode()}")
+    return st, ns.S
+
+
+def run_step_native(eng, gen, d, seeds, segs, out_img, out_seg, scale) -> bool:
+    """One batched step with everything after the draws in the library: `fsg_step_fill` turns the draws (made by
+    `fsg_draw_batch`) and the input addresses into sample structs, `fsg_step_run` builds the jobs and launches.
+    Python only gathers addresses.  Returns False when the step is not covered (callers fall back)."""
+    prepared = prepare_step_native(eng, gen, d, seeds, segs, out_img, out_seg, scale)
+    if prepared is None:
         return False
-    st, S = filled
+    st, S = prepared
+    lib = _lib.load()
     eng.begin()
-    b = eng._batch
+    bt = eng._batch
     try:
         hring, dring, events, _ = eng._ring
-        st.ring_host, st.ring_dev, st.ring_floats = hring[b["slot"]].data_ptr(), dring[b["slot"]].data_ptr(), eng.RING_FLOATS
-        lib = _lib.load()
-        rc = lib.fsg_step_run(C.byref(st), C.cast(S.ctypes.data, C.POINTER(_lib.StepSample)), _stream())
+        st.ring_host, st.ring_dev, st.ring_floats = hring[bt["slot"]].data_ptr(), dring[bt["slot"]].data_ptr(), eng.RING_FLOATS
+        rc = lib.fsg_step_run(C.byref(st), S, _stream())
         if rc > 0:
             raise _lib.FsgError(f"fsg_step_run failed ({rc}): {lib.fsg_last_error().decode()}")
         if rc == 0:
             _lib.stats.calls["fsg_step_run"] = _lib.stats.calls.get("fsg_step_run", 0) + 1
             e = torch.cuda.Event()
             e.record()
-            events[b["slot"]] = e  # the pinned slot is reusable once this step's fetch has run
+            events[bt["slot"]] = e
     finally:
         eng._batch = None
         eng.tables.hold = False
-    eng._keep_native = keep
+    eng._keep_native = d  # the sample structs point into the draw's arrays until the next step replaces them
     return rc == 0

@@ -145,6 +145,9 @@ int fsg_sizeof(const char* name) {
   FSG_SZ(fsg_em_job)
   FSG_SZ(fsg_unpack_job)
   FSG_SZ(fsg_texvol)
+  FSG_SZ(fsg_draw_config)
+  FSG_SZ(fsg_draw_out)
+  FSG_SZ(fsg_step_inputs)
   FSG_SZ(fsg_step_sample)
   FSG_SZ(fsg_step)
   FSG_SZ(fsg_step_jobs)

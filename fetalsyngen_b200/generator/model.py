@@ -290,12 +290,24 @@ class FetalSynthGen:
             # throughput path: every sample of the step drawn at once (batch_draw.py), a pure function of
             # (base_seed, sample id)
             from ..batch_draw import draw_batch
-            from ..batch_step import run_base_batch, run_base_native
+            from ..batch_step import run_base_batch, run_step_native
             from .. import _lib as _L
             from ..data.packed import PackedSeeds
 
             use_dict = any(isinstance(sd, (dict, PackedSeeds)) for sd in seeds)
             d = draw_batch(self, list(sample_ids), int(base_seed or 0), shape, with_subclusters=use_dict)
+            B = len(segmentations)
+            shp = (B, *shape)
+            fast_ok = _FAST_STEP and 1 <= B == len(seeds) and all(t is None or (tuple(t.shape) == shp and t.is_contiguous() and t.device == eng.device) for t in (out_img, out_seg))
+            img = seg = None
+            if fast_ok:
+                img = torch.empty(shp, dtype=torch.float32, device=eng.device) if out_img is None else out_img
+                seg = torch.empty(shp, dtype=torch.uint8, device=eng.device) if out_seg is None else out_seg
+                fast_ok = img.dtype == torch.float32 and seg.dtype == torch.uint8
+            # native step (draws, sample structs, job structs and launches in the library) unless the per-entry-point
+            # timing of bench.py is on
+            if fast_ok and _NATIVE_STEP and not _L.stats.timing and run_step_native(eng, self, d, seeds, segmentations, img, seg, scale):
+                return img, seg, d.params()
             for b, sd in enumerate(seeds):
                 if isinstance(sd, (dict, PackedSeeds)):
                     m2s = {m: int(d.m2s[b, m - 1]) for m in range(1, self.intensity_generator.meta_labels + 1)}
@@ -305,18 +317,8 @@ class FetalSynthGen:
                         vols.append([v.view(-1) for v in self.intensity_generator.select_seeds(sd, m2s, eng.device)])
                 else:
                     vols.append([v.view(-1) for v in sd])
-            B = len(segmentations)
-            shp = (B, *shape)
-            fast_ok = _FAST_STEP and 1 <= B == len(seeds) and all(t is None or (tuple(t.shape) == shp and t.is_contiguous() and t.device == eng.device) for t in (out_img, out_seg))
-            if fast_ok:
-                img = torch.empty(shp, dtype=torch.float32, device=eng.device) if out_img is None else out_img
-                seg = torch.empty(shp, dtype=torch.uint8, device=eng.device) if out_seg is None else out_seg
-                if img.dtype == torch.float32 and seg.dtype == torch.uint8:
-                    # native builder (one C-ABI call per step) unless the per-entry-point timing of bench.py is on
-                    if _NATIVE_STEP and not _L.stats.timing and run_base_native(eng, d, vols, segmentations, img, seg, scale):
-                        return img, seg, d.params()
-                    if run_base_batch(eng, d, vols, segmentations, img, seg, scale):
-                        return img, seg, d.params()
+            if fast_ok and run_base_batch(eng, d, vols, segmentations, img, seg, scale):
+                return img, seg, d.params()
             # anything the vectorised builder does not take: per-sample plans through the generic path
             img, seg = eng.run_base(d.plans(), vols, [s.view(-1) for s in segmentations], out_img=out_img, out_seg=out_seg, scale=scale)
             return img, seg, d.params()

@@ -68,8 +68,19 @@ def gaussian_taps(sigma: float) -> np.ndarray:
 
 
 def gaussian_taps_np(sigma: float) -> np.ndarray:
-    """Same taps as ``gaussian_taps`` in plain numpy float32 (no torch dispatch on the hot host
-    path); differs from torch's by at most an ulp of exp()."""
+    """Same taps as ``gaussian_taps`` from the library (``fsg_gaussian_taps``: float32 arithmetic, no torch dispatch
+    on the hot host path; the native step builder uses the same routine); differs from torch's by an ulp of exp()
+    and of the normalising sum at most."""
+    from . import _lib
+
+    out = np.empty(2 * int(np.ceil(3 * sigma)) + 1, dtype=np.float32)
+    n = _lib.load().fsg_gaussian_taps(float(sigma), out.ctypes.data, out.size)
+    if n != out.size:
+        raise _lib.FsgError(f"fsg_gaussian_taps({sigma}) returned {n}")
+    return out
+
+
+def _gaussian_taps_numpy(sigma: float) -> np.ndarray:
     sl = int(np.ceil(3 * sigma))
     ts = np.arange(-sl, sl + 1, dtype=np.float32)
     g = np.exp(-((ts / np.float32(sigma)) ** 2) / np.float32(2))

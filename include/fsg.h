@@ -486,6 +486,77 @@ typedef struct fsg_step_jobs {
 int fsg_step_build(const fsg_step* step, const fsg_step_sample* samples_host, fsg_step_jobs* out);
 int fsg_step_run(const fsg_step* step, const fsg_step_sample* samples_host, void* stream);
 
+/* Per-sample parameter draws of the batched path, natively: every parameter FetalSynthGen.sample draws for a sample
+ * (rand_gmm.py:81-85,120-145; affine_nonrigid.py:140-145,249-324; synthseg.py:63-80,157-176,217-235,262-275), for B
+ * samples at once, as a pure function of (base_seed, sample id): uniform (sample, column) = splitmix64 counter
+ * stream, shaped by the distributions of the stage objects.  The host mirror (batch_draw.draw_batch) calls this, so the
+ * per-sample plans of the generic path and the native step share one definition.  All pointers are HOST memory. */
+typedef struct fsg_draw_config {
+  int32_t nlabels, nseed;              /* max(seed_labels) + 1, len(seed_labels) */
+  const int32_t* seed_labels;          /* [nseed] */
+  const int32_t* generation_classes;   /* [nseed] */
+  int32_t tied;                        /* generation_classes != seed_labels: means tied to the class mean */
+  int32_t meta_labels, min_subclusters, max_subclusters;
+  int32_t shape[3];
+  int32_t nonlinear;
+  double res[3];
+  double deform_prob, flip_prb, max_rotation, max_shear, max_scaling, nonlin_scale_min, nonlin_scale_max, nonlin_std_max;
+  double centre2[3], max_shift[3];
+  double gamma_prob, gamma_std;
+  double bias_prob, bf_scale_min, bf_scale_max, bf_std_min, bf_std_max;
+  double res_prob, min_resolution, max_resolution;
+  double noise_prob, noise_std_min, noise_std_max;
+} fsg_draw_config;
+typedef struct fsg_draw_out {          /* struct of arrays over the batch, caller-allocated */
+  float* mus;                          /* [B][nlabels] */
+  float* sigmas;                       /* [B][nlabels] */
+  uint8_t *deform_on, *flip, *gamma_on, *bias_on, *res_on, *noise_on; /* [B] */
+  double *rot, *shear, *scal;          /* [B][3] */
+  float* A;                            /* [B][9] */
+  double* c2;                          /* [B][3] */
+  double* nonlin_scale;                /* [B] */
+  int64_t* size_f;                     /* [B][3] */
+  float* nonlin_std;                   /* [B] */
+  double* gamma;                       /* [B] */
+  double* bf_scale;                    /* [B] */
+  int64_t* bf_size;                    /* [B][3] */
+  float* bf_std;                       /* [B] */
+  double* spacing;                     /* [B] */
+  double* stds;                        /* [B][3] */
+  float* noise_std;                    /* [B] */
+  int64_t* m2s;                        /* [B][meta_labels] or NULL */
+} fsg_draw_out;
+int fsg_draw_batch(const fsg_draw_config* cfg, const uint64_t* sample_ids, int B, uint64_t base_seed, fsg_draw_out* out);
+/* Zero-padded Gaussian taps of make_gaussian_kernel (utils/generation.py:74-81) for one sigma: writes
+ * 2 * ceil(3 sigma) + 1 normalised float32 taps into `out` (capacity `cap`), returns their number (or -1). */
+int fsg_gaussian_taps(double sigma, float* out, int cap);
+
+/* Inputs of a drawn step that are not drawn: where each sample's volumes live and the host mirror's caches of
+ * device tables.  All pointers HOST arrays; entries are device addresses stored as 64-bit integers. */
+typedef struct fsg_step_inputs {
+  const uint64_t* seg;         /* [B] uint8 segmentation volumes */
+  const uint64_t* words;       /* [B] bit-packed seed words of the sample's subject, 0 = label volumes instead */
+  const int32_t* word_bytes;   /* [B] */
+  const int32_t* const* layout; /* [B] -> the subject's field layout [nmax + 1][2] = (shift, mask) per sub-class count (-1: absent) */
+  const int32_t* layout_len;   /* [B] nmax + 1 */
+  const uint64_t* seed;        /* [B][4] label volumes when words[b] == 0 */
+  const uint64_t* tex;         /* [B] fsg_texvol handles of the engine's block-linear volumes (0: linear hand-over) */
+  const uint64_t* surf;        /* [B] */
+  /* dense address tables per axis: [key] = device address of the cached 1-D table, 0 = not built yet */
+  const uint64_t* zoom_tab[3]; /* key = control-grid extent -> zoom table to the volume extent */
+  int32_t zoom_len[3];
+  const uint64_t* pos_tab[3];  /* key = coarse extent -> down-sampling positions */
+  const uint64_t* back_tab[3]; /* key = coarse extent -> zoom table back to the volume extent */
+  int32_t res_len[3];
+  float* taps_host;            /* [B][3][FSG_STEP_MAX_TAPS] scratch for the Gaussian taps of the step */
+} fsg_step_inputs;
+#define FSG_STEP_MAX_TAPS 64
+/* Fills samples_out[B] from the draws + inputs (what batch_step.fill_step does in numpy).  Returns 0, -1 when the step
+ * is not covered by the native builder, or -2 when a table is missing: then missing_out[0..2] = (kind 0 zoom / 1 pos+back,
+ * axis, key) of the first missing table, for the caller to build and retry. */
+int fsg_step_fill(const fsg_step* step, const fsg_draw_config* cfg, const fsg_draw_out* draw, const uint64_t* sample_ids, const fsg_step_inputs* in,
+                  fsg_step_sample* samples_out, int32_t* missing_out);
+
 /* Bit-packed seed cache.  A subject's seed volumes for every sub-class count
  * share the meta-label support, so one word per voxel holds them all: bits 0-2 the meta-label
  * (0 = background, 1..4), then one field per sub-class count n >= 2 holding the voxel's sub-class

@@ -551,3 +551,90 @@ def test_native_step_builder_matches_the_per_sample_builder(prob, packed):
             assert scaled == [out_img.data_ptr() + 4 * nv * int(J.scale_idx[i]) for i in range(J.n_scale)]
     finally:
         restore()
+
+
+def test_native_draws_match_the_numpy_definition():
+    """fsg_draw_batch (the library's per-sample parameter draws) against the numpy code it was written from: gates,
+    integers and everything built from +, -, *, / bit for bit; cos / sin / exp / ndtri to rounding."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from fetalsyngen_b200.batch_draw import draw_batch, draw_batch_numpy
+
+    shape = (256, 256, 256)
+    gen = bench.build_generator(shape, "cpu")
+    ids = list(range(1000, 1256))
+    a = draw_batch(gen, ids, 4242, shape, True)
+    b = draw_batch_numpy(gen, ids, 4242, shape, True)
+    for name in ("deform_on", "flip", "gamma_on", "bias_on", "res_on", "noise_on", "size_f", "bf_size", "m2s", "sample_ids"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for name in ("mus", "sigmas", "rot", "shear", "scal", "A", "c2", "nonlin_scale", "nonlin_std", "gamma", "bf_scale", "bf_std", "spacing", "stds", "noise_std"):
+        x, y = np.asarray(getattr(a, name), dtype=np.float64), np.asarray(getattr(b, name), dtype=np.float64)
+        assert x.shape == y.shape and np.abs(x - y).max() <= 1e-6 * max(1.0, np.abs(y).max()), name
+        assert getattr(a, name).dtype == getattr(b, name).dtype, name
+    assert np.array_equal(a.spacing, b.spacing) and np.array_equal(a.stds, b.stds) and np.array_equal(a.c2, b.c2)  # pure arithmetic: exact
+    # plans and parameter dictionaries come out of either
+    assert len(a.plans()) == 256 and a.params()[3]["resample_params"]["spacing"] == b.params()[3]["resample_params"]["spacing"]
+
+
+@pytest.mark.parametrize("prob,packed", [(1.0, True), (0.6, True), (0.6, False)])
+def test_native_sample_structs_match_the_numpy_ones(prob, packed):
+    """fsg_step_fill (draws + input addresses -> fsg_step_sample) against batch_step.fill_step (the same in numpy)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from fetalsyngen_b200 import _lib
+    from fetalsyngen_b200.batch_draw import draw_batch
+    from fetalsyngen_b200.batch_step import fill_step, prepare_step_native
+    from fetalsyngen_b200.generator.augmentation.synthseg import RandBiasField, RandGamma, RandNoise, RandResample
+    from fetalsyngen_b200.generator.deformation.affine_nonrigid import SpatialDeformation
+    from fetalsyngen_b200.generator.intensity.rand_gmm import ImageFromSeeds
+    from fetalsyngen_b200.generator.model import FetalSynthGen
+    from host_mock import FakePacked, Recorder, cpu_engine, install
+
+    shape, B = (48, 40, 56), 8
+    labels = [0] + list(range(10, 50))
+    classes = [0] + [10] * 10 + [20] * 10 + [30] * 10 + list(range(40, 50))
+    gen = FetalSynthGen(shape=list(shape), resolution=[0.5, 0.5, 0.5], device="cpu", intensity_generator=ImageFromSeeds(1, 6, labels, classes),
+                        spatial_deform=SpatialDeformation(20, 0.02, 0.1, list(shape), prob, True, 0.03, 0.06, 4, 0.5, "cpu"),
+                        resampler=RandResample(prob, 0.5, 1.5), bias_field=RandBiasField(prob, 0.004, 0.02, 0.01, 0.3), noise=RandNoise(prob, 5, 15), gamma=RandGamma(prob, 0.1))
+    restore = install(Recorder())
+    try:
+        eng = cpu_engine(shape, gen.resolution)
+        nv = eng.nvox
+        segs = [torch.zeros(nv, dtype=torch.uint8) for _ in range(B)]
+        subj = [FakePacked(shape) for _ in range(3)]
+        vols_l = [[torch.zeros(nv, dtype=torch.int8) for _ in range(3)] for b in range(B)]
+        out_img = torch.empty((B, *shape), dtype=torch.float32)
+        out_seg = torch.empty((B, *shape), dtype=torch.uint8)
+        for step in range(8):
+            ids = list(range(step * B, (step + 1) * B))
+            d = draw_batch(gen, ids, 17, shape, with_subclusters=True)
+            raw = [subj[b % 3] for b in range(B)] if packed else vols_l
+            tup = [(subj[b % 3], {m: int(d.m2s[b, m - 1]) for m in range(1, 5)}) for b in range(B)] if packed else vols_l
+            keep = []
+            _, S_np = fill_step(eng, d, tup, segs, out_img, out_seg, True, keep)
+            prepared = prepare_step_native(eng, gen, d, raw, segs, out_img, out_seg, True)
+            assert prepared is not None
+            st, S_c = prepared
+            got = np.frombuffer(bytes(S_c), dtype=_lib.np_dtype(_lib.StepSample))[:B]
+            for f in got.dtype.names:
+                if f in ("mus", "sigmas", "taps"):
+                    continue  # host addresses: compared by content below
+                # table fields only matter (and are only filled by the library) where the sample's gate is on
+                rows = {"ftab": d.deform_on, "tex": d.deform_on, "surf": d.deform_on, "btab": d.bias_on, "pos": d.res_on, "ztab": d.res_on, "n_out": d.res_on,
+                        "ntaps": d.res_on}.get(f, np.ones(B, dtype=bool))
+                assert np.array_equal(got[f][rows], S_np[f][rows]), (f, got[f], S_np[f], step)
+            import ctypes as C
+
+            for b in range(B):
+                nl = d.mus.shape[1]
+                assert np.array_equal(np.ctypeslib.as_array(C.cast(int(got["mus"][b]), C.POINTER(C.c_float)), (nl,)), d.mus[b])
+                for a in range(3):
+                    if not d.res_on[b]:
+                        continue
+                    pa, pb, n = int(got["taps"][b, a]), int(S_np["taps"][b, a]), int(got["ntaps"][b, a])
+                    assert (pa == 0) == (pb == 0)
+                    if pa:
+                        assert np.array_equal(np.ctypeslib.as_array(C.cast(pa, C.POINTER(C.c_float)), (n,)), np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_float)), (n,)))
+                        for p in range(a):  # the same width shares one array in both
+                            assert (got["taps"][b, p] == got["taps"][b, a]) == (S_np["taps"][b, p] == S_np["taps"][b, a])
+    finally:
+        restore()
