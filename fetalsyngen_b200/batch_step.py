@@ -460,6 +460,7 @@ def _layout_array(ps):
         for n, (sh, mk) in ps.layout.items():
             arr[n] = (sh, mk)
         ps._layout_arr = arr
+        ps._nvox = int(np.prod(ps.shape))
     return arr
 
 
@@ -484,9 +485,9 @@ def prepare_step_native(eng, gen, d, seeds, segs, out_img, out_seg, scale):
             return None
         ns.seg[b] = s.data_ptr()
         if isinstance(sd, PackedSeeds):
-            if int(np.prod(sd.shape)) != nvox or d.m2s is None:
-                return None
             la = _layout_array(sd)
+            if sd._nvox != nvox or d.m2s is None:
+                return None
             ns.words[b], ns.word_bytes[b], ns.layout[b], ns.layout_len[b] = sd.on(dev).data_ptr(), sd.word_bytes, la.ctypes.data, la.shape[0]
         elif isinstance(sd, (list, tuple)) and 1 <= len(sd) <= 4 and all(torch.is_tensor(v) for v in sd):
             ns.words[b] = 0
