@@ -16,7 +16,6 @@ import numpy as np
 from scipy.special import ndtri
 
 from .engine import SamplePlan
-from .tables import resample_stds
 
 _MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
 

@@ -1,4 +1,5 @@
-"""Vectorised launch builder of the batched base path.
+"""Launch builders of the batched base path: the native step (``run_step_native``: draws, sample structs, job structs
+and launches in the library, csrc/step.cu) and its numpy fallback (``run_base_batch``).
 
 ``SynthEngine.run_base`` fills one ctypes job struct per sample and stage, field by field (~250 attribute
 stores and as many small conversions per step of 8 samples: 0.9 ms of Python).  Here the same job arrays are
@@ -23,7 +24,7 @@ import torch
 
 from . import _lib
 from .engine import STAGE_BIAS, STAGE_FIELD, STAGE_GMM, STAGE_NOISE, _PAIRS, _stream
-from .tables import gaussian_taps_np, resample_size
+from .tables import gaussian_taps_np
 
 _U64 = np.uint64
 
