@@ -27,6 +27,9 @@
 namespace fsg {
 
 constexpr int SEP_THREADS = 128;
+#ifndef FSG_SEP_MINBLOCKS
+#define FSG_SEP_MINBLOCKS 5
+#endif
 constexpr int SEPZ_THREADS = 256;
 constexpr int SEPZ_ROWS = 32;
 
@@ -85,7 +88,7 @@ __device__ __forceinline__ float noise_apply(float v, float std, float n) {
 // Output I is emitted when its last source plane has been loaded; its weights are stored
 // right-aligned in a W-wide row, so the tap loop is W FMAs on statically indexed registers.
 template <int W, int VEC>
-__global__ void __launch_bounds__(SEP_THREADS) sep_stream_kernel(const __grid_constant__ SepPass p, int a_in, int inner) {
+__global__ void __launch_bounds__(SEP_THREADS, FSG_SEP_MINBLOCKS) sep_stream_kernel(const __grid_constant__ SepPass p, int a_in, int inner) {
   using V = VecT<VEC>;
   using T = typename V::T;
   const int jb = blockIdx.y;
@@ -221,6 +224,10 @@ __global__ void __launch_bounds__(SEPZ_THREADS) sep_z_kernel(const __grid_consta
 // r02 ncu of sep_z_kernel at these extents: bound by shared-memory wavefronts (W loads per output, 2-way bank
 // conflicts at stride 1/f); here a row costs 2 + 16 shared-memory instructions per lane instead of 16 per output.
 constexpr int ZR_THREADS = 256;
+#ifndef FSG_ZR_MINBLOCKS
+#define FSG_ZR_MINBLOCKS 3
+#endif
+
 constexpr int ZR_R = 6;      // blur radius held in registers (13 taps)
 constexpr int ZR_ROW = 256;  // row / coarse row limit (8 samples per lane)
 struct SepZRow {
@@ -248,7 +255,7 @@ __device__ __forceinline__ void zr_load_row(const float* __restrict__ src, int r
 }
 
 template <bool INJECT>
-__global__ void __launch_bounds__(ZR_THREADS, 3) sep_zrow_kernel(const __grid_constant__ SepZRow p, const __grid_constant__ SepNoise nz, int sz) {
+__global__ void __launch_bounds__(ZR_THREADS, FSG_ZR_MINBLOCKS) sep_zrow_kernel(const __grid_constant__ SepZRow p, const __grid_constant__ SepNoise nz, int sz) {
   const int jb = blockIdx.y;
   const int n2 = p.n_out[jb], rows = p.rows[jb];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
