@@ -32,6 +32,7 @@ struct Config {
   bool adj_lean;          // FSG_ADJ_LEAN=0: reference operation order in the PSF reconstruction
   bool adj_thread;        // FSG_ADJ_THREAD=1: thread-per-pixel PSF reconstruction
   int tile_debug;         // FSG_TILE_DEBUG
+  bool sep_xy;            // FSG_SEP_XY=1: x and y passes of fsg_sepconv fused in one kernel (sep_xy_kernel)
 };
 const Config& config();
 

@@ -28,6 +28,7 @@ static Config read_config() {
   c.adj_lean = flag("FSG_ADJ_LEAN", true);
   c.adj_thread = flag("FSG_ADJ_THREAD", false);
   c.tile_debug = num("FSG_TILE_DEBUG", 0);
+  c.sep_xy = num("FSG_SEP_XY", 0) != 0;
   return c;
 }
 static const Config g_config = read_config();  // static initialiser: runs at dlopen

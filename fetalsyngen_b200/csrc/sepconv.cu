@@ -22,6 +22,9 @@
 // z blur at full resolution costs ~27 instructions per voxel against ~10 for the streaming x pass, which already
 // runs at 5.2 TB/s of its own traffic.  Cheap-first (x, y streaming) and the instruction-heavy axis last wins.
 // Float image path: FMA accumulation, parity is the 1e-4 tolerance (tests/test_gpu_base.py).
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace fsg {
@@ -139,6 +142,138 @@ __global__ void __launch_bounds__(SEP_THREADS, FSG_SEP_MINBLOCKS) sep_stream_ker
           next_last = I < n_out ? s_last[I] : -1;
         }
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fused x + y
+// The x and y passes in ONE kernel (r02): the x-pass result (4 f N bytes written and read back) never exists.
+// A WARP owns a 32-float z chunk, a tile of XY_TJ outputs along y and a segment of the x outputs, and walks the
+// source planes of the segment once:
+//   per plane q: the y pass of the tile's rows with the rotating register window of sep_stream_kernel (lane = z,
+//     one coalesced 128-byte load per row), each emitted y output stored in slot q mod 16 of a per-warp ring in
+//     shared memory [16 planes][XY_TJ][32];
+//   when q completes the window of x output I: out[I][J][z] = sum_t wx[I][t] * ring[q - 15 + t][J][z] for the
+//     tile's J (weights right-aligned in 16 slots), one coalesced store per (I, J).
+// Warps never synchronise with each other; rows shared by neighbouring y tiles (the 13-row halo) are re-read
+// through L1 / L2.  Result = the same separable sum in the order y, x (x, y in the two-pass schedule): equal to
+// rounding.
+constexpr int XY_W = 16, XY_TJ = 8, XY_WARPS = 4;
+struct SepXY {
+  const float* src[FSG_MAX_JOBS];
+  float* dst[FSG_MAX_JOBS];
+  const int16_t* q0x[FSG_MAX_JOBS];
+  const float* wx[FSG_MAX_JOBS];
+  const int16_t* q0y[FSG_MAX_JOBS];
+  const float* wy[FSG_MAX_JOBS];
+  int n0[FSG_MAX_JOBS], n1[FSG_MAX_JOBS], widthx[FSG_MAX_JOBS], widthy[FSG_MAX_JOBS];
+};
+
+__global__ void __launch_bounds__(XY_WARPS * 32) sep_xy_kernel(const __grid_constant__ SepXY p, int sx, int sy, int sz, int xsegs, int seg_cap) {
+  const int jb = blockIdx.y;
+  const int n0 = p.n0[jb], n1 = p.n1[jb], widthx = p.widthx[jb], widthy = p.widthy[jb];
+  const int nzc = sz / 32, nyg = (n1 + XY_TJ * XY_WARPS - 1) / (XY_TJ * XY_WARPS);
+  int bid = blockIdx.x;
+  const int zc = bid % nzc;
+  bid /= nzc;
+  const int yg = bid % nyg, xs = bid / nyg;
+  if (xs >= xsegs) return;  // uniform per block: jobs with fewer y tiles than the largest
+  const int seg_len = (n0 + xsegs - 1) / xsegs;
+  const int Ia = xs * seg_len, Ib = min(n0, Ia + seg_len);
+  if (Ia >= Ib) return;
+
+  extern __shared__ __align__(16) float s_xy[];
+  float* s_ring = s_xy;                                                 // [XY_WARPS][16][XY_TJ][32]
+  float* s_wx = s_ring + XY_WARPS * XY_W * XY_TJ * 32;                  // [seg_cap][16] right-aligned
+  int* s_lastx = reinterpret_cast<int*>(s_wx + seg_cap * XY_W);         // [seg_cap]
+  float* s_wy = reinterpret_cast<float*>(s_lastx + seg_cap);            // [XY_TJ * XY_WARPS][16] right-aligned
+  int* s_lasty = reinterpret_cast<int*>(s_wy + XY_TJ * XY_WARPS * XY_W);  // [XY_TJ * XY_WARPS]
+  const int Jb0 = yg * XY_TJ * XY_WARPS;
+  for (int e = threadIdx.x; e < (Ib - Ia) * XY_W; e += XY_WARPS * 32) {
+    const int I = Ia + e / XY_W, t = e % XY_W - (XY_W - widthx);
+    s_wx[e] = t >= 0 ? p.wx[jb][I * widthx + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < Ib - Ia; i += XY_WARPS * 32) s_lastx[i] = (int)p.q0x[jb][Ia + i] + widthx - 1;
+  for (int e = threadIdx.x; e < XY_TJ * XY_WARPS * XY_W; e += XY_WARPS * 32) {
+    const int J = Jb0 + e / XY_W, t = e % XY_W - (XY_W - widthy);
+    s_wy[e] = (J < n1 && t >= 0) ? p.wy[jb][J * widthy + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < XY_TJ * XY_WARPS; i += XY_WARPS * 32) s_lasty[i] = Jb0 + i < n1 ? (int)p.q0y[jb][Jb0 + i] + widthy - 1 : -1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = s_ring + warp * (XY_W * XY_TJ * 32) + lane;
+#pragma unroll 4
+  for (int e = 0; e < XY_W * XY_TJ; ++e) ring[e * 32] = 0.f;
+  __syncthreads();
+
+  const int Jl0 = warp * XY_TJ, J0 = Jb0 + Jl0;
+  if (J0 >= n1) return;
+  const int nJ = min(XY_TJ, n1 - J0);
+  const int r_lo = (int)p.q0y[jb][J0], r_hi = s_lasty[Jl0 + nJ - 1];
+  const int qa = (int)p.q0x[jb][Ia], qb = s_lastx[Ib - Ia - 1];
+  const float* __restrict__ src = p.src[jb] + (size_t)zc * 32 + lane;
+  float* __restrict__ dst = p.dst[jb] + (size_t)zc * 32 + lane;
+  const size_t plane = (size_t)sy * sz;
+
+  int Il = 0;  // x output index within the segment
+  int next_last_x = s_lastx[0];
+  for (int q = qa; q <= qb; ++q) {
+    const float* __restrict__ in = src + (size_t)q * plane;
+    float* const slot = ring + (q & (XY_W - 1)) * (XY_TJ * 32);
+    // ---- y pass of the tile's rows of plane q
+    float win[XY_W];
+#pragma unroll
+    for (int u = 0; u < XY_W; ++u) win[u] = 0.f;
+    int Jl = 0;
+    int next_last = s_lasty[Jl0];
+    for (int rb = r_lo; rb <= r_hi; rb += XY_W) {
+      float cur[XY_W];
+#pragma unroll
+      for (int u = 0; u < XY_W; ++u) cur[u] = (rb + u <= r_hi) ? __ldcs(in + (size_t)(rb + u) * sz) : 0.f;
+#pragma unroll
+      for (int u = 0; u < XY_W; ++u) {
+        win[u] = cur[u];
+        const int r = rb + u;
+        while (next_last == r) {
+          const float4* wr = reinterpret_cast<const float4*>(s_wy + (Jl0 + Jl) * XY_W);
+          float acc = 0.f;
+#pragma unroll
+          for (int t4 = 0; t4 < XY_W / 4; ++t4) {
+            const float4 w4 = wr[t4];
+            acc = __fmaf_rn(w4.x, win[(u + 1 + 4 * t4 + 0) % XY_W], acc);
+            acc = __fmaf_rn(w4.y, win[(u + 1 + 4 * t4 + 1) % XY_W], acc);
+            acc = __fmaf_rn(w4.z, win[(u + 1 + 4 * t4 + 2) % XY_W], acc);
+            acc = __fmaf_rn(w4.w, win[(u + 1 + 4 * t4 + 3) % XY_W], acc);
+          }
+          slot[Jl * 32] = acc;
+          ++Jl;
+          next_last = Jl < nJ ? s_lasty[Jl0 + Jl] : -1;
+        }
+      }
+    }
+    // ---- x outputs completed by plane q
+    while (next_last_x == q) {
+      const float4* wr = reinterpret_cast<const float4*>(s_wx + Il * XY_W);
+      float wxr[XY_W];
+#pragma unroll
+      for (int t4 = 0; t4 < XY_W / 4; ++t4) {
+        const float4 w4 = wr[t4];
+        wxr[4 * t4] = w4.x, wxr[4 * t4 + 1] = w4.y, wxr[4 * t4 + 2] = w4.z, wxr[4 * t4 + 3] = w4.w;
+      }
+      float acc[XY_TJ];
+#pragma unroll
+      for (int j = 0; j < XY_TJ; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int e = 0; e < XY_W; ++e) {
+        const float* rp = ring + ((q + 1 + e) & (XY_W - 1)) * (XY_TJ * 32);
+#pragma unroll
+        for (int j = 0; j < XY_TJ; ++j) acc[j] = __fmaf_rn(wxr[e], rp[j * 32], acc[j]);
+      }
+      float* out = dst + ((size_t)(Ia + Il) * n1 + J0) * sz;
+#pragma unroll
+      for (int j = 0; j < XY_TJ; ++j)
+        if (j < nJ) out[(size_t)j * sz] = acc[j];
+      ++Il;
+      next_last_x = Ia + Il < Ib ? s_lastx[Il] : -1;
     }
   }
 }
@@ -526,7 +661,49 @@ extern "C" int fsg_sepconv(const fsg_sepconv_job* jobs, int njobs, int sx, int s
   SepNoise none;
   memset(&none, 0, sizeof(none));
 
-  for (int a = 0; a < 3; ++a) {
+  // ---- x and y passes fused (sep_xy_kernel) when every window fits 16 slots and a row is a whole number of 32-float chunks
+  int first_axis = 0;
+  {
+    bool fuse = config().sep_xy && sz % 32 == 0;
+    int max_n0 = 1, max_n1 = 1;
+    for (int i = 0; i < njobs && fuse; ++i) {
+      const fsg_sepconv_job& j = jobs[i];
+      fuse = j.ax[0].width <= XY_W && j.ax[1].width <= XY_W;
+      max_n0 = std::max(max_n0, j.ax[0].n_out);
+      max_n1 = std::max(max_n1, j.ax[1].n_out);
+    }
+    if (fuse) {
+      SepXY q;
+      memset(&q, 0, sizeof(q));
+      int64_t tiles = 0;
+      for (int i = 0; i < njobs; ++i) {
+        const fsg_sepconv_job& j = jobs[i];
+        q.src[i] = j.src, q.dst[i] = j.tmp2;
+        q.q0x[i] = j.ax[0].q0, q.wx[i] = j.ax[0].w, q.n0[i] = j.ax[0].n_out, q.widthx[i] = j.ax[0].width;
+        q.q0y[i] = j.ax[1].q0, q.wy[i] = j.ax[1].w, q.n1[i] = j.ax[1].n_out, q.widthy[i] = j.ax[1].width;
+        tiles += (int64_t)(sz / 32) * ((j.ax[1].n_out + XY_TJ * XY_WARPS - 1) / (XY_TJ * XY_WARPS));
+      }
+      // x segments: enough blocks for whole waves of 3 resident blocks per SM; every segment re-reads 15 planes
+      const int slots = 148 * 3;
+      int xsegs = 1;
+      double best = 1e30;
+      for (int c = 1; c <= 8 && c <= max_n0; ++c) {
+        const double waves = std::ceil((double)tiles * c / slots);
+        const double cost = waves * ((double)sx / c + (XY_W - 1));
+        if (cost < best) best = cost, xsegs = c;
+      }
+      const int seg_cap = ((max_n0 + xsegs - 1) / xsegs + 3) / 4 * 4;  // multiple of 4: keeps the tables behind it 16-byte aligned
+      const size_t smem = sizeof(float) * ((size_t)XY_WARPS * XY_W * XY_TJ * 32 + (size_t)seg_cap * (XY_W + 1) + (size_t)XY_TJ * XY_WARPS * (XY_W + 1));
+      if (smem <= 200 * 1024) {
+        const int nyg = (max_n1 + XY_TJ * XY_WARPS - 1) / (XY_TJ * XY_WARPS);
+        cudaFuncSetAttribute(sep_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sep_xy_kernel<<<dim3((unsigned)((sz / 32) * nyg * xsegs), njobs), XY_WARPS * 32, smem, s>>>(q, sx, sy, sz, xsegs, seg_cap);
+        first_axis = 2;
+      }
+    }
+  }
+
+  for (int a = first_axis; a < 3; ++a) {
     SepPass p;
     memset(&p, 0, sizeof(p));
     int maxw = 0, max_nout = 0, max_outer = 0;

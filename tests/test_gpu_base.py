@@ -360,6 +360,10 @@ def test_warp_kernel_variants_agree(monkeypatch):
         res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, FSG_WARP_PIPE="1", FSG_WARP_TILE="0", **extra), timeout=300)
         assert res.returncode == 0, res.stderr[-1500:]
         assert float(res.stdout.split("ERR")[1]) <= TOL
+    # the fused x + y kernel of the resolution simulation (opt-in: slower than the two streaming passes)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, FSG_SEP_XY="1"), timeout=300)
+    assert res.returncode == 0, res.stderr[-1500:]
+    assert float(res.stdout.split("ERR")[1]) <= TOL
     # the linear float32 hand-over (FSG_WARP_TEX=0; the default gathers from a block-linear texture volume)
     if os.environ.get("FSG_WARP_TEX", "1") != "0":
         assert eng.use_tex and eng.tex_eligible(plan)
