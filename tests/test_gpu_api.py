@@ -433,3 +433,27 @@ def test_batched_path_with_sr_artifacts_equals_the_per_sample_artifact_calls():
     one, _, _ = gen.sample_batch([seg_d], [seeds_d], scale=True, sample_ids=[6], base_seed=base, artifacts=True)
     diff = (one[0] - img[1]).abs()
     assert float(diff.max()) <= 1e-3 and float(diff.mean()) <= 1e-5, (float(diff.max()), float(diff.mean()))
+
+
+@pytest.mark.parametrize("shape,probs,B", [((64, 48, 80), 0.7, 16), ((96, 96, 96), 1.0, 5)])
+def test_native_step_equals_the_python_builders_on_the_device(shape, probs, B, monkeypatch):
+    """The batched path through the native step (fsg_draw_batch + fsg_step_fill + fsg_step_run), through the numpy job
+    builder and through the per-sample builder: the same launches, so the same volumes bit for bit — with per-sample
+    gates (probabilities < 1), a non-cubic shape and a full batch of FSG_MAX_JOBS samples (label volumes as seeds; the
+    packed-seed route is compared the same way in test_packed_only_dataset_and_dataset_pipeline_on_the_bundled_subjects)."""
+    import fetalsyngen_b200.generator.model as M
+    gen = _gen(shape, probs=probs)
+    seg_h, seeds_h = label_phantom(shape)
+    seg_d = torch.from_numpy(seg_h).to(DEV)
+    vols = [torch.from_numpy(s).to(DEV) for s in seeds_h]
+    ids = list(range(40, 40 + B))
+    outs = []
+    for native, fast in ((True, True), (False, True), (False, False)):
+        monkeypatch.setattr(M, "_NATIVE_STEP", native)
+        monkeypatch.setattr(M, "_FAST_STEP", fast)
+        img, seg, params = gen.sample_batch([seg_d] * B, [vols] * B, scale=True, sample_ids=ids, base_seed=8)
+        outs.append((img.clone(), seg.clone(), [params[b]["resample_params"]["spacing"] for b in range(B)]))
+    for k in (1, 2):
+        assert torch.equal(outs[0][0], outs[k][0]) and torch.equal(outs[0][1], outs[k][1]) and outs[0][2] == outs[k][2], k
+    if probs < 1:
+        assert any(s is None for s in outs[0][2]) and any(s is not None for s in outs[0][2])  # both kinds of sample in the batch
