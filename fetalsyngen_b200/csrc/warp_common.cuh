@@ -5,7 +5,13 @@
 
 namespace fsg {
 
-constexpr int WX = 8, WY = 4;
+#ifndef FSG_WARP_WX
+#define FSG_WARP_WX 8
+#endif
+#ifndef FSG_WARP_WY
+#define FSG_WARP_WY 4
+#endif
+constexpr int WX = FSG_WARP_WX, WY = FSG_WARP_WY;  // tile of (x, y) rows a block stages the control grids for
 constexpr int WARP_THREADS = 256;
 constexpr int MAX_FZ = 32;  // control-grid extent along z kept in smem (reference: <= 0.06*S)
 constexpr int MAX_BZ = 16;  // bias-grid extent along z (reference: <= 0.02*S)
